@@ -1,0 +1,183 @@
+/*
+ * pygho_b200 -- C ABI of the B200 (sm_100a) kernels behind PygHO's pygho.backend layer.
+ *
+ * The reference (GraphPKU/PygHO) is pure Python on torch and has no FFI seam; the
+ * natural boundary is the pygho.backend function API.  Every
+ * entry point below replaces one ATen call chain of the reference; the citation after
+ * each declaration is the reference code it stands in for (paths relative to
+ * /root/reference/pygho).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless said
+ *     otherwise; `stream` is a cudaStream_t passed as void*.
+ *   - functions never allocate and never synchronise; outputs and workspaces are
+ *     provided by the caller (size queries: *_ws_bytes).  Data-dependent sizes are
+ *     written to device counters that the caller reads back once per batch.
+ *   - return value: 0 on success, >0 a cudaError_t, <0 an argument error;
+ *     pgh_last_error() returns a static, thread-local description.
+ *   - value tensors are row-major (rows, dense) float32; plan indices are int32;
+ *     API-level indices (LongTensor in the reference) are int64.
+ *   - aggr: 0 sum, 1 mean, 2 max, 3 min.  Rows that receive nothing are 0 for every
+ *     aggr (backend/utils.py:50-55: zero init + include_self=False).
+ */
+#ifndef PYGHO_B200_H
+#define PYGHO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGH_SUM 0
+#define PGH_MEAN 1
+#define PGH_MAX 2
+#define PGH_MIN 3
+
+const char* pgh_last_error(void);
+int pgh_abi_version(void);
+/* fills {device ordinal, SM count, L2 bytes, cc major, cc minor}; host pointer */
+int pgh_device_info(int32_t* out5);
+
+/* ------------------------------------------------------------------ value kernels */
+
+/* Fused gather - multiply - segmented reduce.
+ *   out[r,:] = aggr_{t in seg(r)} A(t) * B(t),  seg(r) = [rowptr[r], rowptr[r+1])  or {r} if rowptr==NULL
+ *   A(t) = a_val[ia(t),:] * (a_scale ? a_scale[ia(t)] : 1),  ia(t) = c ? c[t] : t
+ *   B(t) = b_val ? b_val[ib(t),:] : 1,                       ib(t) = d ? d[t] : t
+ * Deterministic (sequential in t), no atomics, one coalesced store per output row.
+ * Replaces gather+gather+mul+scatter_reduce_ of backend/Spspmm.py:314-315, Spmm.py:40-43,
+ * the scatter of SpTensor.py:388-394 (sparse pooling), the gather of SpTensor.py:476
+ * (unpooling) and every autograd replay of those (index_add_ / gather).            */
+int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float* a_scale,
+                    const float* b_val, const int32_t* d, const int32_t* rowptr,
+                    int64_t n_rows, int64_t dense, int aggr, float* out, void* stream);
+
+/* max/min backward, step 1: gscaled[r,:] = grad[r,:] / (#{t in seg(r): A(t)*B(t) == out[r,:]}
+ *                                                       + [out[r,:] == 0])
+ * (torch's scatter_reduce amax/amin backward splits the gradient evenly among ties and
+ * counts the zero-initialised output itself as one of them). */
+int pgh_seg_tie_scale_f32(const float* a_val, const int32_t* c, const float* b_val,
+                          const int32_t* d, const int32_t* rowptr, int64_t n_rows,
+                          int64_t dense, const float* out, const float* grad,
+                          float* gscaled, void* stream);
+
+/* max/min backward, step 2 (transposed plan, rows p of the operand being differentiated):
+ *   g_self[p,:] = sum_{t in seg(p)} [self[p,:]*O(t) == out[row(t),:]] * gscaled[row(t),:] * O(t)
+ *   O(t) = other_val ? other_val[io(t),:] : 1,  row(t) = row_idx ? row_idx[t] : t          */
+int pgh_seg_select_bwd_f32(const float* self_val, const float* other_val,
+                           const int32_t* other_idx, const int32_t* row_idx,
+                           const int32_t* rowptr, int64_t n_rows, int64_t dense,
+                           const float* out, const float* gscaled, float* g_self,
+                           void* stream);
+
+/* inv[r] = 1 / max(rowptr[r+1]-rowptr[r], 1)  (mean backward scale) */
+int pgh_inv_count_f32(const int32_t* rowptr, int64_t n_rows, float* inv, void* stream);
+
+/* Integer segmented reduce for coalescing integer tuple features
+ * (SpTupleSampler.py:126 coalesces distances with "min"); mean floors like torch. */
+int pgh_seg_reduce_i64(const int64_t* val, const int32_t* perm, const int32_t* rowptr,
+                       int64_t n_rows, int64_t dense, int aggr, int64_t* out, void* stream);
+
+/* ------------------------------------------------------------------- plan kernels */
+
+/* key[i] = pack of the listed rows of ind (row-major (sd, ld) int64), `bits` per field,
+ * first listed row most significant (backend/SpTensor.py:10-42 indicehash).
+ * info[0] += #negative entries, info[1] += #entries >= 2^bits.                          */
+int pgh_pack_keys(const int64_t* ind, int64_t ld, const int32_t* rows_host, int n_rows_sel,
+                  int bits, int64_t nnz, int64_t* key, int32_t* info, void* stream);
+/* out (sd, ld) int64 <- key  (backend/SpTensor.py:45-87 decodehash) */
+int pgh_unpack_keys(const int64_t* key, int64_t n, int sd, int bits, int64_t* out,
+                    int64_t ld, void* stream);
+/* mixed-radix flatten / unflatten (backend/SpTensor.py:90-164); dims on host */
+int pgh_pack_tight(const int64_t* ind, int64_t ld, const int32_t* rows_host,
+                   const int64_t* dims_host, int n_rows_sel, int64_t nnz, int64_t* key,
+                   int32_t* info, void* stream);
+int pgh_unpack_tight(const int64_t* key, int64_t n, const int64_t* dims_host, int sd,
+                     int64_t* out, int64_t ld, void* stream);
+
+/* stable LSD radix sort of (key, iota) pairs on bits [0, end_bit) (torch.argsort /
+ * the sort inside torch.unique, backend/Spspmm.py:102,135-142, SpTensor.py:190) */
+size_t pgh_sort_ws_bytes(int64_t n);
+int pgh_sort_keys_perm(const int64_t* key_in, int64_t n, int end_bit, int64_t* key_out,
+                       int32_t* perm_out, void* ws, size_t ws_bytes, void* stream);
+
+/* run-length unique of sorted keys: ukey[0..count), seg[i] = index of key[i]'s run,
+ * count written to *count_dev (torch.unique(sorted, return_inverse), Spspmm.py:135) */
+size_t pgh_unique_ws_bytes(int64_t n);
+int pgh_unique_sorted(const int64_t* key_sorted, int64_t n, int64_t* ukey, int32_t* seg,
+                      int32_t* count_dev, void* ws, size_t ws_bytes, void* stream);
+
+/* rowptr (n_rows+1) of a non-decreasing int32 key array with values in [0, n_rows) */
+int pgh_rowptr_from_sorted(const int32_t* key_sorted, int64_t n, int64_t n_rows,
+                           int32_t* rowptr, void* stream);
+
+/* For each query q: lo[q] = lower_bound(sorted, q), off = exclusive scan of match counts,
+ * off[m] = total (2x torch.searchsorted + cumsum, backend/Spspmm.py:114-126)            */
+size_t pgh_match_ws_bytes(int64_t m);
+int pgh_match_ranges(const int64_t* sorted_keys, int64_t n, const int64_t* queries, int64_t m,
+                     int32_t* lo, int64_t* off, void* ws, size_t ws_bytes, void* stream);
+/* expand the ranges: for t in [0,total): c[t] = q with off[q] <= t < off[q+1],
+ * d[t] = perm2[lo[c] + t - off[c]]   (repeat_interleave/arange, Spspmm.py:128-131)      */
+int pgh_expand_pairs(const int64_t* off, const int32_t* lo, const int32_t* perm2, int64_t m,
+                     int64_t total, int32_t* c, int32_t* d, void* stream);
+/* key[t] = pack(rest dims of ind1[:,c[t]], rest dims of ind2[:,d[t]])  (Spspmm.py:133-137) */
+int pgh_pair_keys(const int64_t* ind1, int64_t ld1, int sd1, int dim1, const int64_t* ind2,
+                  int64_t ld2, int sd2, int dim2, const int32_t* c, const int32_t* d,
+                  int64_t total, int bits, int64_t* key, int32_t* info, void* stream);
+
+/* pos[i] = index of keys[i] in sorted unique tkeys, -1 if absent
+ * (spsphadamard_ind, backend/Spspmm.py:174-183; SpTensor.unpooling :454-468)            */
+int pgh_lookup_sorted(const int64_t* tkeys, int64_t nt, const int64_t* keys, int64_t n,
+                      int32_t* pos, void* stream);
+
+/* order-preserving compaction of triples with a[t] >= 0; optional remap a = map[a] first
+ * (filterind, backend/Spspmm.py:218-222).  count -> *count_dev                            */
+size_t pgh_compact_ws_bytes(int64_t n);
+int pgh_compact_triples(const int32_t* a, const int32_t* map, const int32_t* c,
+                        const int32_t* d, int64_t n, int32_t* oa, int32_t* oc, int32_t* od,
+                        int32_t* count_dev, void* ws, size_t ws_bytes, void* stream);
+
+/* small conversions / gathers used while assembling plans */
+int pgh_i64_to_i32(const int64_t* src, int64_t n, int32_t* dst, int32_t* info, void* stream);
+int pgh_i32_to_i64(const int32_t* src, int64_t n, int64_t* dst, void* stream);
+int pgh_gather_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t* dst, void* stream);
+int pgh_gather_i64_as_i32(const int64_t* src, const int32_t* idx, int64_t n, int32_t* dst,
+                          void* stream);
+/* info[0] += number of descents key[i] > key[i+1] (0 <=> non-decreasing);
+ * with strict != 0 equal neighbours count as well (sorted AND duplicate free) */
+int pgh_check_sorted_i64(const int64_t* key, int64_t n, int strict, int32_t* info,
+                         void* stream);
+
+/* --------------------------------------------------------------------- masked path */
+
+/* 2-FWL contraction of (b, n, n, dense) fp32 tensors (backend/Mamamm.py:7-64):
+ *   out[b,i,k,:] = mask[b,i,k] ? sum_j A'[b,i,j,:] * B'[b,j,k,:] : 0
+ *   A' = A if !trans_a else A with dims 1,2 swapped (dim1==1); same for B (dim2==2).
+ * Operand pads must already be zero (MaskedTensor keeps pads at padvalue 0).
+ * algo 0 = CUDA-core tiled kernel (exact fp32), 1 = tcgen05 TF32 tensor-core kernel.   */
+int pgh_mamamm_f32(const float* A, int trans_a, const float* B, int trans_b,
+                   const uint8_t* mask, int64_t b, int64_t n_i, int64_t n_j, int64_t n_k,
+                   int64_t dense, int algo, float* out, void* stream);
+
+/* masked pooling of (b, n1, n2, dense) over dim 1, dim 2 or both (backend/MaTensor.py:175-206)
+ *   red_dims: 1 -> over n1 (out (b,n2,dense)), 2 -> over n2 (out (b,n1,dense)), 3 -> both (out (b,dense))
+ * out_mask (uint8) = any(mask) over the reduced dims.  max/min of no valid entry -> 0.   */
+int pgh_masked_pool_f32(const float* data, const uint8_t* mask, int64_t b, int64_t n1,
+                        int64_t n2, int64_t dense, int red_dims, int aggr, float* out,
+                        uint8_t* out_mask, void* stream);
+/* its backward: g_data = mask ? w * g_out[broadcast] : 0 with w = 1 (sum), 1/count (mean),
+ * [data == out]/ties (max/min)                                                          */
+int pgh_masked_pool_bwd_f32(const float* data, const uint8_t* mask, const float* out,
+                            const float* g_out, int64_t b, int64_t n1, int64_t n2,
+                            int64_t dense, int red_dims, int aggr, float* g_data,
+                            void* stream);
+/* out = mask ? data : value  (MaskedTensor.fill_masked, backend/MaTensor.py:113-128) */
+int pgh_masked_fill_f32(const float* data, const uint8_t* mask, int64_t rows, int64_t dense,
+                        float value, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYGHO_B200_H */

@@ -1,0 +1,505 @@
+// Device-side index-plan builders (integer work, HBM/latency bound, cub for sort/scan).
+//
+// The reference builds its plans with torch.argsort / searchsorted / cumsum /
+// repeat_interleave / unique (backend/Spspmm.py:57-222, SpTensor.py:167-197), each a
+// separate ATen launch with host synchronisation in between.  Here every stage is a
+// stream-ordered kernel; data-dependent sizes land in device counters that the host
+// reads once.  All orders are canonical (stable sorts), so plans are deterministic.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace pgh {
+
+constexpr int kT = 256;
+
+struct RowSel {
+  int n;
+  int rows[8];
+  long long dims[8];
+};
+
+__global__ void pack_keys_kernel(const long long* __restrict__ ind, long long ld, RowSel sel,
+                                 int bits, long long nnz, long long* __restrict__ key,
+                                 int* __restrict__ info) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  long long k = 0;
+  int neg = 0, big = 0;
+  for (int r = 0; r < sel.n; ++r) {
+    const long long v = ind[(long long)sel.rows[r] * ld + i];
+    neg |= v < 0;
+    big |= (sel.n > 1) && (v >> bits) != 0;
+    k = (sel.n > 1) ? ((k << bits) | v) : v;
+  }
+  key[i] = k;
+  if (info) {
+    if (neg) atomicAdd(info + 0, 1);
+    if (big && !neg) atomicAdd(info + 1, 1);
+  }
+}
+
+__global__ void pack_tight_kernel(const long long* __restrict__ ind, long long ld, RowSel sel,
+                                  long long nnz, long long* __restrict__ key,
+                                  int* __restrict__ info) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  long long k = 0;
+  int bad = 0;
+  for (int r = 0; r < sel.n; ++r) {
+    const long long v = ind[(long long)sel.rows[r] * ld + i];
+    bad |= (v < 0) || (v >= sel.dims[r]);
+    k = k * sel.dims[r] + v;
+  }
+  key[i] = k;
+  if (info && bad) atomicAdd(info + 0, 1);
+}
+
+__global__ void unpack_keys_kernel(const long long* __restrict__ key, long long n, int sd,
+                                   int bits, long long* __restrict__ out, long long ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long k = key[i];
+  if (sd == 1) {
+    out[i] = k;
+    return;
+  }
+  const long long field = (1ll << bits) - 1;
+  for (int r = 0; r < sd; ++r) out[(long long)r * ld + i] = (k >> (bits * (sd - 1 - r))) & field;
+}
+
+__global__ void unpack_tight_kernel(const long long* __restrict__ key, long long n, RowSel sel,
+                                    long long* __restrict__ out, long long ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long k = key[i];
+  for (int r = sel.n - 1; r >= 0; --r) {
+    const long long s = sel.dims[r];
+    out[(long long)r * ld + i] = (r == 0) ? k : k % s;
+    k /= s;
+  }
+}
+
+__global__ void iota_kernel(int* __restrict__ p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int)i;
+}
+
+__global__ void head_flags_kernel(const long long* __restrict__ key, long long n,
+                                  int* __restrict__ flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+}
+
+// seg (inclusive scan of head flags, in place) -> seg-1; heads write their key; last writes count
+__global__ void unique_finish_kernel(const long long* __restrict__ key, long long n,
+                                     int* __restrict__ seg, long long* __restrict__ ukey,
+                                     int* __restrict__ count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = seg[i] - 1;
+  seg[i] = s;
+  if (i == 0 || key[i] != key[i - 1]) ukey[s] = key[i];
+  if (i == n - 1) *count = s + 1;
+}
+
+// rowptr[r] = first position whose key >= r ; one thread per position boundary
+__global__ void rowptr_kernel(const int* __restrict__ key, long long n, long long n_rows,
+                              int* __restrict__ rowptr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const long long prev = (i == 0) ? -1 : (long long)key[i - 1];
+  const long long cur = (i == n) ? n_rows : (long long)key[i];
+  for (long long r = prev + 1; r <= cur && r <= n_rows; ++r) rowptr[r] = (int)i;
+}
+
+__device__ __forceinline__ long long lower_bound_ll(const long long* __restrict__ a, long long n,
+                                                    long long q) {
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (a[mid] < q) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ long long upper_bound_ll(const long long* __restrict__ a, long long n,
+                                                    long long q) {
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (a[mid] <= q) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void match_kernel(const long long* __restrict__ sorted, long long n,
+                             const long long* __restrict__ q, long long m,
+                             int* __restrict__ lo, long long* __restrict__ cnt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const long long l = lower_bound_ll(sorted, n, q[i]);
+  const long long u = upper_bound_ll(sorted, n, q[i]);
+  lo[i] = (int)l;
+  cnt[i] = u - l;
+}
+
+__global__ void set_last_kernel(const long long* __restrict__ excl, const long long* __restrict__ cnt,
+                                long long m, long long* __restrict__ off) {
+  // off[0..m) already holds the exclusive scan; write the total
+  if (threadIdx.x == 0 && blockIdx.x == 0) off[m] = (m > 0) ? excl[m - 1] + cnt[m - 1] : 0;
+}
+
+__global__ void expand_kernel(const long long* __restrict__ off, const int* __restrict__ lo,
+                              const int* __restrict__ perm2, long long m, long long total,
+                              int* __restrict__ c, int* __restrict__ d) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const long long q = upper_bound_ll(off, m + 1, t) - 1;
+  const long long j = (long long)lo[q] + (t - off[q]);
+  c[t] = (int)q;
+  d[t] = perm2 ? perm2[j] : (int)j;
+}
+
+struct PairSel {
+  int n1, n2;
+  int rows1[8], rows2[8];
+};
+
+__global__ void pair_keys_kernel(const long long* __restrict__ ind1, long long ld1,
+                                 const long long* __restrict__ ind2, long long ld2, PairSel sel,
+                                 const int* __restrict__ c, const int* __restrict__ d,
+                                 long long total, int bits, long long* __restrict__ key,
+                                 int* __restrict__ info) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const long long p = c[t], q = d[t];
+  long long k = 0;
+  int big = 0;
+  const bool single = (sel.n1 + sel.n2) == 1;
+  for (int r = 0; r < sel.n1; ++r) {
+    const long long v = ind1[(long long)sel.rows1[r] * ld1 + p];
+    big |= !single && (v >> bits) != 0;
+    k = single ? v : ((k << bits) | v);
+  }
+  for (int r = 0; r < sel.n2; ++r) {
+    const long long v = ind2[(long long)sel.rows2[r] * ld2 + q];
+    big |= !single && (v >> bits) != 0;
+    k = single ? v : ((k << bits) | v);
+  }
+  key[t] = k;
+  if (info && big) atomicAdd(info + 1, 1);
+}
+
+__global__ void lookup_kernel(const long long* __restrict__ tkeys, long long nt,
+                              const long long* __restrict__ keys, long long n,
+                              int* __restrict__ pos) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long k = keys[i];
+  const long long l = lower_bound_ll(tkeys, nt, k);
+  pos[i] = (l < nt && tkeys[l] == k) ? (int)l : -1;
+}
+
+__global__ void keep_flags_kernel(const int* __restrict__ a, const int* __restrict__ map,
+                                  long long n, int* __restrict__ a_mapped,
+                                  int* __restrict__ flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int v = a[i];
+  if (map && v >= 0) v = map[v];
+  a_mapped[i] = v;
+  flag[i] = v >= 0 ? 1 : 0;
+}
+
+__global__ void compact_scatter_kernel(const int* __restrict__ a_mapped,
+                                       const int* __restrict__ c, const int* __restrict__ d,
+                                       const int* __restrict__ excl, long long n,
+                                       int* __restrict__ oa, int* __restrict__ oc,
+                                       int* __restrict__ od, int* __restrict__ count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = a_mapped[i];
+  const int o = excl[i];
+  if (v >= 0) {
+    oa[o] = v;
+    oc[o] = c[i];
+    od[o] = d[i];
+  }
+  if (i == n - 1) *count = o + (v >= 0 ? 1 : 0);
+}
+
+__global__ void i64_to_i32_kernel(const long long* __restrict__ s, long long n,
+                                  int* __restrict__ dst, int* __restrict__ info) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long v = s[i];
+  dst[i] = (int)v;
+  if (info && (v < 0 || v > 0x7fffffffll)) atomicAdd(info + 0, 1);
+}
+
+__global__ void i32_to_i64_kernel(const int* __restrict__ s, long long n,
+                                  long long* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = s[i];
+}
+
+__global__ void gather_i32_kernel(const int* __restrict__ s, const int* __restrict__ idx,
+                                  long long n, int* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = s[idx[i]];
+}
+
+__global__ void gather_i64_i32_kernel(const long long* __restrict__ s,
+                                      const int* __restrict__ idx, long long n,
+                                      int* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (int)s[idx[i]];
+}
+
+__global__ void check_sorted_kernel(const long long* __restrict__ key, long long n, int strict,
+                                    int* __restrict__ info) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 < n && (key[i] > key[i + 1] || (strict && key[i] == key[i + 1])))
+    atomicAdd(info + 0, 1);
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace pgh
+
+using namespace pgh;
+
+static int fill_rowsel(RowSel& s, const int32_t* rows, const int64_t* dims, int n) {
+  if (n < 1 || n > 8) return arg_error("1..8 index rows supported");
+  s.n = n;
+  for (int i = 0; i < n; ++i) {
+    s.rows[i] = rows[i];
+    s.dims[i] = dims ? dims[i] : 0;
+  }
+  return 0;
+}
+
+extern "C" int pgh_pack_keys(const int64_t* ind, int64_t ld, const int32_t* rows_host,
+                             int n_rows_sel, int bits, int64_t nnz, int64_t* key, int32_t* info,
+                             void* stream) {
+  RowSel s;
+  if (int e = fill_rowsel(s, rows_host, nullptr, n_rows_sel)) return e;
+  if (n_rows_sel > 1 && (bits < 1 || bits * n_rows_sel > 63)) return arg_error("pack_keys: bits");
+  if (nnz <= 0) return 0;
+  pack_keys_kernel<<<blocks_for(nnz, kT), kT, 0, as_stream(stream)>>>(
+      (const long long*)ind, ld, s, bits, nnz, (long long*)key, info);
+  return check_launch("pack_keys");
+}
+
+extern "C" int pgh_pack_tight(const int64_t* ind, int64_t ld, const int32_t* rows_host,
+                              const int64_t* dims_host, int n_rows_sel, int64_t nnz, int64_t* key,
+                              int32_t* info, void* stream) {
+  RowSel s;
+  if (int e = fill_rowsel(s, rows_host, dims_host, n_rows_sel)) return e;
+  if (nnz <= 0) return 0;
+  pack_tight_kernel<<<blocks_for(nnz, kT), kT, 0, as_stream(stream)>>>(
+      (const long long*)ind, ld, s, nnz, (long long*)key, info);
+  return check_launch("pack_tight");
+}
+
+extern "C" int pgh_unpack_keys(const int64_t* key, int64_t n, int sd, int bits, int64_t* out,
+                               int64_t ld, void* stream) {
+  if (sd < 1 || sd > 8) return arg_error("unpack_keys: sd");
+  if (n <= 0) return 0;
+  unpack_keys_kernel<<<blocks_for(n, kT), kT, 0, as_stream(stream)>>>(
+      (const long long*)key, n, sd, bits, (long long*)out, ld);
+  return check_launch("unpack_keys");
+}
+
+extern "C" size_t pgh_sort_ws_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const unsigned long long*)nullptr,
+                                  (unsigned long long*)nullptr, (const int*)nullptr,
+                                  (int*)nullptr, (int)n, 0, 64);
+  return align_up(tmp) + align_up(sizeof(int) * (size_t)n);
+}
+
+extern "C" int pgh_sort_keys_perm(const int64_t* key_in, int64_t n, int end_bit, int64_t* key_out,
+                                  int32_t* perm_out, void* ws, size_t ws_bytes, void* stream) {
+  if (n <= 0) return 0;
+  if (n > 0x7fffffff) return arg_error("sort: n too large");
+  if (end_bit < 1) end_bit = 1;
+  if (end_bit > 64) end_bit = 64;
+  cudaStream_t s = as_stream(stream);
+  const size_t iota_bytes = align_up(sizeof(int) * (size_t)n);
+  if (ws_bytes < iota_bytes + 256) return arg_error("sort: workspace too small");
+  int* iota = reinterpret_cast<int*>(ws);
+  void* tmp = reinterpret_cast<char*>(ws) + iota_bytes;
+  size_t tmp_bytes = ws_bytes - iota_bytes;
+  iota_kernel<<<blocks_for(n, kT), kT, 0, s>>>(iota, n);
+  PGH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const unsigned long long*)key_in,
+                                           (unsigned long long*)key_out, (const int*)iota,
+                                           (int*)perm_out, (int)n, 0, end_bit, s));
+  return check_launch("sort_keys_perm");
+}
+
+extern "C" size_t pgh_unique_ws_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  size_t tmp = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, tmp, (const int*)nullptr, (int*)nullptr, (int)n);
+  return align_up(tmp);
+}
+
+extern "C" int pgh_unique_sorted(const int64_t* key_sorted, int64_t n, int64_t* ukey, int32_t* seg,
+                                 int32_t* count_dev, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t s = as_stream(stream);
+  if (n <= 0) {
+    PGH_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(int), s));
+    return 0;
+  }
+  head_flags_kernel<<<blocks_for(n, kT), kT, 0, s>>>((const long long*)key_sorted, n, seg);
+  size_t tmp = ws_bytes;
+  PGH_CUDA(cub::DeviceScan::InclusiveSum(ws, tmp, (const int*)seg, (int*)seg, (int)n, s));
+  unique_finish_kernel<<<blocks_for(n, kT), kT, 0, s>>>((const long long*)key_sorted, n, seg,
+                                                        (long long*)ukey, count_dev);
+  return check_launch("unique_sorted");
+}
+
+extern "C" int pgh_rowptr_from_sorted(const int32_t* key_sorted, int64_t n, int64_t n_rows,
+                                      int32_t* rowptr, void* stream) {
+  if (n_rows < 0 || n < 0) return arg_error("rowptr: sizes");
+  rowptr_kernel<<<blocks_for(n + 1, kT), kT, 0, as_stream(stream)>>>(key_sorted, n, n_rows, rowptr);
+  return check_launch("rowptr_from_sorted");
+}
+
+extern "C" size_t pgh_match_ws_bytes(int64_t m) {
+  if (m <= 0) return 256;
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const long long*)nullptr, (long long*)nullptr, (int)m);
+  return align_up(tmp) + align_up(sizeof(long long) * (size_t)m);
+}
+
+extern "C" int pgh_match_ranges(const int64_t* sorted_keys, int64_t n, const int64_t* queries,
+                                int64_t m, int32_t* lo, int64_t* off, void* ws, size_t ws_bytes,
+                                void* stream) {
+  cudaStream_t s = as_stream(stream);
+  if (m <= 0) {
+    PGH_CUDA(cudaMemsetAsync(off, 0, sizeof(int64_t), s));
+    return 0;
+  }
+  const size_t cnt_bytes = align_up(sizeof(long long) * (size_t)m);
+  if (ws_bytes < cnt_bytes + 256) return arg_error("match: workspace too small");
+  long long* cnt = reinterpret_cast<long long*>(ws);
+  void* tmp = reinterpret_cast<char*>(ws) + cnt_bytes;
+  size_t tmp_bytes = ws_bytes - cnt_bytes;
+  match_kernel<<<blocks_for(m, kT), kT, 0, s>>>((const long long*)sorted_keys, n,
+                                               (const long long*)queries, m, lo, cnt);
+  PGH_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const long long*)cnt, (long long*)off,
+                                         (int)m, s));
+  set_last_kernel<<<1, 32, 0, s>>>((const long long*)off, cnt, m, (long long*)off);
+  return check_launch("match_ranges");
+}
+
+extern "C" int pgh_expand_pairs(const int64_t* off, const int32_t* lo, const int32_t* perm2,
+                                int64_t m, int64_t total, int32_t* c, int32_t* d, void* stream) {
+  if (total <= 0) return 0;
+  expand_kernel<<<blocks_for(total, kT), kT, 0, as_stream(stream)>>>((const long long*)off, lo,
+                                                                     perm2, m, total, c, d);
+  return check_launch("expand_pairs");
+}
+
+extern "C" int pgh_pair_keys(const int64_t* ind1, int64_t ld1, int sd1, int dim1,
+                             const int64_t* ind2, int64_t ld2, int sd2, int dim2, const int32_t* c,
+                             const int32_t* d, int64_t total, int bits, int64_t* key, int32_t* info,
+                             void* stream) {
+  if (sd1 < 1 || sd2 < 1 || sd1 + sd2 - 2 > 8 || sd1 + sd2 - 2 < 1)
+    return arg_error("pair_keys: sparse dims");
+  PairSel sel;
+  sel.n1 = sel.n2 = 0;
+  for (int r = 0; r < sd1; ++r) if (r != dim1) sel.rows1[sel.n1++] = r;
+  for (int r = 0; r < sd2; ++r) if (r != dim2) sel.rows2[sel.n2++] = r;
+  if (total <= 0) return 0;
+  pair_keys_kernel<<<blocks_for(total, kT), kT, 0, as_stream(stream)>>>(
+      (const long long*)ind1, ld1, (const long long*)ind2, ld2, sel, c, d, total, bits,
+      (long long*)key, info);
+  return check_launch("pair_keys");
+}
+
+extern "C" int pgh_lookup_sorted(const int64_t* tkeys, int64_t nt, const int64_t* keys, int64_t n,
+                                 int32_t* pos, void* stream) {
+  if (n <= 0) return 0;
+  lookup_kernel<<<blocks_for(n, kT), kT, 0, as_stream(stream)>>>((const long long*)tkeys, nt,
+                                                                 (const long long*)keys, n, pos);
+  return check_launch("lookup_sorted");
+}
+
+extern "C" size_t pgh_compact_ws_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int*)nullptr, (int*)nullptr, (int)n);
+  return align_up(tmp) + 2 * align_up(sizeof(int) * (size_t)n);
+}
+
+extern "C" int pgh_compact_triples(const int32_t* a, const int32_t* map, const int32_t* c,
+                                   const int32_t* d, int64_t n, int32_t* oa, int32_t* oc,
+                                   int32_t* od, int32_t* count_dev, void* ws, size_t ws_bytes,
+                                   void* stream) {
+  cudaStream_t s = as_stream(stream);
+  if (n <= 0) {
+    PGH_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(int), s));
+    return 0;
+  }
+  const size_t arr = align_up(sizeof(int) * (size_t)n);
+  if (ws_bytes < 2 * arr + 256) return arg_error("compact: workspace too small");
+  int* a_mapped = reinterpret_cast<int*>(ws);
+  int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + arr);
+  void* tmp = reinterpret_cast<char*>(ws) + 2 * arr;
+  size_t tmp_bytes = ws_bytes - 2 * arr;
+  keep_flags_kernel<<<blocks_for(n, kT), kT, 0, s>>>(a, map, n, a_mapped, flag);
+  PGH_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const int*)flag, flag, (int)n, s));
+  compact_scatter_kernel<<<blocks_for(n, kT), kT, 0, s>>>(a_mapped, c, d, flag, n, oa, oc, od,
+                                                          count_dev);
+  return check_launch("compact_triples");
+}
+
+extern "C" int pgh_i64_to_i32(const int64_t* src, int64_t n, int32_t* dst, int32_t* info,
+                              void* stream) {
+  if (n <= 0) return 0;
+  i64_to_i32_kernel<<<blocks_for(n, kT), kT, 0, as_stream(stream)>>>((const long long*)src, n, dst, info);
+  return check_launch("i64_to_i32");
+}
+
+extern "C" int pgh_i32_to_i64(const int32_t* src, int64_t n, int64_t* dst, void* stream) {
+  if (n <= 0) return 0;
+  i32_to_i64_kernel<<<blocks_for(n, kT), kT, 0, as_stream(stream)>>>(src, n, (long long*)dst);
+  return check_launch("i32_to_i64");
+}
+
+extern "C" int pgh_gather_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t* dst,
+                              void* stream) {
+  if (n <= 0) return 0;
+  gather_i32_kernel<<<blocks_for(n, kT), kT, 0, as_stream(stream)>>>(src, idx, n, dst);
+  return check_launch("gather_i32");
+}
+
+extern "C" int pgh_gather_i64_as_i32(const int64_t* src, const int32_t* idx, int64_t n,
+                                     int32_t* dst, void* stream) {
+  if (n <= 0) return 0;
+  gather_i64_i32_kernel<<<blocks_for(n, kT), kT, 0, as_stream(stream)>>>((const long long*)src, idx, n, dst);
+  return check_launch("gather_i64_as_i32");
+}
+
+extern "C" int pgh_unpack_tight(const int64_t* key, int64_t n, const int64_t* dims_host, int sd,
+                                int64_t* out, int64_t ld, void* stream) {
+  RowSel s;
+  int32_t rows[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+  if (int e = fill_rowsel(s, rows, dims_host, sd)) return e;
+  if (n <= 0) return 0;
+  unpack_tight_kernel<<<blocks_for(n, kT), kT, 0, as_stream(stream)>>>((const long long*)key, n, s,
+                                                                       (long long*)out, ld);
+  return check_launch("unpack_tight");
+}
+
+extern "C" int pgh_check_sorted_i64(const int64_t* key, int64_t n, int strict, int32_t* info,
+                                    void* stream) {
+  if (n <= 1) return 0;
+  check_sorted_kernel<<<blocks_for(n, kT), kT, 0, as_stream(stream)>>>((const long long*)key, n, strict, info);
+  return check_launch("check_sorted");
+}

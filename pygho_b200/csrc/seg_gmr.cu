@@ -1,0 +1,446 @@
+// Fused gather - multiply - segmented reduce kernels (the sparse half of the hot path).
+//
+// One kernel family serves spspmm forward and backward, spmm, sparse pooling, unpooling
+// and their autograd replays: every one of them is
+//     out[r,:] = aggr_{t in seg(r)}  A[ia(t),:] * B[ib(t),:]
+// over a CSR-by-row plan.  Design (B200): a group of `lpr` lanes owns one output row and
+// 4 consecutive floats per lane (128-bit loads, a 512 B row of dense=128 is one fully
+// coalesced warp request); the row's slice of the plan is loaded cooperatively (one
+// coalesced request per 32 entries) and broadcast with warp shuffles, so the dependent
+// chain is rowptr -> plan slice -> values with up to 4 independent value loads in flight
+// per lane.  Accumulation is sequential in plan order in registers: deterministic, no
+// atomics, one coalesced store per row.  HBM-bound: algorithmic bytes are
+// 4*dense*(nA + nB + n_rows) + 4*(2T + n_rows + 1)  (SURVEY.md section 8d).
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace pgh {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+template <int VEC>
+__device__ __forceinline__ void ldv(const float* __restrict__ p, float (&r)[VEC]) {
+  if constexpr (VEC == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+  } else {
+    r[0] = __ldg(p);
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void stv(float* __restrict__ p, const float (&r)[VEC]) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
+  } else {
+    p[0] = r[0];
+  }
+}
+
+// Geometry shared by the three kernels: which row / column slice this lane owns.
+struct Lane {
+  long long row;
+  int sub, beg, len, maxlen;
+  bool row_ok;
+};
+
+__device__ __forceinline__ Lane lane_setup(const int* __restrict__ rowptr, long long n_rows,
+                                           int lpr) {
+  Lane L;
+  const int lane = threadIdx.x & 31;
+  const int rpw = 32 / lpr;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  L.sub = lane & (lpr - 1);
+  L.row = warp * rpw + lane / lpr;
+  L.row_ok = L.row < n_rows;
+  int beg = 0, end = 0;
+  if (L.row_ok) {
+    if (rowptr) {
+      beg = __ldg(rowptr + L.row);
+      end = __ldg(rowptr + L.row + 1);
+    } else {
+      beg = (int)L.row;
+      end = beg + 1;
+    }
+  }
+  L.beg = beg;
+  L.len = end - beg;
+  L.maxlen = (rpw == 1) ? L.len : __reduce_max_sync(0xffffffffu, L.len);
+  return L;
+}
+
+constexpr int kUnroll = 4;
+constexpr int kThreads = 256;
+
+template <int AGGR, int VEC, bool HAS_B>
+__global__ void __launch_bounds__(kThreads)
+seg_gmr_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
+               const float* __restrict__ a_scale, const float* __restrict__ b_val,
+               const int* __restrict__ d, const int* __restrict__ rowptr, long long n_rows,
+               int dense, int lpr, float* __restrict__ out) {
+  const Lane L = lane_setup(rowptr, n_rows, lpr);
+  const int colstep = lpr * VEC;
+  for (int col0 = 0; col0 < dense; col0 += colstep) {
+    const int col = col0 + L.sub * VEC;
+    const bool col_ok = col < dense;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+      acc[v] = (AGGR == PGH_MAX) ? -INFINITY : (AGGR == PGH_MIN) ? INFINITY : 0.f;
+    for (int base = 0; base < L.maxlen; base += lpr) {
+      // cooperative, coalesced load of this row's slice of the plan
+      const int t = L.beg + base + L.sub;
+      int ci = 0, di = 0;
+      float sc = 1.f;
+      if (base + L.sub < L.len) {
+        ci = c ? __ldg(c + t) : t;
+        if (HAS_B) di = d ? __ldg(d + t) : t;
+        if (a_scale) sc = __ldg(a_scale + ci);
+      }
+      const int chunk = min(lpr, L.maxlen - base);
+#pragma unroll 1
+      for (int k = 0; k < chunk; k += kUnroll) {
+        int cc[kUnroll], dd[kUnroll];
+        float ss[kUnroll];
+        bool ok[kUnroll];
+        float av[kUnroll][VEC], bv[kUnroll][VEC];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int kk = k + u;
+          cc[u] = __shfl_sync(0xffffffffu, ci, kk, lpr);
+          dd[u] = HAS_B ? __shfl_sync(0xffffffffu, di, kk, lpr) : 0;
+          ss[u] = __shfl_sync(0xffffffffu, sc, kk, lpr);
+          ok[u] = col_ok && kk < chunk && (base + kk) < L.len;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          if (ok[u]) {
+            ldv<VEC>(a_val + (size_t)cc[u] * dense + col, av[u]);
+            if (HAS_B) ldv<VEC>(b_val + (size_t)dd[u] * dense + col, bv[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          if (ok[u]) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              float m = __fmul_rn(av[u][v], ss[u]);
+              if (HAS_B) m = __fmul_rn(m, bv[u][v]);
+              if (AGGR == PGH_MAX) acc[v] = fmaxf(acc[v], m);
+              else if (AGGR == PGH_MIN) acc[v] = fminf(acc[v], m);
+              else acc[v] = __fadd_rn(acc[v], m);
+            }
+          }
+        }
+      }
+    }
+    if (L.row_ok && col_ok) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (L.len == 0) acc[v] = 0.f;
+        else if (AGGR == PGH_MEAN) acc[v] = acc[v] / (float)L.len;
+      }
+      stv<VEC>(out + (size_t)L.row * dense + col, acc);
+    }
+  }
+}
+
+// gscaled[r,:] = grad[r,:] / (#entries of seg(r) whose product equals out[r,:])
+template <int VEC, bool HAS_B>
+__global__ void __launch_bounds__(kThreads)
+seg_tie_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
+               const float* __restrict__ b_val, const int* __restrict__ d,
+               const int* __restrict__ rowptr, long long n_rows, int dense, int lpr,
+               const float* __restrict__ outp, const float* __restrict__ grad,
+               float* __restrict__ gscaled) {
+  const Lane L = lane_setup(rowptr, n_rows, lpr);
+  const int colstep = lpr * VEC;
+  for (int col0 = 0; col0 < dense; col0 += colstep) {
+    const int col = col0 + L.sub * VEC;
+    const bool col_ok = col < dense;
+    float ov[VEC], gv[VEC];
+    int cnt[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { ov[v] = 0.f; gv[v] = 0.f; cnt[v] = 0; }
+    if (L.row_ok && col_ok) {
+      ldv<VEC>(outp + (size_t)L.row * dense + col, ov);
+      ldv<VEC>(grad + (size_t)L.row * dense + col, gv);
+      // torch's scatter_reduce amax/amin backward also counts the (zero) initial value of
+      // the output as a tie when the result is exactly 0, even with include_self=False
+      // (FunctionsManual.cpp scatter_reduce_backward: N = (self == result) + ...); the
+      // reference inherits that through backend/utils.py:50-55, so it is reproduced here.
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) cnt[v] = (ov[v] == 0.f) ? 1 : 0;
+    }
+    for (int base = 0; base < L.maxlen; base += lpr) {
+      const int t = L.beg + base + L.sub;
+      int ci = 0, di = 0;
+      if (base + L.sub < L.len) {
+        ci = c ? __ldg(c + t) : t;
+        if (HAS_B) di = d ? __ldg(d + t) : t;
+      }
+      const int chunk = min(lpr, L.maxlen - base);
+#pragma unroll 1
+      for (int k = 0; k < chunk; ++k) {
+        const int cc = __shfl_sync(0xffffffffu, ci, k, lpr);
+        const int dd = HAS_B ? __shfl_sync(0xffffffffu, di, k, lpr) : 0;
+        if (col_ok && (base + k) < L.len) {
+          float av[VEC], bv[VEC];
+          ldv<VEC>(a_val + (size_t)cc * dense + col, av);
+          if (HAS_B) ldv<VEC>(b_val + (size_t)dd * dense + col, bv);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const float m = HAS_B ? __fmul_rn(av[v], bv[v]) : av[v];
+            cnt[v] += (m == ov[v]) ? 1 : 0;
+          }
+        }
+      }
+    }
+    if (L.row_ok && col_ok) {
+      float r[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) r[v] = cnt[v] > 0 ? gv[v] / (float)cnt[v] : 0.f;
+      stv<VEC>(gscaled + (size_t)L.row * dense + col, r);
+    }
+  }
+}
+
+// g_self[p,:] = sum_{t in seg(p)} [self[p,:]*O(t) == out[row(t),:]] * gscaled[row(t),:] * O(t)
+template <int VEC, bool HAS_O>
+__global__ void __launch_bounds__(kThreads)
+seg_select_bwd_kernel(const float* __restrict__ self_val, const float* __restrict__ other_val,
+                      const int* __restrict__ other_idx, const int* __restrict__ row_idx,
+                      const int* __restrict__ rowptr, long long n_rows, int dense, int lpr,
+                      const float* __restrict__ outp, const float* __restrict__ gscaled,
+                      float* __restrict__ g_self) {
+  const Lane L = lane_setup(rowptr, n_rows, lpr);
+  const int colstep = lpr * VEC;
+  for (int col0 = 0; col0 < dense; col0 += colstep) {
+    const int col = col0 + L.sub * VEC;
+    const bool col_ok = col < dense;
+    float sv[VEC], acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { sv[v] = 0.f; acc[v] = 0.f; }
+    if (L.row_ok && col_ok) ldv<VEC>(self_val + (size_t)L.row * dense + col, sv);
+    for (int base = 0; base < L.maxlen; base += lpr) {
+      const int t = L.beg + base + L.sub;
+      int ri = 0, oi = 0;
+      if (base + L.sub < L.len) {
+        ri = row_idx ? __ldg(row_idx + t) : t;
+        if (HAS_O) oi = other_idx ? __ldg(other_idx + t) : t;
+      }
+      const int chunk = min(lpr, L.maxlen - base);
+#pragma unroll 1
+      for (int k = 0; k < chunk; ++k) {
+        const int rr = __shfl_sync(0xffffffffu, ri, k, lpr);
+        const int oo = HAS_O ? __shfl_sync(0xffffffffu, oi, k, lpr) : 0;
+        if (col_ok && (base + k) < L.len) {
+          float ov[VEC], gv[VEC], xv[VEC];
+          ldv<VEC>(outp + (size_t)rr * dense + col, ov);
+          ldv<VEC>(gscaled + (size_t)rr * dense + col, gv);
+          if (HAS_O) ldv<VEC>(other_val + (size_t)oo * dense + col, xv);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const float m = HAS_O ? __fmul_rn(sv[v], xv[v]) : sv[v];
+            const float w = HAS_O ? __fmul_rn(gv[v], xv[v]) : gv[v];
+            acc[v] = __fadd_rn(acc[v], (m == ov[v]) ? w : 0.f);
+          }
+        }
+      }
+    }
+    if (L.row_ok && col_ok) stv<VEC>(g_self + (size_t)L.row * dense + col, acc);
+  }
+}
+
+__global__ void inv_count_kernel(const int* __restrict__ rowptr, long long n_rows,
+                                 float* __restrict__ inv) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rows) {
+    const int n = __ldg(rowptr + r + 1) - __ldg(rowptr + r);
+    inv[r] = 1.f / (float)max(n, 1);
+  }
+}
+
+template <int AGGR>
+__global__ void seg_reduce_i64_kernel(const long long* __restrict__ val,
+                                      const int* __restrict__ perm,
+                                      const int* __restrict__ rowptr, long long n_rows,
+                                      int dense, long long* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * dense) return;
+  const long long r = i / dense;
+  const int col = (int)(i % dense);
+  const int beg = rowptr[r], end = rowptr[r + 1];
+  long long acc = 0;
+  for (int t = beg; t < end; ++t) {
+    const long long x = val[(size_t)(perm ? perm[t] : t) * dense + col];
+    if (t == beg) acc = x;
+    else if (AGGR == PGH_MAX) acc = x > acc ? x : acc;
+    else if (AGGR == PGH_MIN) acc = x < acc ? x : acc;
+    else acc += x;
+  }
+  if (AGGR == PGH_MEAN && end > beg) {
+    // torch integer "mean" = floor division (backend/utils.py:50-55 via scatter_reduce_)
+    const long long n = end - beg;
+    long long q = acc / n;
+    if ((acc % n != 0) && ((acc < 0) != (n < 0))) --q;
+    acc = q;
+  }
+  out[i] = acc;
+}
+
+struct Geometry {
+  int vec, lpr;
+  unsigned blocks;
+};
+
+static Geometry geometry(int64_t n_rows, int64_t dense, bool aligned) {
+  Geometry g;
+  g.vec = (aligned && dense % 4 == 0) ? 4 : 1;
+  const int64_t units = dense / g.vec;
+  int lpr = 1;
+  while (lpr < 32 && lpr < units) lpr <<= 1;
+  g.lpr = lpr;
+  const int rows_per_block = (kThreads / 32) * (32 / lpr);
+  g.blocks = blocks_for(n_rows, rows_per_block);
+  return g;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int AGGR, int VEC>
+static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, const int* c,
+                       const float* a_scale, const float* b_val, const int* d,
+                       const int* rowptr, int64_t n_rows, int dense, float* out) {
+  if (b_val)
+    seg_gmr_kernel<AGGR, VEC, true><<<g.blocks, kThreads, 0, s>>>(
+        a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, g.lpr, out);
+  else
+    seg_gmr_kernel<AGGR, VEC, false><<<g.blocks, kThreads, 0, s>>>(
+        a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, g.lpr, out);
+}
+
+}  // namespace pgh
+
+using namespace pgh;
+
+extern "C" const char* pgh_last_error(void) { return pgh::g_err; }
+extern "C" int pgh_abi_version(void) { return 1; }
+
+extern "C" int pgh_device_info(int32_t* out5) {
+  int dev = 0;
+  PGH_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  PGH_CUDA(cudaGetDeviceProperties(&p, dev));
+  out5[0] = dev;
+  out5[1] = p.multiProcessorCount;
+  out5[2] = (int32_t)(p.l2CacheSize >> 10);  // KiB
+  out5[3] = p.major;
+  out5[4] = p.minor;
+  return 0;
+}
+
+extern "C" int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float* a_scale,
+                               const float* b_val, const int32_t* d, const int32_t* rowptr,
+                               int64_t n_rows, int64_t dense, int aggr, float* out,
+                               void* stream) {
+  if (!a_val || !out) return arg_error("seg_gmr: a_val and out are required");
+  if (n_rows < 0 || dense <= 0 || dense > (1 << 20)) return arg_error("seg_gmr: sizes");
+  if (aggr < 0 || aggr > 3) return arg_error("seg_gmr: aggr");
+  if (n_rows == 0) return 0;
+  const bool al = aligned16(a_val) && aligned16(out) && (!b_val || aligned16(b_val));
+  const Geometry g = geometry(n_rows, dense, al);
+  cudaStream_t s = as_stream(stream);
+#define PGH_GMR(AG)                                                                       \
+  if (g.vec == 4) launch_gmr<AG, 4>(g, s, a_val, c, a_scale, b_val, d, rowptr, n_rows,   \
+                                    (int)dense, out);                                     \
+  else launch_gmr<AG, 1>(g, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, (int)dense, out)
+  switch (aggr) {
+    case PGH_SUM: PGH_GMR(PGH_SUM); break;
+    case PGH_MEAN: PGH_GMR(PGH_MEAN); break;
+    case PGH_MAX: PGH_GMR(PGH_MAX); break;
+    default: PGH_GMR(PGH_MIN); break;
+  }
+#undef PGH_GMR
+  return check_launch("seg_gmr");
+}
+
+extern "C" int pgh_seg_tie_scale_f32(const float* a_val, const int32_t* c, const float* b_val,
+                                     const int32_t* d, const int32_t* rowptr, int64_t n_rows,
+                                     int64_t dense, const float* out, const float* grad,
+                                     float* gscaled, void* stream) {
+  if (!a_val || !out || !grad || !gscaled) return arg_error("seg_tie_scale: null pointer");
+  if (n_rows < 0 || dense <= 0) return arg_error("seg_tie_scale: sizes");
+  if (n_rows == 0) return 0;
+  const bool al = aligned16(a_val) && aligned16(out) && aligned16(grad) && aligned16(gscaled) &&
+                  (!b_val || aligned16(b_val));
+  const Geometry g = geometry(n_rows, dense, al);
+  cudaStream_t s = as_stream(stream);
+  const int dn = (int)dense;
+  if (g.vec == 4) {
+    if (b_val) seg_tie_kernel<4, true><<<g.blocks, kThreads, 0, s>>>(a_val, c, b_val, d, rowptr, n_rows, dn, g.lpr, out, grad, gscaled);
+    else seg_tie_kernel<4, false><<<g.blocks, kThreads, 0, s>>>(a_val, c, b_val, d, rowptr, n_rows, dn, g.lpr, out, grad, gscaled);
+  } else {
+    if (b_val) seg_tie_kernel<1, true><<<g.blocks, kThreads, 0, s>>>(a_val, c, b_val, d, rowptr, n_rows, dn, g.lpr, out, grad, gscaled);
+    else seg_tie_kernel<1, false><<<g.blocks, kThreads, 0, s>>>(a_val, c, b_val, d, rowptr, n_rows, dn, g.lpr, out, grad, gscaled);
+  }
+  return check_launch("seg_tie_scale");
+}
+
+extern "C" int pgh_seg_select_bwd_f32(const float* self_val, const float* other_val,
+                                      const int32_t* other_idx, const int32_t* row_idx,
+                                      const int32_t* rowptr, int64_t n_rows, int64_t dense,
+                                      const float* out, const float* gscaled, float* g_self,
+                                      void* stream) {
+  if (!self_val || !out || !gscaled || !g_self) return arg_error("seg_select_bwd: null pointer");
+  if (n_rows < 0 || dense <= 0) return arg_error("seg_select_bwd: sizes");
+  if (n_rows == 0) return 0;
+  const bool al = aligned16(self_val) && aligned16(out) && aligned16(gscaled) &&
+                  aligned16(g_self) && (!other_val || aligned16(other_val));
+  const Geometry g = geometry(n_rows, dense, al);
+  cudaStream_t s = as_stream(stream);
+  const int dn = (int)dense;
+  if (g.vec == 4) {
+    if (other_val) seg_select_bwd_kernel<4, true><<<g.blocks, kThreads, 0, s>>>(self_val, other_val, other_idx, row_idx, rowptr, n_rows, dn, g.lpr, out, gscaled, g_self);
+    else seg_select_bwd_kernel<4, false><<<g.blocks, kThreads, 0, s>>>(self_val, other_val, other_idx, row_idx, rowptr, n_rows, dn, g.lpr, out, gscaled, g_self);
+  } else {
+    if (other_val) seg_select_bwd_kernel<1, true><<<g.blocks, kThreads, 0, s>>>(self_val, other_val, other_idx, row_idx, rowptr, n_rows, dn, g.lpr, out, gscaled, g_self);
+    else seg_select_bwd_kernel<1, false><<<g.blocks, kThreads, 0, s>>>(self_val, other_val, other_idx, row_idx, rowptr, n_rows, dn, g.lpr, out, gscaled, g_self);
+  }
+  return check_launch("seg_select_bwd");
+}
+
+extern "C" int pgh_inv_count_f32(const int32_t* rowptr, int64_t n_rows, float* inv,
+                                 void* stream) {
+  if (!rowptr || !inv) return arg_error("inv_count: null pointer");
+  if (n_rows <= 0) return 0;
+  inv_count_kernel<<<blocks_for(n_rows, 256), 256, 0, as_stream(stream)>>>(rowptr, n_rows, inv);
+  return check_launch("inv_count");
+}
+
+extern "C" int pgh_seg_reduce_i64(const int64_t* val, const int32_t* perm, const int32_t* rowptr,
+                                  int64_t n_rows, int64_t dense, int aggr, int64_t* out,
+                                  void* stream) {
+  if (!val || !rowptr || !out) return arg_error("seg_reduce_i64: null pointer");
+  if (n_rows <= 0 || dense <= 0) return 0;
+  const unsigned nb = blocks_for(n_rows * dense, 256);
+  cudaStream_t s = as_stream(stream);
+  const long long* v = reinterpret_cast<const long long*>(val);
+  long long* o = reinterpret_cast<long long*>(out);
+  switch (aggr) {
+    case PGH_SUM: seg_reduce_i64_kernel<PGH_SUM><<<nb, 256, 0, s>>>(v, perm, rowptr, n_rows, (int)dense, o); break;
+    case PGH_MEAN: seg_reduce_i64_kernel<PGH_MEAN><<<nb, 256, 0, s>>>(v, perm, rowptr, n_rows, (int)dense, o); break;
+    case PGH_MAX: seg_reduce_i64_kernel<PGH_MAX><<<nb, 256, 0, s>>>(v, perm, rowptr, n_rows, (int)dense, o); break;
+    case PGH_MIN: seg_reduce_i64_kernel<PGH_MIN><<<nb, 256, 0, s>>>(v, perm, rowptr, n_rows, (int)dense, o); break;
+    default: return arg_error("seg_reduce_i64: aggr");
+  }
+  return check_launch("seg_reduce_i64");
+}

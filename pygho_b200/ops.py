@@ -1,0 +1,392 @@
+"""``torch.library`` operators ``pygho_b200::*`` -- thin shims over the C ABI.
+
+Each operator allocates its output with torch (device memory is torch's job), passes raw
+device pointers plus the current CUDA stream to ``libpygho_b200.so`` and returns.  They are
+registered for the CUDA dispatch key only: calling them with CPU tensors raises (there is
+no CPU implementation of this package).  ``register_fake`` gives shape propagation so the
+ops trace under ``torch.compile`` (the reference compiles its models, example/zinc.py:407).
+
+Autograd lives one level up in :class:`SegGmr`, :class:`MaMaMM` and :class:`MaskedPool`,
+which call only these operators in both directions.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import AGGR_CODE, call, ptr, stream_ptr
+
+_LIB = torch.library.Library("pygho_b200", "DEF")
+
+
+def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"pygho_b200 kernels are float32; got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.int32:
+        raise TypeError(f"plan indices must be int32; got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------- seg_gmr
+_LIB.define("seg_gmr(Tensor a_val, Tensor? c, Tensor? a_scale, Tensor? b_val, Tensor? d, "
+            "Tensor? rowptr, int n_rows, int aggr) -> Tensor")
+
+
+def _seg_gmr_cuda(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr):
+    a_val, b_val, a_scale = _f32c(a_val), _f32c(b_val), _f32c(a_scale)
+    c, d, rowptr = _i32c(c), _i32c(d), _i32c(rowptr)
+    dense = a_val.shape[1]
+    if a_val.shape[0] == 0 or (b_val is not None and b_val.shape[0] == 0):
+        return torch.zeros((n_rows, dense), dtype=torch.float32, device=a_val.device)
+    out = torch.empty((n_rows, dense), dtype=torch.float32, device=a_val.device)
+    if n_rows and dense:
+        call("pgh_seg_gmr_f32", ptr(a_val), ptr(c), ptr(a_scale), ptr(b_val), ptr(d),
+             ptr(rowptr), n_rows, dense, aggr, ptr(out), stream_ptr(a_val.device))
+        _lib.count_launch()
+    return out
+
+
+_LIB.impl("seg_gmr", _seg_gmr_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::seg_gmr")
+def _seg_gmr_fake(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr):
+    return a_val.new_empty((n_rows, a_val.shape[1]))
+
+
+_LIB.define("seg_tie_scale(Tensor a_val, Tensor? c, Tensor? b_val, Tensor? d, Tensor? rowptr, "
+            "Tensor out, Tensor grad) -> Tensor")
+
+
+def _seg_tie_scale_cuda(a_val, c, b_val, d, rowptr, out, grad):
+    a_val, b_val, out, grad = _f32c(a_val), _f32c(b_val), _f32c(out), _f32c(grad)
+    n_rows, dense = out.shape
+    gs = torch.empty_like(out)
+    if out.numel():
+        call("pgh_seg_tie_scale_f32", ptr(a_val), ptr(_i32c(c)), ptr(b_val), ptr(_i32c(d)),
+             ptr(_i32c(rowptr)), n_rows, dense, ptr(out), ptr(grad), ptr(gs),
+             stream_ptr(out.device))
+        _lib.count_launch()
+    return gs
+
+
+_LIB.impl("seg_tie_scale", _seg_tie_scale_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::seg_tie_scale")
+def _seg_tie_scale_fake(a_val, c, b_val, d, rowptr, out, grad):
+    return torch.empty_like(out)
+
+
+_LIB.define("seg_select_bwd(Tensor self_val, Tensor? other_val, Tensor? other_idx, "
+            "Tensor? row_idx, Tensor? rowptr, Tensor out, Tensor gscaled) -> Tensor")
+
+
+def _seg_select_bwd_cuda(self_val, other_val, other_idx, row_idx, rowptr, out, gscaled):
+    self_val, other_val = _f32c(self_val), _f32c(other_val)
+    out, gscaled = _f32c(out), _f32c(gscaled)
+    n_rows, dense = self_val.shape
+    g = torch.empty_like(self_val)
+    if g.numel():
+        call("pgh_seg_select_bwd_f32", ptr(self_val), ptr(other_val), ptr(_i32c(other_idx)),
+             ptr(_i32c(row_idx)), ptr(_i32c(rowptr)), n_rows, dense, ptr(out), ptr(gscaled),
+             ptr(g), stream_ptr(g.device))
+        _lib.count_launch()
+    return g
+
+
+_LIB.impl("seg_select_bwd", _seg_select_bwd_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::seg_select_bwd")
+def _seg_select_bwd_fake(self_val, other_val, other_idx, row_idx, rowptr, out, gscaled):
+    return torch.empty_like(self_val)
+
+
+_LIB.define("inv_count(Tensor rowptr) -> Tensor")
+
+
+def _inv_count_cuda(rowptr):
+    rowptr = _i32c(rowptr)
+    n = rowptr.shape[0] - 1
+    inv = torch.empty((n,), dtype=torch.float32, device=rowptr.device)
+    if n > 0:
+        call("pgh_inv_count_f32", ptr(rowptr), n, ptr(inv), stream_ptr(rowptr.device))
+        _lib.count_launch()
+    return inv
+
+
+_LIB.impl("inv_count", _inv_count_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::inv_count")
+def _inv_count_fake(rowptr):
+    return rowptr.new_empty((rowptr.shape[0] - 1,), dtype=torch.float32)
+
+
+# -------------------------------------------------------------------------- masked
+_LIB.define("mamamm(Tensor A, bool trans_a, Tensor B, bool trans_b, Tensor mask, int algo) -> Tensor")
+
+
+def _mamamm_cuda(A, trans_a, B, trans_b, mask, algo):
+    A, B = _f32c(A), _f32c(B)
+    mask = mask.contiguous()
+    b = A.shape[0]
+    n_i, n_j = (A.shape[2], A.shape[1]) if trans_a else (A.shape[1], A.shape[2])
+    n_j2, n_k = (B.shape[2], B.shape[1]) if trans_b else (B.shape[1], B.shape[2])
+    if n_j != n_j2 or A.shape[3] != B.shape[3] or B.shape[0] != b:
+        raise ValueError(f"mamamm: incompatible shapes {tuple(A.shape)} x {tuple(B.shape)}")
+    if tuple(mask.shape) != (b, n_i, n_k):
+        raise ValueError(f"mamamm: mask shape {tuple(mask.shape)} != {(b, n_i, n_k)}")
+    dense = A.shape[3]
+    out = torch.empty((b, n_i, n_k, dense), dtype=torch.float32, device=A.device)
+    if out.numel():
+        call("pgh_mamamm_f32", ptr(A), int(trans_a), ptr(B), int(trans_b),
+             ptr(mask.view(torch.uint8)), b, n_i, n_j, n_k, dense, algo, ptr(out),
+             stream_ptr(A.device))
+        _lib.count_launch()
+    return out
+
+
+_LIB.impl("mamamm", _mamamm_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::mamamm")
+def _mamamm_fake(A, trans_a, B, trans_b, mask, algo):
+    n_i = A.shape[2] if trans_a else A.shape[1]
+    n_k = B.shape[1] if trans_b else B.shape[2]
+    return A.new_empty((A.shape[0], n_i, n_k, A.shape[3]))
+
+
+_LIB.define("masked_pool(Tensor data, Tensor mask, int red_dims, int aggr) -> (Tensor, Tensor)")
+
+
+def _pool_shape(b, n1, n2, red):
+    return (b, n2) if red == 1 else (b, n1) if red == 2 else (b,)
+
+
+def _masked_pool_cuda(data, mask, red_dims, aggr):
+    data = _f32c(data)
+    mask = mask.contiguous()
+    b, n1, n2, dense = data.shape
+    keep = _pool_shape(b, n1, n2, red_dims)
+    out = torch.empty(keep + (dense,), dtype=torch.float32, device=data.device)
+    omask = torch.empty(keep, dtype=torch.bool, device=data.device)
+    if out.numel():
+        call("pgh_masked_pool_f32", ptr(data), ptr(mask.view(torch.uint8)), b, n1, n2, dense,
+             red_dims, aggr, ptr(out), ptr(omask.view(torch.uint8)), stream_ptr(data.device))
+        _lib.count_launch()
+    return out, omask
+
+
+_LIB.impl("masked_pool", _masked_pool_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::masked_pool")
+def _masked_pool_fake(data, mask, red_dims, aggr):
+    b, n1, n2, dense = data.shape
+    keep = _pool_shape(b, n1, n2, red_dims)
+    return data.new_empty(keep + (dense,)), mask.new_empty(keep)
+
+
+_LIB.define("masked_pool_bwd(Tensor data, Tensor mask, Tensor out, Tensor g_out, int red_dims, "
+            "int aggr) -> Tensor")
+
+
+def _masked_pool_bwd_cuda(data, mask, out, g_out, red_dims, aggr):
+    data, out, g_out = _f32c(data), _f32c(out), _f32c(g_out)
+    mask = mask.contiguous()
+    b, n1, n2, dense = data.shape
+    g = torch.empty_like(data)
+    if g.numel():
+        call("pgh_masked_pool_bwd_f32", ptr(data), ptr(mask.view(torch.uint8)), ptr(out),
+             ptr(g_out), b, n1, n2, dense, red_dims, aggr, ptr(g), stream_ptr(data.device))
+        _lib.count_launch()
+    return g
+
+
+_LIB.impl("masked_pool_bwd", _masked_pool_bwd_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::masked_pool_bwd")
+def _masked_pool_bwd_fake(data, mask, out, g_out, red_dims, aggr):
+    return torch.empty_like(data)
+
+
+_LIB.define("masked_fill_rows(Tensor data, Tensor mask, float value) -> Tensor")
+
+
+def _masked_fill_cuda(data, mask, value):
+    data = _f32c(data)
+    mask = mask.contiguous()
+    rows = mask.numel()
+    dense = data.numel() // max(rows, 1)
+    out = torch.empty_like(data)
+    if out.numel():
+        call("pgh_masked_fill_f32", ptr(data), ptr(mask.view(torch.uint8)), rows, dense,
+             float(value), ptr(out), stream_ptr(data.device))
+        _lib.count_launch()
+    return out
+
+
+_LIB.impl("masked_fill_rows", _masked_fill_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::masked_fill_rows")
+def _masked_fill_fake(data, mask, value):
+    return torch.empty_like(data)
+
+
+_ops = torch.ops.pygho_b200
+
+
+# ------------------------------------------------------------------------- autograd
+class SegGmr(torch.autograd.Function):
+    """out[r] = aggr_{t in seg(r)} A[c_t] * B[d_t] with the three CSR groupings of a
+    :class:`pygho_b200.plans.TriplePlan`.  Gradients flow to the value operands only
+    (SURVEY.md 8b "Autograd"); max/min split the gradient evenly among ties like
+    torch's ``scatter_reduce_`` backward."""
+
+    @staticmethod
+    def forward(ctx, a_val: Tensor, b_val: Optional[Tensor], plan, aggr: int):
+        ga = plan.group("a")
+        out = _ops.seg_gmr(a_val, ga.first, None, b_val, ga.second if b_val is not None else None,
+                           ga.rowptr, plan.n_out, aggr)
+        ctx.plan, ctx.aggr = plan, aggr
+        ctx.has_b = b_val is not None
+        if aggr >= 2:
+            ctx.save_for_backward(a_val, b_val, out)
+        else:
+            ctx.save_for_backward(a_val if ctx.has_b else None, b_val)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g: Tensor):
+        plan, aggr = ctx.plan, ctx.aggr
+        need_a, need_b = ctx.needs_input_grad[0], ctx.has_b and ctx.needs_input_grad[1]
+        g = g.contiguous()
+        g_a = g_b = None
+        if aggr >= 2:
+            a_val, b_val, out = ctx.saved_tensors
+            ga = plan.group("a")
+            gs = _ops.seg_tie_scale(a_val, ga.first, b_val,
+                                    ga.second if ctx.has_b else None, ga.rowptr, out, g)
+            if need_a:
+                gc = plan.group("c")
+                g_a = _ops.seg_select_bwd(a_val, b_val, gc.second if ctx.has_b else None,
+                                          gc.first, gc.rowptr, out, gs)
+            if need_b:
+                gd = plan.group("d")
+                g_b = _ops.seg_select_bwd(b_val, a_val, gd.second, gd.first, gd.rowptr, out, gs)
+            return g_a, g_b, None, None
+        a_val, b_val = ctx.saved_tensors
+        scale = plan.inv_count() if aggr == 1 else None
+        if need_a:
+            gc = plan.group("c")
+            g_a = _ops.seg_gmr(g, gc.first, scale, b_val, gc.second if ctx.has_b else None,
+                               gc.rowptr, plan.n_a, 0)
+        if need_b:
+            gd = plan.group("d")
+            g_b = _ops.seg_gmr(g, gd.first, scale, a_val, gd.second, gd.rowptr, plan.n_b, 0)
+        return g_a, g_b, None, None
+
+
+def seg_gmr(a_val: Optional[Tensor], b_val: Optional[Tensor], plan, aggr: str) -> Tensor:
+    """Differentiable gather-multiply-segment-reduce over ``plan``; a ``None`` operand
+    counts as 1 (backend/Spspmm.py:309-314).  Operands are (rows, dense) float32."""
+    code = AGGR_CODE[aggr]
+    if a_val is None and b_val is None:
+        raise ValueError("at least one operand needs values")
+    if a_val is None:
+        return SegGmr.apply(b_val, None, plan.swapped(), code)
+    return SegGmr.apply(a_val, b_val, plan, code)
+
+
+class MaMaMM(torch.autograd.Function):
+    """out = mask * (A' @ B') per channel; A' / B' optionally transposed in dims (1, 2)."""
+
+    @staticmethod
+    def forward(ctx, A, trans_a, B, trans_b, mask, algo):
+        ctx.save_for_backward(A, B, mask)
+        ctx.cfg = (trans_a, trans_b, algo)
+        return _ops.mamamm(A, trans_a, B, trans_b, mask, algo)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        A, B, mask = ctx.saved_tensors
+        trans_a, trans_b, algo = ctx.cfg
+        # out is masked in the epilogue -> its gradient only exists where mask is True
+        g = _ops.masked_fill_rows(g.contiguous(), mask, 0.0)
+        ones_a = _ones_mask(A)
+        ones_b = _ones_mask(B)
+        g_a = g_b = None
+        if ctx.needs_input_grad[0]:
+            # dA'[i,j] = sum_k g[i,k] B'[j,k]  -> g @ B'^T ; stored transposed if trans_a
+            if not trans_a:
+                g_a = _ops.mamamm(g, False, B, not trans_b, ones_a, algo)
+            else:
+                g_a = _ops.mamamm(B, trans_b, g, True, ones_a, algo)
+        if ctx.needs_input_grad[2]:
+            # dB'[j,k] = sum_i A'[i,j] g[i,k] -> A'^T @ g ; stored transposed if trans_b
+            if not trans_b:
+                g_b = _ops.mamamm(A, not trans_a, g, False, ones_b, algo)
+            else:
+                g_b = _ops.mamamm(g, True, A, trans_a, ones_b, algo)
+        return g_a, None, g_b, None, None, None
+
+
+_ONES_CACHE = {}
+
+
+def _ones_mask(t: Tensor) -> Tensor:
+    key = (t.device, tuple(t.shape[:3]))
+    m = _ONES_CACHE.get(key)
+    if m is None:
+        if len(_ONES_CACHE) > 16:
+            _ONES_CACHE.clear()
+        m = torch.ones(t.shape[:3], dtype=torch.bool, device=t.device)
+        _ONES_CACHE[key] = m
+    return m
+
+
+class MaskedPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, mask, red_dims, aggr):
+        out, omask = _ops.masked_pool(data, mask, red_dims, aggr)
+        ctx.save_for_backward(data, mask, out)
+        ctx.cfg = (red_dims, aggr)
+        ctx.mark_non_differentiable(omask)
+        return out, omask
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g, _gm):
+        data, mask, out = ctx.saved_tensors
+        red_dims, aggr = ctx.cfg
+        return _ops.masked_pool_bwd(data, mask, out, g.contiguous(), red_dims, aggr), None, None, None
+
+
+class MaskedFill(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, mask, value):
+        ctx.save_for_backward(mask)
+        return _ops.masked_fill_rows(data, mask, value)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return _ops.masked_fill_rows(g.contiguous(), mask, 0.0), None, None

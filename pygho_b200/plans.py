@@ -1,0 +1,468 @@
+"""Device-side index plans (int32 CSR groupings) and the integer kernels that build them.
+
+A *triple plan* is a list of T triples ``(a_t, c_t, d_t)`` meaning "row ``c_t`` of operand
+A times row ``d_t`` of operand B contributes to output row ``a_t``".  The reference keeps
+it as a ``(3, T)`` LongTensor (``acd``, backend/Spspmm.py:186-222) and scatters with
+atomics; here it is regrouped once per batch into up to three CSR groupings
+
+* by ``a`` -- the forward pass (segmented reduce into output rows),
+* by ``c`` and by ``d`` -- the two operand gradients,
+
+each built with a stable radix sort so every reduction order is deterministic.  An index
+that is ``None`` is the identity (``t`` itself); a grouping whose ``rowptr`` is ``None``
+has exactly one triple per row, in order.  Plans are cached on the index tensor they
+were derived from (``tensor._pgh_cache``), which is how "precomputed once per batch in
+hodata and cached on device" (BASELINE.json north_star) is realised without changing the
+reference's ``datadict`` contract.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, NamedTuple, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import call, ptr, size_query, stream_ptr
+
+_CHECK = os.environ.get("PYGHO_B200_CHECK", "0") == "1"
+
+
+class Group(NamedTuple):
+    rowptr: Optional[Tensor]
+    first: Optional[Tensor]
+    second: Optional[Tensor]
+
+
+# ------------------------------------------------------------------ small raw wrappers
+def _empty(n, dtype, device):
+    return torch.empty((int(n),), dtype=dtype, device=device)
+
+
+def _ws(nbytes: int, device) -> Tensor:
+    return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
+
+
+def _launch(name, *args):
+    call(name, *args)
+    _lib.count_launch()
+
+
+def _host_i32(vals: Sequence[int]):
+    import ctypes as C
+    return (C.c_int32 * len(vals))(*[int(v) for v in vals])
+
+
+def _host_i64(vals: Sequence[int]):
+    import ctypes as C
+    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def to_i32(x: Tensor) -> Tensor:
+    """int64 -> int32 on the device (values are row ids, < 2^31)."""
+    if x.dtype == torch.int32:
+        return x.contiguous()
+    x = x.contiguous()
+    _lib.require_cuda(x)
+    out = _empty(x.numel(), torch.int32, x.device)
+    _launch("pgh_i64_to_i32", ptr(x), x.numel(), ptr(out), None, stream_ptr(x.device))
+    return out
+
+
+def to_i64(x: Tensor) -> Tensor:
+    x = x.contiguous()
+    out = _empty(x.numel(), torch.int64, x.device)
+    _launch("pgh_i32_to_i64", ptr(x), x.numel(), ptr(out), stream_ptr(x.device))
+    return out
+
+
+def gather_i32(src: Tensor, idx: Tensor) -> Tensor:
+    out = _empty(idx.numel(), torch.int32, idx.device)
+    _launch("pgh_gather_i32", ptr(src), ptr(idx), idx.numel(), ptr(out), stream_ptr(idx.device))
+    return out
+
+
+def sort_keys(key: Tensor, end_bit: int) -> Tuple[Tensor, Tensor]:
+    """Stable sort of int64 keys on their low ``end_bit`` bits -> (sorted keys, perm int32)."""
+    n = key.numel()
+    dev = key.device
+    ks, perm = _empty(n, torch.int64, dev), _empty(n, torch.int32, dev)
+    if n:
+        nb = size_query("pgh_sort_ws_bytes", n)
+        ws = _ws(nb, dev)
+        _launch("pgh_sort_keys_perm", ptr(key), n, int(end_bit), ptr(ks), ptr(perm), ptr(ws),
+                ws.numel(), stream_ptr(dev))
+    return ks, perm
+
+
+def unique_sorted(ks: Tensor) -> Tuple[Tensor, Tensor, int]:
+    """Run-length unique of sorted keys -> (unique keys, run id per element, count).
+    Reads the count back (one host synchronisation)."""
+    n = ks.numel()
+    dev = ks.device
+    ukey, seg = _empty(n, torch.int64, dev), _empty(n, torch.int32, dev)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if n:
+        ws = _ws(size_query("pgh_unique_ws_bytes", n), dev)
+        _launch("pgh_unique_sorted", ptr(ks), n, ptr(ukey), ptr(seg), ptr(cnt), ptr(ws),
+                ws.numel(), stream_ptr(dev))
+    count = int(cnt.item()) if n else 0
+    return ukey[:count], seg, count
+
+
+def rowptr_from_sorted(key32: Tensor, n_rows: int) -> Tensor:
+    rp = _empty(n_rows + 1, torch.int32, key32.device)
+    _launch("pgh_rowptr_from_sorted", ptr(key32), key32.numel(), int(n_rows), ptr(rp),
+            stream_ptr(key32.device))
+    return rp
+
+
+def csr_of(key32: Tensor, n_rows: int, assume_sorted: bool = False
+           ) -> Tuple[Tensor, Optional[Tensor]]:
+    """(rowptr, perm) of an int32 key array; ``perm`` is None when the caller knows the
+    keys are non-decreasing.  Sorting is stable, so a segment keeps the input order."""
+    if assume_sorted or key32.numel() == 0:
+        return rowptr_from_sorted(key32, n_rows), None
+    ks, perm = sort_keys(to_i64(key32), max(1, int(n_rows - 1).bit_length()))
+    return rowptr_from_sorted(to_i32(ks), n_rows), perm
+
+
+def _take(x: Optional[Tensor], perm: Optional[Tensor]) -> Optional[Tensor]:
+    if perm is None:
+        return x
+    if x is None:
+        return perm
+    return gather_i32(x, perm)
+
+
+class TriplePlan:
+    """T triples (a, c, d) with lazily built, cached CSR groupings (all int32)."""
+
+    def __init__(self, T: int, n_out: int, n_a: int, n_b: int, a: Optional[Tensor],
+                 c: Optional[Tensor], d: Optional[Tensor], sorted_by: str = ""):
+        self.T, self.n_out, self.n_a, self.n_b = int(T), int(n_out), int(n_a), int(n_b)
+        self.idx = {"a": a, "c": c, "d": d}
+        self.sorted_by = sorted_by  # which index arrays are known to be non-decreasing
+        self._groups: Dict[str, Group] = {}
+        self._inv: Optional[Tensor] = None
+        self._swapped: Optional["TriplePlan"] = None
+
+    _ORDER = {"a": ("c", "d", "n_out"), "c": ("a", "d", "n_a"), "d": ("a", "c", "n_b")}
+
+    def group(self, which: str) -> Group:
+        g = self._groups.get(which)
+        if g is None:
+            first, second, nrows = self._ORDER[which]
+            key = self.idx[which]
+            if key is None:  # identity: one triple per row, in order
+                g = Group(None, self.idx[first], self.idx[second])
+            else:
+                rowptr, perm = csr_of(key, getattr(self, nrows), which in self.sorted_by)
+                g = Group(rowptr, _take(self.idx[first], perm), _take(self.idx[second], perm))
+            self._groups[which] = g
+        return g
+
+    def inv_count(self) -> Tensor:
+        """1 / max(#triples of each output row, 1): the mean-backward scale."""
+        if self._inv is None:
+            g = self.group("a")
+            if g.rowptr is None:
+                self._inv = torch.ones((self.n_out,), dtype=torch.float32,
+                                       device=self._device())
+            else:
+                self._inv = torch.ops.pygho_b200.inv_count(g.rowptr)
+        return self._inv
+
+    def _device(self):
+        for v in self.idx.values():
+            if v is not None:
+                return v.device
+        raise RuntimeError("plan without index arrays")
+
+    def swapped(self) -> "TriplePlan":
+        """Same triples with the roles of the two operands exchanged."""
+        if self._swapped is None:
+            s = TriplePlan(self.T, self.n_out, self.n_b, self.n_a, self.idx["a"], self.idx["d"],
+                           self.idx["c"], self.sorted_by.replace("c", "#").replace("d", "c")
+                           .replace("#", "d"))
+            s._swapped = self
+            rename = {"a": "a", "c": "d", "d": "c"}
+            for k, g in self._groups.items():
+                s._groups[rename[k]] = Group(g.rowptr, g.second, g.first) if k == "a" else g
+            s._inv = self._inv
+            self._swapped = s
+        return self._swapped
+
+    def transposed(self) -> "TriplePlan":
+        """Exchange the roles of output rows and operand-A rows (pooling <-> un-pooling);
+        shares the sorted groupings with ``self``."""
+        t = getattr(self, "_transposed", None)
+        if t is None:
+            flip = {"a": "c", "c": "a", "d": "d"}
+            t = TriplePlan(self.T, self.n_a, self.n_out, self.n_b, self.idx["c"], self.idx["a"],
+                           self.idx["d"], "".join(flip[k] for k in self.sorted_by))
+            t._groups = _TransposedGroups(self)
+            t._transposed = self
+            self._transposed = t
+        return t
+
+    def prefetch(self, backward: bool = True) -> "TriplePlan":
+        self.group("a")
+        if backward:
+            self.group("c")
+            self.group("d")
+        return self
+
+
+class _TransposedGroups(dict):
+    """Group cache of a transposed plan: builds through the parent so both share sorts."""
+
+    _FLIP = {"a": "c", "c": "a", "d": "d"}
+
+    def __init__(self, parent: TriplePlan):
+        super().__init__()
+        self.parent = parent
+
+    def get(self, which, default=None):
+        if which in self:
+            return self[which]
+        g = self.parent.group(self._FLIP[which])
+        if which == "d":  # parent order (a, c) -> ours (a', c') = (c, a)
+            g = Group(g.rowptr, g.second, g.first)
+        self[which] = g
+        return g
+
+
+def _cache(t: Tensor) -> dict:
+    c = getattr(t, "_pgh_cache", None)
+    if c is None:
+        c = {}
+        t._pgh_cache = c
+    return c
+
+
+def plan_from_acd(acd: Tensor, n_out: int, n_a: int, n_b: int) -> TriplePlan:
+    """Plan of a reference-format ``acd``/``bcd`` LongTensor (3, T); cached on ``acd``.
+    ``acd[0]`` is not assumed sorted (a stable sort puts it in CSR order either way)."""
+    cache = _cache(acd)
+    key = ("acd", int(n_out), int(n_a), int(n_b))
+    plan = cache.get(key)
+    if plan is None:
+        if acd.ndim != 2 or acd.shape[0] != 3:
+            raise ValueError("acd must have shape (3, T)")
+        _lib.require_cuda(acd)
+        acd = acd.contiguous()
+        if _CHECK and acd.numel():
+            lim = torch.tensor([[n_out], [n_a], [n_b]], device=acd.device)
+            assert bool(((acd >= 0) & (acd < lim)).all()), "acd index out of range"
+        plan = TriplePlan(acd.shape[1], n_out, n_a, n_b, to_i32(acd[0]), to_i32(acd[1]),
+                          to_i32(acd[2]))
+        cache[key] = plan
+    return plan
+
+
+def plan_from_key(key: Tensor, n_rows: int, assume_sorted: bool = False) -> TriplePlan:
+    """Pooling plan: value row t goes to output row ``key[t]`` (a = key, c = identity);
+    its transpose is the un-pooling gather.  Cached on ``key``."""
+    cache = _cache(key)
+    ck = ("key", int(n_rows), bool(assume_sorted))
+    plan = cache.get(ck)
+    if plan is None:
+        _lib.require_cuda(key)
+        if _CHECK and key.numel():
+            assert int(key.min()) >= 0 and int(key.max()) < n_rows, "index out of range"
+        n = key.numel()
+        plan = TriplePlan(n, n_rows, n, 0, to_i32(key), None, None,
+                          "a" if assume_sorted else "")
+        cache[ck] = plan
+    return plan
+
+
+# ------------------------------------------------------------------------------ hashing
+def hash_bits(sparse_dim: int) -> int:
+    return 63 // sparse_dim
+
+
+def pack_keys(ind: Tensor, rows: Optional[Sequence[int]] = None, check: bool = False) -> Tensor:
+    """Packed lexicographic key of the selected rows of an (sd, nnz) LongTensor."""
+    _lib.require_cuda(ind)
+    if ind.dtype != torch.int64:
+        raise TypeError("indices must be int64 (LongTensor)")
+    if ind.stride(1) != 1 and ind.shape[1] > 1:
+        ind = ind.contiguous()
+    rows = list(range(ind.shape[0])) if rows is None else list(rows)
+    nnz = ind.shape[1]
+    key = _empty(nnz, torch.int64, ind.device)
+    info = torch.zeros((2,), dtype=torch.int32, device=ind.device) if check else None
+    bits = hash_bits(len(rows)) if len(rows) > 1 else 63
+    if nnz:
+        _launch("pgh_pack_keys", ptr(ind), ind.stride(0), _host_i32(rows), len(rows), bits, nnz,
+                ptr(key), ptr(info), stream_ptr(ind.device))
+    if check and nnz:
+        neg, big = info.tolist()
+        assert neg == 0, "indice cannot be negative"
+        assert big == 0, "too large indice, hash is not injective"
+    return key
+
+
+def unpack_keys(key: Tensor, sparse_dim: int) -> Tensor:
+    _lib.require_cuda(key)
+    key = key.contiguous()
+    n = key.numel()
+    out = torch.empty((sparse_dim, n), dtype=torch.int64, device=key.device)
+    if n:
+        _launch("pgh_unpack_keys", ptr(key), n, int(sparse_dim),
+                hash_bits(sparse_dim) if sparse_dim > 1 else 63, ptr(out), n,
+                stream_ptr(key.device))
+    return out
+
+
+def pack_tight(ind: Tensor, dims: Sequence[int], rows: Optional[Sequence[int]] = None,
+               check: bool = False) -> Tensor:
+    _lib.require_cuda(ind)
+    if ind.stride(1) != 1 and ind.shape[1] > 1:
+        ind = ind.contiguous()
+    rows = list(range(ind.shape[0])) if rows is None else list(rows)
+    assert len(rows) == len(dims), "indice dim and dim size not match"
+    nnz = ind.shape[1]
+    key = _empty(nnz, torch.int64, ind.device)
+    info = torch.zeros((2,), dtype=torch.int32, device=ind.device) if check else None
+    if nnz:
+        _launch("pgh_pack_tight", ptr(ind), ind.stride(0), _host_i32(rows), _host_i64(dims),
+                len(rows), nnz, ptr(key), ptr(info), stream_ptr(ind.device))
+    if check and nnz:
+        assert info.tolist()[0] == 0, "indice exceeds dimsize"
+    return key
+
+
+def unpack_tight(key: Tensor, dims: Sequence[int]) -> Tensor:
+    _lib.require_cuda(key)
+    key = key.contiguous()
+    n = key.numel()
+    out = torch.empty((len(dims), n), dtype=torch.int64, device=key.device)
+    if n:
+        _launch("pgh_unpack_tight", ptr(key), n, _host_i64(dims), len(dims), ptr(out), n,
+                stream_ptr(key.device))
+    return out
+
+
+def is_sorted(key: Tensor, strict: bool = False) -> bool:
+    """Host-synchronising check (debug / assert paths only)."""
+    info = torch.zeros((1,), dtype=torch.int32, device=key.device)
+    key = key.contiguous()
+    if key.numel() > 1:
+        _launch("pgh_check_sorted_i64", ptr(key), key.numel(), int(strict), ptr(info),
+                stream_ptr(key.device))
+    return int(info.item()) == 0
+
+
+def lookup_sorted(tkeys: Tensor, keys: Tensor) -> Tensor:
+    """Position (int32) of each key in the sorted unique ``tkeys`` or -1."""
+    pos = _empty(keys.numel(), torch.int32, keys.device)
+    if keys.numel():
+        _launch("pgh_lookup_sorted", ptr(tkeys), tkeys.numel(), ptr(keys), keys.numel(),
+                ptr(pos), stream_ptr(keys.device))
+    return pos
+
+
+# --------------------------------------------------------------- contraction plans
+def _expand_matches(ind1: Tensor, dim1: int, ind2: Tensor, dim2: int, k2_sorted: bool):
+    """All (p, q) with ind1[dim1, p] == ind2[dim2, q], ordered by p then by position of q
+    in the key-sorted ind2.  Returns (c int32, d int32, T0).  One host sync (T0)."""
+    dev = _lib.require_cuda(ind1, ind2)
+    nnz1 = ind1.shape[1]
+    k1 = ind1[dim1].contiguous()
+    k2 = ind2[dim2].contiguous()
+    perm2 = None
+    if not k2_sorted:
+        # keys are node ids; sort on as many bits as the largest possible id needs
+        k2, perm2 = sort_keys(k2, 63)
+    lo = _empty(nnz1, torch.int32, dev)
+    off = _empty(nnz1 + 1, torch.int64, dev)
+    ws = _ws(size_query("pgh_match_ws_bytes", nnz1), dev)
+    _launch("pgh_match_ranges", ptr(k2), k2.numel(), ptr(k1), nnz1, ptr(lo), ptr(off), ptr(ws),
+            ws.numel(), stream_ptr(dev))
+    total = int(off[-1].item())
+    c, d = _empty(total, torch.int32, dev), _empty(total, torch.int32, dev)
+    if total:
+        _launch("pgh_expand_pairs", ptr(off), ptr(lo), ptr(perm2), nnz1, total, ptr(c), ptr(d),
+                stream_ptr(dev))
+    return c, d, total
+
+
+def _pair_keys(ind1, dim1, ind2, dim2, c, d) -> Tensor:
+    sd_out = ind1.shape[0] + ind2.shape[0] - 2
+    if sd_out < 1:
+        raise ValueError("contraction leaves no sparse dimension")
+    ind1 = ind1 if ind1.stride(1) == 1 else ind1.contiguous()
+    ind2 = ind2 if ind2.stride(1) == 1 else ind2.contiguous()
+    key = _empty(c.numel(), torch.int64, c.device)
+    if c.numel():
+        _launch("pgh_pair_keys", ptr(ind1), ind1.stride(0), ind1.shape[0], int(dim1), ptr(ind2),
+                ind2.stride(0), ind2.shape[0], int(dim2), ptr(c), ptr(d), c.numel(),
+                hash_bits(sd_out) if sd_out > 1 else 63, ptr(key), None, stream_ptr(c.device))
+    return key
+
+
+def spspmm_ind_i32(ind1: Tensor, dim1: int, ind2: Tensor, dim2: int, k2_sorted: bool):
+    """Device build of the contraction plan.  Returns (tarind int64 (sd_out, nnzP),
+    b int32, c int32, d int32) with the triples sorted by (b, c, d-position)."""
+    sd_out = ind1.shape[0] + ind2.shape[0] - 2
+    c, d, total = _expand_matches(ind1, dim1, ind2, dim2, k2_sorted)
+    key = _pair_keys(ind1, dim1, ind2, dim2, c, d)
+    end_bit = hash_bits(sd_out) * sd_out if sd_out > 1 else 63
+    ks, permT = sort_keys(key, end_bit)
+    ukey, seg, _count = unique_sorted(ks)
+    tarind = unpack_keys(ukey, sd_out)
+    if total:
+        c, d = gather_i32(c, permT), gather_i32(d, permT)
+    return tarind, seg, c, d
+
+
+def filter_triples(tar_ind: Tensor, ind: Tensor, b: Tensor, c: Tensor, d: Tensor, check: bool):
+    """Hadamard filter of a plan onto the pattern ``tar_ind`` (filterind); keeps order."""
+    dev = _lib.require_cuda(tar_ind, ind)
+    tkey = pack_keys(tar_ind, check=check)
+    if check:
+        assert is_sorted(tkey, strict=True), "tar_ind should be sorted and coalesce"
+    b2a = lookup_sorted(tkey, pack_keys(ind, check=check))
+    n = b.numel()
+    oa, oc, od = (_empty(n, torch.int32, dev) for _ in range(3))
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if n:
+        ws = _ws(size_query("pgh_compact_ws_bytes", n), dev)
+        _launch("pgh_compact_triples", ptr(b), ptr(b2a), ptr(c), ptr(d), n, ptr(oa), ptr(oc),
+                ptr(od), ptr(cnt), ptr(ws), ws.numel(), stream_ptr(dev))
+    T = int(cnt.item()) if n else 0
+    return oa[:T], oc[:T], od[:T]
+
+
+def filtered_plan(tar_ind: Tensor, ind1: Tensor, dim1: int, ind2: Tensor, dim2: int,
+                  k2_sorted: bool = False) -> Tuple[Tensor, TriplePlan]:
+    """Fused ``filterind(tar_ind, *spspmm_ind(ind1, dim1, ind2, dim2))`` that never
+    materialises the unfiltered product pattern: expand matches, look each output
+    coordinate up in ``tar_ind`` directly, compact, sort by output row.
+    Returns (acd int64 (3, T) in canonical order, its TriplePlan).  Two host syncs."""
+    dev = _lib.require_cuda(tar_ind, ind1, ind2)
+    c, d, total = _expand_matches(ind1, dim1, ind2, dim2, k2_sorted)
+    key = _pair_keys(ind1, dim1, ind2, dim2, c, d)
+    a = lookup_sorted(pack_keys(tar_ind), key)
+    oa, oc, od = (_empty(total, torch.int32, dev) for _ in range(3))
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if total:
+        ws = _ws(size_query("pgh_compact_ws_bytes", total), dev)
+        _launch("pgh_compact_triples", ptr(a), None, ptr(c), ptr(d), total, ptr(oa), ptr(oc),
+                ptr(od), ptr(cnt), ptr(ws), ws.numel(), stream_ptr(dev))
+    T = int(cnt.item()) if total else 0
+    oa, oc, od = oa[:T].contiguous(), oc[:T].contiguous(), od[:T].contiguous()
+    n_out = tar_ind.shape[1]
+    rowptr, perm = csr_of(oa, n_out)
+    if perm is not None:
+        oa, oc, od = gather_i32(oa, perm), gather_i32(oc, perm), gather_i32(od, perm)
+    plan = TriplePlan(T, n_out, ind1.shape[1], ind2.shape[1], oa, oc, od, sorted_by="a")
+    plan._groups["a"] = Group(rowptr, oc, od)
+    acd = torch.stack((to_i64(oa), to_i64(oc), to_i64(od))) if T else \
+        torch.zeros((3, 0), dtype=torch.int64, device=dev)
+    _cache(acd)[("acd", n_out, ind1.shape[1], ind2.shape[1])] = plan
+    return acd, plan

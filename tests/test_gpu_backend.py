@@ -1,0 +1,434 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the golden vectors
+produced by the real reference.  Indices bit-exact; fp32 values within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pygho_oracle as O
+from oracle import torch_oracle as TO
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RTOL = 1e-5
+
+
+def T(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    return t.to(dtype) if dtype is not None else t
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, rtol=RTOL):
+    a = N(a) if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = N(b) if isinstance(b, torch.Tensor) else np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(1.0, float(np.abs(b).max()) if b.size else 1.0)
+    err = float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max(initial=0.0))
+    assert err <= rtol * scale, err
+
+
+def canon(plan):
+    p = N(plan)
+    return p[:, np.lexsort((p[2], p[1], p[0]))]
+
+
+@pytest.fixture(scope="module")
+def B():
+    import pygho_b200.backend as B
+    return B
+
+
+# ------------------------------------------------------------------------------ hashing
+def test_hash_roundtrip_and_golden(B, golden):
+    g = golden("hash")
+    for sd in (2, 3, 5):
+        ind = T(g[f"ind{sd}"])
+        h = B.indicehash(ind)
+        assert np.array_equal(N(h), g[f"hash{sd}"])
+        assert np.array_equal(N(B.decodehash(h, sd)), g[f"ind{sd}"])
+        ht = B.indicehash_tight(ind, T(g[f"shape{sd}"]))
+        assert np.array_equal(N(ht), g[f"tight{sd}"])
+        assert np.array_equal(N(B.decodehash_tight(ht, T(g[f"shape{sd}"]))), g[f"ind{sd}"])
+    assert np.array_equal(N(B.ptr2batch(T(g["ptr"]), 16)), g["ptr2batch"])
+    assert np.array_equal(N(B.deg2batch(T(g["deg"]), 11)), g["deg2batch"])
+
+
+def test_hash_rejects_bad_indices(B):
+    with pytest.raises(AssertionError):
+        B.indicehash(torch.tensor([[0, -1], [1, 2]], device=DEV))
+    with pytest.raises(AssertionError):
+        B.indicehash(torch.tensor([[0, 1 << 40], [1, 2]], device=DEV))
+
+
+def test_no_cpu_fallback(B):
+    ind = torch.tensor([[0, 1], [1, 0]])
+    with pytest.raises(Exception):
+        B.SparseTensor(ind, torch.ones(2, 4), (2, 2, 4), is_coalesced=False)
+    with pytest.raises(Exception):
+        B.torch_scatter_reduce(0, torch.ones(2, 4), torch.tensor([0, 1]), 2, "sum")
+
+
+# ------------------------------------------------------------------ coalesce / create
+def test_coalesce_golden(B, golden):
+    g = golden("coalesce")
+    for red in ("sum", "mean", "max", "min"):
+        st = B.SparseTensor(T(g["ind"]), T(g["val"]), (2, 3, 5, 7), False, red)
+        assert np.array_equal(N(st.indices), g[f"ind_{red}"])
+        close(st.values, g[f"val_{red}"])
+        si = B.SparseTensor(T(g["ind"]), T(g["ival"]), (2, 3, 5), False, red)
+        assert np.array_equal(N(si.values), g[f"ival_{red}"])
+        close(B.torch_scatter_reduce(0, T(g["s_src"]), T(g["s_idx"]), 50, red), g[f"s_{red}"])
+
+
+def test_create_matches_torch_sparse(B):
+    # reference tests/test_backend_sparse.py:62-85
+    gen = torch.Generator().manual_seed(0)
+    n, m, l, nnz, d = 2, 3, 5, 23, 7
+    ind = torch.stack([torch.randint(0, s, (nnz,), generator=gen) for s in (n, m, l)])
+    val = torch.randn((nnz, d), generator=gen)
+    A1 = torch.sparse_coo_tensor(ind, val, size=(n, m, l, d)).coalesce()
+    A2 = B.SparseTensor(ind.to(DEV), val.to(DEV), (n, m, l, d), False)
+    assert torch.equal(A2.indices.cpu(), A1.indices())
+    close(A2.values, A1.values(), 5e-5)
+    A2f = B.SparseTensor.from_torch_sparse_coo(
+        torch.sparse_coo_tensor(ind, val, size=(n, m, l, d)).to(DEV))
+    assert torch.equal(A2f.indices, A2.indices)
+    close(A2f.values, A2.values)
+    close(A2.to_torch_sparse_coo().to_dense(), A1.to_dense(), 5e-5)
+
+
+# -------------------------------------------------------------------------------- plans
+def test_plans_golden(B, golden):
+    g = golden("plans")
+    for tag in ("mm10", "mm01", "mm11", "mm00", "t33", "t32"):
+        d1, d2 = (int(v) for v in g[f"{tag}_dims"])
+        tar, bcd = B.spspmm_ind(T(g[f"{tag}_i1"]), d1, T(g[f"{tag}_i2"]), d2)
+        assert np.array_equal(N(tar), g[f"{tag}_tar"]), tag
+        assert np.array_equal(canon(bcd), g[f"{tag}_bcd"]), tag
+        assert np.all(np.diff(N(bcd[0])) >= 0)
+        if f"{tag}_tgt" in g:
+            tgt = T(g[f"{tag}_tgt"])
+            assert np.array_equal(N(B.spsphadamard_ind(tgt, tar)), g[f"{tag}_b2a"])
+            assert np.array_equal(canon(B.filterind(tgt, tar, bcd)), g[f"{tag}_acd"])
+            # filterind on a plan that lost its cached int32 copy (fresh tensor)
+            assert np.array_equal(canon(B.filterind(tgt, tar, bcd.clone())), g[f"{tag}_acd"])
+    tar, bcd = B.spspmm_ind(T(g["t32_i1"]), 2, T(g["t32_i2"]), 0)
+    assert np.array_equal(canon(B.filterind(T(g["t32_i1"]), tar, bcd)), g["t32_acd"])
+
+
+def test_fused_filtered_plan_equals_two_step(B, golden):
+    from pygho_b200 import plans as P
+    g = golden("spspmm")
+    ei, tid = T(g["edge_index"]), T(g["tupleid"])
+    for tag, (i1, d1, i2, d2) in {"XA": (tid, 1, ei, 0), "AX": (ei, 1, tid, 0),
+                                  "XX": (tid, 1, tid, 0)}.items():
+        acd, plan = P.filtered_plan(tid, i1, d1, i2, d2)
+        assert np.array_equal(canon(acd), g[f"{tag}_acd"]), tag
+        assert plan.T == g[f"{tag}_acd"].shape[1]
+
+
+def test_empty_inputs(B):
+    e2 = torch.zeros((2, 0), dtype=torch.int64, device=DEV)
+    ind = torch.tensor([[0, 1, 2], [1, 2, 0]], device=DEV)
+    tar, bcd = B.spspmm_ind(ind, 1, e2, 0)
+    assert tar.shape == (2, 0) and bcd.shape == (3, 0)
+    tar, bcd = B.spspmm_ind(e2, 1, ind, 0)
+    assert tar.shape == (2, 0) and bcd.shape == (3, 0)
+    X = B.SparseTensor(e2, torch.zeros((0, 4), device=DEV), (3, 3, 4), True)
+    assert X.sum([1]).shape == (3, 4) and float(X.sum([1]).abs().sum()) == 0.0
+    out = B.torch_scatter_reduce(0, torch.zeros((0, 4), device=DEV),
+                                 torch.zeros((0,), dtype=torch.int64, device=DEV), 5, "max")
+    assert out.shape == (5, 4) and float(out.abs().sum()) == 0.0
+
+
+def test_random_2dmm_vs_dense(B):
+    # reference tests/test_backend_sparse.py:101-143
+    gen = torch.Generator().manual_seed(3)
+    n, m, l = 300, 200, 400
+    A = torch.rand((n, m), generator=gen)
+    A[torch.rand((n, m), generator=gen) > 0.1] = 0
+    Bm = torch.rand((m, l), generator=gen)
+    Bm[torch.rand((m, l), generator=gen) > 0.1] = 0
+    As, Bs = A.to_sparse_coo(), Bm.to_sparse_coo()
+    C = (A.double() @ Bm.double())
+    ind1, ind2 = As.indices().to(DEV), Bs.indices().to(DEV)
+    SA = B.SparseTensor(ind1, As.values().to(DEV).unsqueeze(-1), (n, m, 1), True)
+    SB = B.SparseTensor(ind2, Bs.values().to(DEV).unsqueeze(-1), (m, l, 1), True)
+    tar, bcd = B.spspmm_ind(ind1, 1, ind2, 0)
+    with pytest.warns(UserWarning):
+        out = B.spspmm(SA, 1, SB, 0, "sum")
+    assert torch.equal(out.indices.cpu(), C.to_sparse_coo().coalesce().indices())
+    close(out.values[:, 0], C[tuple(out.indices.cpu())].float(), 5e-5)
+    tgt = torch.stack((torch.randint(0, n, (5000,), generator=gen),
+                       torch.randint(0, l, (5000,), generator=gen))).to(DEV)
+    tgt = B.decodehash(torch.unique(B.indicehash(tgt)), 2)
+    acd = B.filterind(tgt, tar, bcd)
+    out = B.spspmm(SA, 1, SB, 0, "sum", acd=acd, tar_ind=tgt)
+    close(out.values[:, 0], C[tuple(tgt.cpu())].float(), 5e-5)
+
+
+# ---------------------------------------------------------------------------- value ops
+AGGRS = ("sum", "mean", "max", "min")
+
+
+def _sp(B, ind, val, N_):
+    return B.SparseTensor(ind, val, (N_, N_) + tuple(val.shape[1:]) if val is not None else (N_, N_), True)
+
+
+def test_value_ops_golden(B, golden):
+    g = golden("spspmm")
+    Nn = int(g["N"])
+    ei, tid = T(g["edge_index"]), T(g["tupleid"])
+    A, X = _sp(B, ei, T(g["Av"]), Nn), _sp(B, tid, T(g["Xv"]), Nn)
+    x = T(g["x"])
+    ops = {"XA": (X, 1, A, 0), "AX": (A, 1, X, 0), "XX": (X, 1, X, 0)}
+    for tag, (P_, d1, Q_, d2) in ops.items():
+        acd = T(g[f"{tag}_acd"])
+        for aggr in AGGRS:
+            out = B.spspmm(P_, d1, Q_, d2, aggr, acd=acd, tar_ind=tid)
+            assert out.indices is tid and out.shape == (Nn, Nn, 8)
+            close(out.values, g[f"{tag}_{aggr}"])
+    Aone = _sp(B, ei, None, Nn)
+    close(B.spspmm(X, 1, Aone, 0, "sum", acd=T(g["XA_acd"]), tar_ind=tid).values, g["XA_sum_noB"])
+    close(B.spspmm(Aone, 1, X, 0, "max", acd=T(g["AX_acd"]), tar_ind=tid).values,
+          O.spspmm(None, g["Xv"], g["AX_acd"], tid.shape[1], "max"))
+    with pytest.warns(UserWarning):
+        full = B.spspmm(X, 1, A, 0, "sum")
+    assert np.array_equal(N(full.indices), g["XA_full_tar"])
+    close(full.values, g["XA_full_sum"])
+    H = B.spsphadamard(X, _sp(B, T(g["had_ind2"]), T(g["had_val2"]), Nn))
+    assert np.array_equal(N(H.indices), g["had_ind"])
+    close(H.values, g["had_val"])
+    for aggr in ("sum", "mean", "max"):
+        close(B.spmm(A, 1, x, aggr), g[f"spmm1_{aggr}"])
+        close(B.spmm(A, 0, x, aggr), g[f"spmm0_{aggr}"])
+        close(getattr(X, aggr)([1]), g[f"pool1_{aggr}"])
+        close(getattr(X, aggr)([0]), g[f"pool0_{aggr}"])
+    A1 = B.SparseTensor(ei, T(g["Av"])[:, :1].contiguous(), (Nn, Nn, 1), True)
+    close(B.spmm(A1, 1, x), g["spmm1_scalar"])
+    close(B.spmm(Aone, 1, x), g["spmm1_noval"])
+    close(X.unpooling_fromdense1dim(0, x).values, g["unpool0"])
+    close(X.unpooling_fromdense1dim(1, x).values, g["unpool1"])
+    close(B.torch_scatter_reduce(0, x, T(g["batch"]), int(g["batch"].max()) + 1, "sum"),
+          g["readout_sum"])
+
+
+def test_3d_tuples_golden(B, golden):
+    g = golden("tuples3d")
+    Nn = int(g["N"])
+    ei, tid = T(g["edge_index"]), T(g["tupleid"])
+    A = B.SparseTensor(ei, T(g["Av"]), (Nn, Nn, 4), True)
+    X = B.SparseTensor(tid, T(g["Xv"]), (Nn, Nn, Nn, 4), True)
+    acd = B.filterind(tid, *B.spspmm_ind(tid, 2, ei, 0))
+    assert np.array_equal(canon(acd), g["acd"])
+    for aggr in ("sum", "max"):
+        close(B.spspmm(X, 2, A, 0, aggr, acd=acd, tar_ind=tid).values, g[f"mp_{aggr}"])
+    for aggr in ("sum", "mean", "max"):
+        Pp = getattr(X, aggr)([2], return_sparse=True)
+        assert np.array_equal(N(Pp.indices), g[f"pool2s_ind_{aggr}"])
+        close(Pp.values, g[f"pool2s_val_{aggr}"])
+        close(getattr(X, aggr)([1, 2]), g[f"pool12_{aggr}"])
+        close(getattr(X, aggr)([2]), g[f"pool2_{aggr}"])
+    Pp = X.sum([2], return_sparse=True)
+    close(Pp.unpooling([2], X).values, g["unpool_sp"])
+
+
+def _rand_problem(seed, n_out=97, n_a=61, n_b=43, T_=700, d=12, ties=False):
+    gen = torch.Generator().manual_seed(seed)
+    acd = torch.stack((torch.randint(0, n_out, (T_,), generator=gen),
+                       torch.randint(0, n_a, (T_,), generator=gen),
+                       torch.randint(0, n_b, (T_,), generator=gen)))
+    if ties:  # small integer values -> many equal products
+        a = torch.randint(-2, 3, (n_a, d), generator=gen).float()
+        b = torch.randint(-2, 3, (n_b, d), generator=gen).float()
+    else:
+        a, b = torch.randn((n_a, d), generator=gen), torch.randn((n_b, d), generator=gen)
+    return acd, a, b
+
+
+@pytest.mark.parametrize("aggr", AGGRS)
+@pytest.mark.parametrize("d", [1, 3, 8, 12, 128, 200])
+@pytest.mark.parametrize("ties", [False, True])
+def test_seg_gmr_forward_backward_vs_torch(aggr, d, ties):
+    """Unsorted random plan, every aggregation and width: values and both operand
+    gradients against torch autograd on the CPU (the reference's own ATen ops)."""
+    from pygho_b200 import plans as P
+    from pygho_b200.ops import seg_gmr
+    acd, a, b = _rand_problem(d * 7 + len(aggr), d=d, ties=ties)
+    n_out = 97
+    a_ref, b_ref = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = TO.spspmm(a_ref, b_ref, acd, n_out, aggr)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    (ref * w).sum().backward()
+    a_g, b_g = a.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    plan = P.plan_from_acd(acd.to(DEV), n_out, a.shape[0], b.shape[0])
+    out = seg_gmr(a_g, b_g, plan, aggr)
+    (out * w.to(DEV)).sum().backward()
+    close(out, ref)
+    close(a_g.grad, a_ref.grad, 2e-5)
+    close(b_g.grad, b_ref.grad, 2e-5)
+    # single-operand forms
+    a_ref2 = a.clone().requires_grad_(True)
+    ref2 = TO.spspmm(a_ref2, None, acd, n_out, aggr)
+    (ref2 * w).sum().backward()
+    a_g2 = a.to(DEV).requires_grad_(True)
+    out2 = seg_gmr(a_g2, None, plan, aggr)
+    (out2 * w.to(DEV)).sum().backward()
+    close(out2, ref2)
+    close(a_g2.grad, a_ref2.grad, 2e-5)
+    b_ref3 = b.clone().requires_grad_(True)
+    ref3 = TO.spspmm(None, b_ref3, acd, n_out, aggr)
+    (ref3 * w).sum().backward()
+    b_g3 = b.to(DEV).requires_grad_(True)
+    out3 = seg_gmr(None, b_g3, plan, aggr)
+    (out3 * w.to(DEV)).sum().backward()
+    close(out3, ref3)
+    close(b_g3.grad, b_ref3.grad, 2e-5)
+
+
+def test_deterministic(B, golden):
+    g = golden("spspmm")
+    Nn = int(g["N"])
+    ei, tid = T(g["edge_index"]), T(g["tupleid"])
+    A, X = _sp(B, ei, T(g["Av"]), Nn), _sp(B, tid, T(g["Xv"]), Nn)
+    acd = T(g["XX_acd"])
+    outs = [B.spspmm(X, 1, X, 0, "sum", acd=acd.clone(), tar_ind=tid).values for _ in range(3)]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("aggr", ("sum", "mean", "max"))
+def test_spmm_pool_unpool_gradients(B, golden, aggr):
+    g = golden("spspmm")
+    Nn = int(g["N"])
+    ei_c, tid_c = torch.from_numpy(g["edge_index"]), torch.from_numpy(g["tupleid"])
+    Av, Xv, x = (torch.from_numpy(g[k]) for k in ("Av", "Xv", "x"))
+    w = torch.randn((Nn, 8), generator=torch.Generator().manual_seed(2))
+    for dim1 in (0, 1):
+        av, xr = Av.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        (TO.spmm(ei_c, av, (Nn, Nn), dim1, xr, aggr) * w).sum().backward()
+        avg, xg = Av.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+        A = B.SparseTensor(ei_c.to(DEV), avg, (Nn, Nn, 8), True)
+        (B.spmm(A, dim1, xg, aggr) * w.to(DEV)).sum().backward()
+        close(avg.grad, av.grad, 2e-5)
+        close(xg.grad, xr.grad, 2e-5)
+    for keep in (0, 1):
+        xv = Xv.clone().requires_grad_(True)
+        (TO.sp_pool(tid_c, xv, (Nn, Nn), keep, aggr) * w).sum().backward()
+        xvg = Xv.to(DEV).requires_grad_(True)
+        X = B.SparseTensor(tid_c.to(DEV), xvg, (Nn, Nn, 8), True)
+        (getattr(X, aggr)([1 - keep]) * w.to(DEV)).sum().backward()
+        close(xvg.grad, xv.grad, 2e-5)
+        xr = x.clone().requires_grad_(True)
+        w2 = torch.randn((tid_c.shape[1], 8), generator=torch.Generator().manual_seed(3))
+        (TO.sp_unpool(tid_c, keep, xr) * w2).sum().backward()
+        xg = x.to(DEV).requires_grad_(True)
+        (X.unpooling_fromdense1dim(keep, xg).values * w2.to(DEV)).sum().backward()
+        close(xg.grad, xr.grad, 2e-5)
+
+
+def test_full_size_properties(B):
+    """BASELINE-size batch (B=1024 graphs): properties that do not need the oracle --
+    linearity of sum, mean*count == sum, max >= mean, plan totals, sortedness."""
+    from pygho_b200.hodata.synthetic import make_batch
+    hb = make_batch(1024, seed=0)
+    ei, tid = T(hb.edge_index), T(hb.tupleid)
+    Nn, d = hb.num_nodes, 128
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    Xv = torch.randn((tid.shape[1], d), device=DEV, generator=gen)
+    Av = torch.randn((ei.shape[1], d), device=DEV, generator=gen)
+    tar, bcd = B.spspmm_ind(tid, 1, ei, 0)
+    acd = B.filterind(tid, tar, bcd)
+    assert bool((acd[0][1:] >= acd[0][:-1]).all())
+    assert bool((tid[1][acd[1]] == ei[0][acd[2]]).all())          # contracted index matches
+    assert bool((tid[0][acd[1]] == tid[0][acd[0]]).all()) and bool((ei[1][acd[2]] == tid[1][acd[0]]).all())
+    X, A = _sp(B, tid, Xv, Nn), _sp(B, ei, Av, Nn)
+    s1 = B.spspmm(X, 1, A, 0, "sum", acd=acd, tar_ind=tid).values
+    X2 = _sp(B, tid, 2.0 * Xv, Nn)
+    s2 = B.spspmm(X2, 1, A, 0, "sum", acd=acd, tar_ind=tid).values
+    assert torch.equal(s2, 2.0 * s1)                               # exact: scaling by 2
+    cnt = torch.bincount(acd[0], minlength=tid.shape[1]).clamp_min(1).unsqueeze(1)
+    mean = B.spspmm(X, 1, A, 0, "mean", acd=acd, tar_ind=tid).values
+    close(mean * cnt, s1, 1e-5)
+    mx = B.spspmm(X, 1, A, 0, "max", acd=acd, tar_ind=tid).values
+    mn = B.spspmm(X, 1, A, 0, "min", acd=acd, tar_ind=tid).values
+    assert bool((mx >= mn).all()) and bool((mx + 1e-4 >= mean).all())
+    # checksum of checksums: total of the sum-aggregated output == total of all messages
+    tot = (Xv[acd[1]].double() * Av[acd[2]].double()).sum()
+    assert abs(float(s1.double().sum() - tot)) <= 1e-6 * float(
+        (Xv[acd[1]].double() * Av[acd[2]].double()).abs().sum())
+    pooled = X.sum([1])
+    close(pooled.double().sum(0), Xv.double().sum(0), 1e-5)
+
+
+# -------------------------------------------------------------------------------- masked
+def test_masked_golden(B, golden):
+    g = golden("masked")
+    A, Bm, mask = T(g["A"]), T(g["B"]), T(g["mask"])
+    MA, MB = B.MaskedTensor(A, mask), B.MaskedTensor(Bm, mask)
+    for d1 in (1, 2):
+        for d2 in (1, 2):
+            close(B.mamamm(MA, d1, MB, d2, mask).data, g[f"mm_{d1}{d2}"])
+    for aggr in ("sum", "mean", "max"):
+        for dims in ((1,), (2,), (1, 2)):
+            tag = "".join(map(str, dims))
+            r = getattr(MA, aggr)(list(dims))
+            assert np.array_equal(N(r.mask), g[f"pool{tag}_mask"])
+            sel = g[f"pool{tag}_mask"][..., None]
+            close(np.where(sel, N(r.data), 0), np.where(sel, g[f"pool{tag}_{aggr}"], 0))
+    close(MA.min([2]).data, g["pool2_min"])
+    close(B.MaskedTensor(A, mask, padvalue=float("inf")).fill_masked(1024), g["fill1024"])
+    assert np.array_equal(N(B.filterinf(T(g["filterinf_in"]))), g["filterinf_out"])
+
+
+def test_masked_constructor_fills_pads(B):
+    data = torch.ones((2, 3, 3, 4), device=DEV)
+    mask = torch.zeros((2, 3, 3), dtype=torch.bool, device=DEV)
+    mask[0, :2, :2] = True
+    mt = B.MaskedTensor(data, mask)
+    assert float(mt.data.sum()) == 16.0                       # intended semantics (Q1)
+    assert float(mt.fill_masked(5.0).sum()) == 16.0 + 5.0 * (72 - 16)
+
+
+@pytest.mark.parametrize("d1,d2", [(2, 1), (1, 1), (1, 2), (2, 2)])
+def test_mamamm_forward_backward(B, d1, d2):
+    gen = torch.Generator().manual_seed(d1 * 3 + d2)
+    b, n, d = 5, 11, 40
+    sizes = torch.randint(3, n + 1, (b,), generator=gen)
+    ar = torch.arange(n)
+    mask = (ar[None, :, None] < sizes[:, None, None]) & (ar[None, None, :] < sizes[:, None, None])
+    a = torch.randn((b, n, n, d), generator=gen) * mask.unsqueeze(-1)
+    bb = torch.randn((b, n, n, d), generator=gen) * mask.unsqueeze(-1)
+    w = torch.randn((b, n, n, d), generator=gen)
+    ar_, br_ = a.clone().requires_grad_(True), bb.clone().requires_grad_(True)
+    ref = TO.mamamm(ar_ * mask.unsqueeze(-1), d1, br_ * mask.unsqueeze(-1), d2, mask)
+    (ref * w).sum().backward()
+    ag, bg = a.to(DEV).requires_grad_(True), bb.to(DEV).requires_grad_(True)
+    mk = mask.to(DEV)
+    out = B.mamamm(B.MaskedTensor(ag, mk), d1, B.MaskedTensor(bg, mk), d2, mk)
+    (out.data * w.to(DEV)).sum().backward()
+    close(out.data, ref, 2e-5)
+    close(ag.grad, ar_.grad, 2e-5)
+    close(bg.grad, br_.grad, 2e-5)
+
+
+@pytest.mark.parametrize("aggr", AGGRS)
+@pytest.mark.parametrize("dims", [(1,), (2,), (1, 2)])
+def test_masked_pool_forward_backward(B, aggr, dims):
+    gen = torch.Generator().manual_seed(5)
+    b, n, d = 4, 9, 24
+    mask = torch.rand((b, n, n), generator=gen) < 0.6
+    mask[0] = False                                          # a fully masked graph
+    data = torch.randn((b, n, n, d), generator=gen)
+    ref_in = data.clone().requires_grad_(True)
+    ref = TO.ma_pool(ref_in * mask.unsqueeze(-1), mask, dims, aggr)
+    w = torch.randn(ref.shape, generator=gen)
+    (ref * w).sum().backward()
+    dg = data.to(DEV).requires_grad_(True)
+    r = getattr(B.MaskedTensor(dg, mask.to(DEV)), aggr)(list(dims))
+    (r.data * w.to(DEV)).sum().backward()
+    close(r.data, ref, 2e-5)
+    assert torch.equal(r.mask.cpu(), mask.any(dim=dims))
+    close(dg.grad, ref_in.grad, 2e-5)
