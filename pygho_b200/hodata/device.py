@@ -1,0 +1,107 @@
+"""Host batch -> device ``datadict`` (the contract of reference ``hodata/SpData.py:80-112``
+/ ``MaData.py:200-255`` + ``Wrapper.py:90-98``), PyG-free.
+
+``sp_datadict`` wraps the concatenated index arrays into ``SparseTensor`` objects and
+makes sure every requested ``<key>___acd`` plan exists: either the host batch already
+carries it (the reference precomputes plans per graph on the CPU and ships them with
+every batch) or it is built on the device by the fused plan kernels."""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+import torch
+
+from .. import plans as P
+from ..backend.MaTensor import MaskedTensor
+from ..backend.SpTensor import SparseTensor
+from ..honn.SpOperator import KEYSEP
+from .synthetic import HostBatch
+
+
+def parse_key(key: str):
+    """``op0___op1___dim1___op2___dim2`` (reference hodata/SpData.py:34-53)."""
+    parts = key.split(KEYSEP)
+    assert len(parts) == 5, "key format not match"
+    op0, op1, dim1, op2, dim2 = parts
+    for op in (op0, op1, op2):
+        if not (op == "A" or op.startswith("X")):
+            raise NotImplementedError(f"operator name {op} not implemented now")
+    return op0, op1, int(dim1), op2, int(dim2)
+
+
+def _h2d(arr: np.ndarray, device, pinned: Optional[Dict[int, torch.Tensor]] = None):
+    t = torch.from_numpy(arr)
+    if pinned is not None:
+        p = pinned.get(id(arr))
+        if p is None:
+            p = t.pin_memory()
+            pinned[id(arr)] = p
+        t = p
+    return t.to(device, non_blocking=True)
+
+
+def sp_datadict(hb: HostBatch, device, keys: Iterable[str] = (),
+                pinned: Optional[dict] = None) -> dict:
+    """Copy a host batch to ``device`` and assemble the sparse-mode ``datadict``."""
+    N = hb.num_nodes
+    ei = _h2d(hb.edge_index, device, pinned)
+    tid = _h2d(hb.tupleid, device, pinned)
+    ea = _h2d(hb.edge_attr, device, pinned)
+    tf = _h2d(hb.tuplefeat, device, pinned)
+    sd = tid.shape[0]
+    dd = {
+        "x": _h2d(hb.x, device, pinned),
+        "A": SparseTensor(ei, ea, (N, N) + tuple(ea.shape[1:]), is_coalesced=True),
+        "X": SparseTensor(tid, tf, (N,) * sd + tuple(tf.shape[1:]), is_coalesced=True),
+        "batch": _h2d(hb.batch, device, pinned),
+        "num_graphs": hb.num_graphs,
+        "y": _h2d(hb.y, device, pinned),
+    }
+    for key in keys:
+        name = key + KEYSEP + "acd"
+        if key in hb.plans:
+            dd[name] = _h2d(hb.plans[key], device, pinned)
+            continue
+        op0, op1, dim1, op2, dim2 = parse_key(key)
+        pick = lambda op: ei if op == "A" else tid  # noqa: E731
+        acd, _plan = P.filtered_plan(pick(op0), pick(op1), dim1, pick(op2), dim2,
+                                     k2_sorted=(dim2 == 0))
+        dd[name] = acd
+    return dd
+
+
+def attach_host_plans(hb: HostBatch, datadict: dict, keys: Iterable[str]) -> None:
+    """Copy the device-built plans back into the host batch (done once per batch when a
+    dataset is prepared), so later epochs ship them like the reference's loader does."""
+    for key in keys:
+        hb.plans[key] = datadict[key + KEYSEP + "acd"].cpu().numpy()
+
+
+def ma_datadict(hb: HostBatch, device, max_dist: int = 5) -> dict:
+    """Dense-mode ``datadict``: x (b, n, 1), A (b, n, n), X (b, n, n) masked tensors padded
+    to the largest graph (reference hodata/MaData.py:109-255 ``to_dense_*``)."""
+    B = hb.num_graphs
+    sizes = np.diff(hb.node_ptr)
+    n = int(sizes.max())
+    x = np.zeros((B, n, 1), dtype=np.int64)
+    A = np.zeros((B, n, n), dtype=np.int64)
+    X = np.zeros((B, n, n), dtype=np.int64)
+    nmask = np.arange(n)[None, :] < sizes[:, None]
+    g_of_node = hb.batch
+    local = np.arange(hb.num_nodes) - hb.node_ptr[g_of_node]
+    x[g_of_node, local, 0] = hb.x
+    ge = g_of_node[hb.edge_index[0]]
+    A[ge, hb.edge_index[0] - hb.node_ptr[ge], hb.edge_index[1] - hb.node_ptr[ge]] = hb.edge_attr
+    gt = g_of_node[hb.tupleid[0]]
+    X[gt, hb.tupleid[0] - hb.node_ptr[gt], hb.tupleid[1] - hb.node_ptr[gt]] = \
+        np.minimum(hb.tuplefeat, max_dist) + 1
+    m2 = nmask[:, :, None] & nmask[:, None, :]
+    to = lambda a: torch.from_numpy(a).to(device)  # noqa: E731
+    return {
+        "x": MaskedTensor(to(x), to(nmask), 0, True),
+        "A": MaskedTensor(to(A), to(m2), 0, True),
+        "X": MaskedTensor(to(X), to(m2), 0, True),
+        "num_graphs": B,
+        "y": to(hb.y),
+    }

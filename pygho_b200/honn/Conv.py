@@ -1,0 +1,126 @@
+"""High-order GNN layers assembled from the tensor operators (reference
+``pygho/honn/Conv.py``: ``NGNNConv`` :20-58, ``SSWLConv`` :62-103, ``I2Conv`` :107-147,
+``DSSGNNConv`` :151-196, ``PPGNConv`` :200-236, ``GNNAKConv`` :240-298).  Every layer has
+the signature ``forward(A, X, datadict) -> SparseTensor | MaskedTensor``."""
+from __future__ import annotations
+
+from typing import Callable, Optional, Union
+
+from torch.nn import Module
+
+from ..backend.MaTensor import MaskedTensor
+from ..backend.SpTensor import SparseTensor
+from . import TensorOp
+from .utils import MLP
+
+AnyTensor = Union[SparseTensor, MaskedTensor]
+
+
+class NGNNConv(Module):
+    """Nested GNN: an MLP on every tuple, then message passing inside each subgraph."""
+
+    def __init__(self, indim: int, outdim: int, aggr: str = "sum", mode: str = "SS",
+                 mlp: dict = {}, optuplefeat: str = "X", opadj: str = "A",
+                 message_func: Optional[Callable] = None):
+        super().__init__()
+        self.aggr = TensorOp.OpMessagePassingOnSubg2D(mode, aggr, optuplefeat, opadj, message_func)
+        self.lin = MLP(indim, outdim, **mlp)
+
+    def forward(self, A: AnyTensor, X: AnyTensor, datadict: dict) -> AnyTensor:
+        h = X.tuplewiseapply(self.lin)
+        return self.aggr.forward(A, h, datadict, h)
+
+
+class SSWLConv(Module):
+    """Subgraph WL (SSWL+): [X, X A (inside subgraphs), A X (across subgraphs)] -> MLP."""
+
+    def __init__(self, indim: int, outdim: int, aggr: str = "sum", mode: str = "SS",
+                 mlp: dict = {}, optuplefeat: str = "X", opadj: str = "A"):
+        super().__init__()
+        self.aggr1 = TensorOp.OpMessagePassingOnSubg2D(mode, aggr, optuplefeat, opadj)
+        self.aggr2 = TensorOp.OpMessagePassingCrossSubg2D(mode, aggr, optuplefeat, opadj)
+        self.lin = MLP(3 * indim, outdim, **mlp)
+
+    def forward(self, A: AnyTensor, X: AnyTensor, datadict: dict) -> AnyTensor:
+        inside = self.aggr1.forward(A, X, datadict, X)
+        across = self.aggr2.forward(A, X, datadict, X)
+        return X.catvalue([inside, across], True).tuplewiseapply(self.lin)
+
+
+class I2Conv(Module):
+    """I2-GNN layer on 3-D tuples: MLP, then message passing over the last tuple dim."""
+
+    def __init__(self, indim: int, outdim: int, aggr: str = "sum", mode: str = "SS",
+                 mlp: dict = {}, optuplefeat: str = "X", opadj: str = "A"):
+        super().__init__()
+        self.aggr = TensorOp.OpMessagePassingOnSubg3D(mode, aggr, optuplefeat, opadj)
+        self.lin = MLP(indim, outdim, **mlp)
+
+    def forward(self, A: AnyTensor, X: AnyTensor, datadict: dict) -> AnyTensor:
+        h = X.tuplewiseapply(self.lin)
+        return self.aggr.forward(A, h, datadict, h)
+
+
+class DSSGNNConv(Module):
+    """DSS-GNN / ESAN: subgraph message passing plus a global branch (pool across
+    subgraphs -> node message passing -> unpool to every subgraph)."""
+
+    def __init__(self, indim: int, outdim: int, aggr_subg: str = "sum", aggr_global: str = "sum",
+                 pool: str = "mean", mode: str = "SS", mlp: dict = {}, optuplefeat: str = "X",
+                 opadj: str = "A"):
+        super().__init__()
+        self.aggr_subg = TensorOp.OpMessagePassingOnSubg2D(mode, aggr_subg, optuplefeat, opadj)
+        self.pool2global = TensorOp.OpPoolingCrossSubg2D(mode[1], pool)
+        self.aggr_global = TensorOp.OpNodeMessagePassing(mode, aggr_global)
+        self.unpooling2subg = TensorOp.OpUnpoolingRootNodes2D(mode[1])
+        self.lin = MLP(2 * indim, outdim, **mlp)
+
+    def forward(self, A: AnyTensor, X: AnyTensor, datadict: dict) -> AnyTensor:
+        shared = self.aggr_global.forward(A, self.pool2global.forward(X))
+        glob = self.unpooling2subg.forward(shared, X)
+        local = self.aggr_subg.forward(A, X, datadict, X)
+        return local.catvalue(glob, True).tuplewiseapply(self.lin)
+
+
+class PPGNConv(Module):
+    """Provably powerful GN / 2-FWL: product of two MLP branches over the middle node."""
+
+    def __init__(self, indim: int, outdim: int, aggr: str = "sum", mode: str = "SS",
+                 mlp: dict = {}, optuplefeat: str = "X"):
+        super().__init__()
+        self.op = TensorOp.Op2FWL(mode, aggr, optuplefeat)
+        self.lin1 = MLP(indim, outdim, **mlp)
+        self.lin2 = MLP(indim, outdim, **mlp)
+
+    def forward(self, A: AnyTensor, X: AnyTensor, datadict: dict) -> AnyTensor:
+        return self.op.forward(X.tuplewiseapply(self.lin1), X.tuplewiseapply(self.lin2),
+                               datadict, X)
+
+
+class GNNAKConv(Module):
+    """GNN-AK(+ctx): subgraph message passing, then [pooled subgraph, centroid (diag),
+    context (pooled across subgraphs)] broadcast back to the tuples."""
+
+    def __init__(self, indim: int, outdim: int, aggr: str = "sum", pool: str = "mean",
+                 mode: str = "SS", mlp0: dict = {}, mlp1: dict = {}, ctx: bool = True,
+                 optuplefeat: str = "X", opadj: str = "A"):
+        super().__init__()
+        self.lin0 = MLP(indim, indim, **mlp0)
+        self.aggr = TensorOp.OpMessagePassingOnSubg2D(mode, aggr, optuplefeat, opadj)
+        self.diag = TensorOp.OpDiag2D(mode[1])
+        self.pool2subg = TensorOp.OpPoolingSubg2D(mode[1], pool)
+        self.unpool4subg = TensorOp.OpUnpoolingSubgNodes2D(mode[1])
+        self.ctx = ctx
+        if ctx:
+            self.pool2node = TensorOp.OpPoolingCrossSubg2D(mode[1], pool)
+            self.unpool4rootnode = TensorOp.OpUnpoolingRootNodes2D(mode[1])
+        self.lin = MLP((3 if ctx else 2) * indim, outdim, **mlp1)
+
+    def forward(self, A: AnyTensor, X: AnyTensor, datadict: dict) -> AnyTensor:
+        X = self.aggr.forward(A, X.tuplewiseapply(self.lin0), datadict, X)
+        centroid = self.unpool4subg.forward(self.diag.forward(X), X)
+        subgraph = self.unpool4subg.forward(self.pool2subg.forward(X), X)
+        parts = [centroid]
+        if self.ctx:
+            parts.append(self.unpool4rootnode.forward(self.pool2node.forward(X), X))
+        return subgraph.catvalue(parts, True).tuplewiseapply(self.lin)

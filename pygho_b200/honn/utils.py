@@ -1,0 +1,101 @@
+"""MLP and normalisation blocks used around the tensor operators (reference
+``pygho/honn/utils.py``: ``NormMomentumScheduler`` :10, ``NoneNorm`` :36, ``BatchNorm`` :46,
+``LayerNorm`` :65, ``MLP`` :85-142).  Stock torch modules: the dense GEMM / norm kernels
+are out of the hot-path scope and are reused as they are."""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch.nn as nn
+from torch import Tensor
+
+
+class NormMomentumScheduler:
+    """Scales the momentum of every norm layer of type ``normtype`` by ``mfunc(epoch)``."""
+
+    def __init__(self, mfunc: Callable, initmomentum: float, normtype=nn.BatchNorm1d) -> None:
+        self.normtype, self.mfunc = normtype, mfunc
+        self.epoch, self.initmomentum = 0, initmomentum
+
+    def step(self, model: nn.Module):
+        ratio = self.mfunc(self.epoch)
+        if abs(ratio - 1) < 1e-6:
+            return self.initmomentum
+        momentum = self.initmomentum * ratio
+        self.epoch += 1
+        for mod in model.modules():
+            if type(mod) is self.normtype:
+                mod.momentum = momentum
+        return momentum
+
+
+class NoneNorm(nn.Module):
+    def __init__(self, dim=0, normparam=0) -> None:
+        super().__init__()
+        self.num_features = dim
+
+    def forward(self, x):
+        return x
+
+
+class BatchNorm(nn.Module):
+    """BatchNorm1d over all leading dims flattened (all tuples of the batch)."""
+
+    def __init__(self, dim, normparam=0.1) -> None:
+        super().__init__()
+        self.num_features = dim
+        self.norm = nn.BatchNorm1d(dim, momentum=normparam)
+
+    def forward(self, x: Tensor):
+        if x.dim() < 2:
+            raise NotImplementedError
+        if x.dim() == 2:
+            return self.norm(x)
+        return self.norm(x.flatten(0, -2)).reshape(x.shape)
+
+
+class LayerNorm(nn.Module):
+    def __init__(self, dim, normparam=0.1) -> None:
+        super().__init__()
+        self.num_features = dim
+        self.norm = nn.LayerNorm(dim)
+
+    def forward(self, x: Tensor):
+        return self.norm(x)
+
+
+normdict = {"bn": BatchNorm, "ln": LayerNorm, "none": NoneNorm}
+act_dict = {"relu": nn.ReLU(inplace=True), "ELU": nn.ELU(inplace=True),
+            "silu": nn.SiLU(inplace=True)}
+
+
+class MLP(nn.Module):
+    """``numlayer`` x [Linear, norm, (Dropout), act]; the last block keeps norm/act only
+    when ``tailact``.  Hidden blocks are hiddim->hiddim, the last one hiddim->outdim."""
+
+    def __init__(self, hiddim: int, outdim: int, numlayer: int, tailact: bool, dp: float = 0,
+                 norm: str = "bn", act: str = "relu", tailbias=True, normparam: float = 0.1) -> None:
+        super().__init__()
+        assert numlayer >= 0
+        if numlayer == 0:
+            assert hiddim == outdim
+            self.lins = NoneNorm()
+            return
+
+        def tail(width):
+            blk = [normdict[norm](width, normparam)]
+            if dp > 0:
+                blk.append(nn.Dropout(dp, inplace=True))
+            blk.append(act_dict[act])
+            return blk
+
+        layers = []
+        for _ in range(numlayer - 1):
+            layers += [nn.Linear(hiddim, hiddim)] + tail(hiddim)
+        layers.append(nn.Linear(hiddim, outdim, bias=tailbias))
+        if tailact:
+            layers += tail(outdim)
+        self.lins = nn.Sequential(*layers)
+
+    def forward(self, x: Tensor):
+        return self.lins(x)

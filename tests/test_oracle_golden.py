@@ -204,3 +204,61 @@ def test_scatter_empty_rows_are_zero():
     out = O.scatter_reduce(src, np.array([2, 2]), 4, "max")
     assert out.tolist() == [[0.0], [0.0], [-3.0], [0.0]]
     assert O.scatter_reduce(src[:0], np.zeros(0, dtype=np.int64), 3, "sum").shape == (3, 1)
+
+
+def test_torch_oracle_matches_golden(golden):
+    """The differentiable torch restatement agrees with the real reference's values."""
+    import torch
+    from oracle import torch_oracle as TO
+    g = golden("spspmm")
+    Tn = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    N = int(g["N"])
+    ops = {"XA": ("Xv", "Av"), "AX": ("Av", "Xv"), "XX": ("Xv", "Xv")}
+    for tag, (p, q) in ops.items():
+        for aggr in ("sum", "mean", "max", "min"):
+            out = TO.spspmm(Tn(p), Tn(q), Tn(f"{tag}_acd"), g["tupleid"].shape[1], aggr)
+            close(out.numpy(), g[f"{tag}_{aggr}"])
+    for aggr in ("sum", "mean", "max"):
+        close(TO.spmm(Tn("edge_index"), Tn("Av"), (N, N), 1, Tn("x"), aggr).numpy(), g[f"spmm1_{aggr}"])
+        close(TO.spmm(Tn("edge_index"), Tn("Av"), (N, N), 0, Tn("x"), aggr).numpy(), g[f"spmm0_{aggr}"])
+        close(TO.sp_pool(Tn("tupleid"), Tn("Xv"), (N, N), 0, aggr).numpy(), g[f"pool1_{aggr}"])
+        close(TO.sp_pool(Tn("tupleid"), Tn("Xv"), (N, N), 1, aggr).numpy(), g[f"pool0_{aggr}"])
+    m = golden("masked")
+    A, B, mask = (torch.from_numpy(m[k]) for k in ("A", "B", "mask"))
+    for d1 in (1, 2):
+        for d2 in (1, 2):
+            close(TO.mamamm(A, d1, B, d2, mask).numpy(), m[f"mm_{d1}{d2}"])
+    for aggr in ("sum", "mean", "max"):
+        for dims in ((1,), (2,), (1, 2)):
+            tag = "".join(map(str, dims))
+            sel = m[f"pool{tag}_mask"][..., None]
+            close(np.where(sel, TO.ma_pool(A, mask, dims, aggr).numpy(), 0),
+                  np.where(sel, m[f"pool{tag}_{aggr}"], 0))
+
+
+def test_oracle_convs_match_reference(golden):
+    """Forward values, input gradient and every parameter gradient of one layer of each
+    in-scope conv against the real reference layers (tests/golden/conv.npz)."""
+    import torch
+    from oracle import model_oracle as MO
+    g = golden("conv")
+    ei, tid = torch.from_numpy(g["edge_index"]), torch.from_numpy(g["tupleid"])
+    gd = {k: torch.from_numpy(v) for k, v in g.items() if k.endswith("___acd")}
+    gd.update(edge_index=ei, tupleid=tid, num_nodes=int(g["N"]))
+    mk = {"NGNN": lambda: MO.ONGNN(8, "sum", 2, 0.1), "SSWL": lambda: MO.OSSWL(8, "sum", 2, 0.1),
+          "SSWLmax": lambda: MO.OSSWL(8, "max", 2, 0.1),
+          "DSSGNN": lambda: MO.ODSSGNN(8, "sum", 2, 0.1, "mean"),
+          "PPGN": lambda: MO.OPPGN(8, "sum", 2, 0.1)}
+    for name, fn in mk.items():
+        conv = fn()
+        sd = {k[len(name) + 4:]: torch.from_numpy(v) for k, v in g.items()
+              if k.startswith(name + ".sd.")}
+        conv.load_state_dict(sd)
+        Av = torch.from_numpy(g["Av"])
+        Xv = torch.from_numpy(g["Xv"]).clone().requires_grad_(True)
+        out = conv(Av, Xv, gd)
+        (out ** 2).mean().backward()
+        close(out.detach().numpy(), g[f"{name}.out"], 2e-5)
+        close(Xv.grad.numpy(), g[f"{name}.gradX"], 2e-5)
+        for k, p in conv.named_parameters():
+            close(p.grad.numpy(), g[f"{name}.grad.{k}"], 5e-5)
