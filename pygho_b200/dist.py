@@ -1,0 +1,75 @@
+"""Data-parallel plumbing: graph sharding and a flat-bucket gradient all-reduce.
+
+The reference has no distributed code; the natural partition of
+its workload is by graph (a batch is a block-diagonal concatenation, docs/HoData.md),
+so each rank owns whole graphs, builds its own plans, and the only exchange per step is
+one all-reduce of the flattened gradient bucket (NCCL over NVLink; ``gloo`` in CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_by_cost(costs: Sequence[int], world_size: int) -> List[List[int]]:
+    """Greedy longest-processing-time partition: item ids per rank, balanced by cost
+    (use the per-graph tuple or triple count).  Deterministic."""
+    order = sorted(range(len(costs)), key=lambda i: (-int(costs[i]), i))
+    loads = [0] * world_size
+    parts: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        parts[r].append(i)
+        loads[r] += int(costs[i])
+    return [sorted(p) for p in parts]
+
+
+def shard_contiguous(n_items: int, rank: int, world_size: int) -> range:
+    """Rank r takes items [r*n/W, (r+1)*n/W)."""
+    lo = (n_items * rank) // world_size
+    hi = (n_items * (rank + 1)) // world_size
+    return range(lo, hi)
+
+
+class FlatGradBucket:
+    """All gradients of a model live in ONE contiguous buffer (``p.grad`` are views), so
+    a step needs a single all-reduce and ``zero()`` is a single memset."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dtype = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=dtype, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def allreduce_mean(self, group=None) -> None:
+        """Average gradients over the ranks (no-op without an initialised group)."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world = dist.get_world_size(group)
+        if world == 1:
+            return
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.flat.div_(world)
+
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Make every replica start from rank ``src``'s weights and buffers."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
