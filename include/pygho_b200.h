@@ -46,13 +46,16 @@ int pgh_device_info(int32_t* out5);
  *   out[r,:] = aggr_{t in seg(r)} A(t) * B(t),  seg(r) = [rowptr[r], rowptr[r+1])  or {r} if rowptr==NULL
  *   A(t) = a_val[ia(t),:] * (a_scale ? a_scale[ia(t)] : 1),  ia(t) = c ? c[t] : t
  *   B(t) = b_val ? b_val[ib(t),:] : 1,                       ib(t) = d ? d[t] : t
+ * n_entries = rowptr[n_rows] when the caller knows it (0 = unknown); it only tunes the
+ * work split (rows per warp), never the result.
  * Deterministic (sequential in t), no atomics, one coalesced store per output row.
  * Replaces gather+gather+mul+scatter_reduce_ of backend/Spspmm.py:314-315, Spmm.py:40-43,
  * the scatter of SpTensor.py:388-394 (sparse pooling), the gather of SpTensor.py:476
  * (unpooling) and every autograd replay of those (index_add_ / gather).            */
 int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float* a_scale,
                     const float* b_val, const int32_t* d, const int32_t* rowptr,
-                    int64_t n_rows, int64_t dense, int aggr, float* out, void* stream);
+                    int64_t n_rows, int64_t n_entries, int64_t dense, int aggr, float* out,
+                    void* stream);
 
 /* max/min backward, step 1: gscaled[r,:] = grad[r,:] / (#{t in seg(r): A(t)*B(t) == out[r,:]}
  *                                                       + [out[r,:] == 0])

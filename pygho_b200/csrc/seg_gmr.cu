@@ -13,6 +13,7 @@
 // 4*dense*(nA + nB + n_rows) + 4*(2T + n_rows + 1)  (SURVEY.md section 8d).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -150,6 +151,110 @@ seg_gmr_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
       }
       stv<VEC>(out + (size_t)L.row * dense + col, acc);
     }
+  }
+}
+
+// Streaming variant for dense % 128 == 0 (the benchmark width): a warp owns kRW consecutive
+// output rows and walks ALL their plan entries as one stream, kSU entries (2*kSU row loads of
+// 512 B) in flight per lane regardless of row boundaries.  The ZINC-shaped plans have ~2
+// entries per row, so batching loads across rows is what turns a latency-bound kernel
+// (rowptr -> plan -> values chain per row) into a bandwidth-bound one.  Row boundaries are
+// warp-uniform (every lane handles the same entry, lanes = columns), so the flush of a
+// finished row is a plain uniform branch and one coalesced 512 B store.
+constexpr int kMaxRW = 16;  // rows per warp upper bound (<= 31: lane i holds rowptr[r0 + i])
+constexpr int kSU = 4;      // plan entries in flight per lane (2 * kSU 128-bit loads)
+
+template <int AGGR, bool HAS_B>
+__global__ void __launch_bounds__(kThreads)
+seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
+                      const float* __restrict__ a_scale, const float* __restrict__ b_val,
+                      const int* __restrict__ d, const int* __restrict__ rowptr,
+                      long long n_rows, int dense, int rw, float* __restrict__ out) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const long long r0 = warp * rw;
+  if (r0 >= n_rows) return;
+  const int nr = (int)min((long long)rw, n_rows - r0);
+  int rp = 0;
+  if (lane <= nr) rp = rowptr ? __ldg(rowptr + r0 + lane) : (int)(r0 + lane);
+  const int e_beg = __shfl_sync(kFull, rp, 0);
+  const int e_end = __shfl_sync(kFull, rp, nr);
+  const float init = (AGGR == PGH_MAX) ? -INFINITY : (AGGR == PGH_MIN) ? INFINITY : 0.f;
+  for (int col = lane * 4; col < dense; col += 128) {
+    const float* __restrict__ a_col = a_val + col;
+    const float* __restrict__ b_col = HAS_B ? b_val + col : nullptr;
+    float* __restrict__ o_col = out + (size_t)r0 * dense + col;
+    float4 acc = make_float4(init, init, init, init);
+    int cur = 0;                                    // local index of the row being reduced
+    int cur_beg = e_beg;
+    int cur_end = __shfl_sync(kFull, rp, 1);
+// finish the current row: one coalesced 512 B store, then advance (warp-uniform)
+#define PGH_FLUSH()                                                                     \
+  do {                                                                                  \
+    const int len_ = cur_end - cur_beg;                                                 \
+    float4 r_ = acc;                                                                    \
+    if (len_ == 0) r_ = make_float4(0.f, 0.f, 0.f, 0.f);                                \
+    else if (AGGR == PGH_MEAN) {                                                        \
+      const float n_ = (float)len_;                                                     \
+      r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);                 \
+    }                                                                                   \
+    *reinterpret_cast<float4*>(o_col + (size_t)cur * dense) = r_;                       \
+    acc = make_float4(init, init, init, init);                                          \
+    ++cur;                                                                              \
+    cur_beg = cur_end;                                                                  \
+    cur_end = __shfl_sync(kFull, rp, min(cur + 1, 31));                                 \
+  } while (0)
+    for (int base = e_beg; base < e_end; base += 32) {
+      const int t = base + lane;
+      int ci = 0, di = 0;
+      float sc = 1.f;
+      if (t < e_end) {
+        ci = c ? __ldg(c + t) : t;
+        if (HAS_B) di = d ? __ldg(d + t) : t;
+        if (a_scale) sc = __ldg(a_scale + ci);
+      }
+      const int chunk = min(32, e_end - base);
+#pragma unroll 1
+      for (int k = 0; k < chunk; k += kSU) {
+        float4 av[kSU], bv[kSU];
+        float ss[kSU];
+        // all 2*kSU loads are unconditional (indices clamped to the last valid entry) so
+        // that they are issued back to back and stay in flight together
+#pragma unroll
+        for (int u = 0; u < kSU; ++u) {
+          const int kk = min(k + u, chunk - 1);
+          const int cc = __shfl_sync(kFull, ci, kk);
+          ss[u] = __shfl_sync(kFull, sc, kk);
+          av[u] = __ldg(reinterpret_cast<const float4*>(a_col + (size_t)cc * dense));
+          if (HAS_B) {
+            const int dd = __shfl_sync(kFull, di, kk);
+            bv[u] = __ldg(reinterpret_cast<const float4*>(b_col + (size_t)dd * dense));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kSU; ++u) {
+          if (k + u < chunk) {
+            const int tt = base + k + u;
+            while (tt >= cur_end) PGH_FLUSH();      // finished (or empty) rows
+            float4 m = make_float4(__fmul_rn(av[u].x, ss[u]), __fmul_rn(av[u].y, ss[u]),
+                                   __fmul_rn(av[u].z, ss[u]), __fmul_rn(av[u].w, ss[u]));
+            if (HAS_B)
+              m = make_float4(__fmul_rn(m.x, bv[u].x), __fmul_rn(m.y, bv[u].y),
+                              __fmul_rn(m.z, bv[u].z), __fmul_rn(m.w, bv[u].w));
+            if (AGGR == PGH_MAX)
+              acc = make_float4(fmaxf(acc.x, m.x), fmaxf(acc.y, m.y), fmaxf(acc.z, m.z), fmaxf(acc.w, m.w));
+            else if (AGGR == PGH_MIN)
+              acc = make_float4(fminf(acc.x, m.x), fminf(acc.y, m.y), fminf(acc.z, m.z), fminf(acc.w, m.w));
+            else
+              acc = make_float4(__fadd_rn(acc.x, m.x), __fadd_rn(acc.y, m.y),
+                                __fadd_rn(acc.z, m.z), __fadd_rn(acc.w, m.w));
+          }
+        }
+      }
+    }
+    while (cur < nr) PGH_FLUSH();
+#undef PGH_FLUSH
   }
 }
 
@@ -297,6 +402,12 @@ __global__ void seg_reduce_i64_kernel(const long long* __restrict__ val,
   out[i] = acc;
 }
 
+// test hook: PYGHO_B200_ROWWISE=1 keeps the row-per-lane-group kernel for every width
+static const bool g_force_rowwise = [] {
+  const char* e = getenv("PYGHO_B200_ROWWISE");
+  return e && e[0] == '1';
+}();
+
 struct Geometry {
   int vec, lpr;
   unsigned blocks;
@@ -319,7 +430,26 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 template <int AGGR, int VEC>
 static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, const int* c,
                        const float* a_scale, const float* b_val, const int* d,
-                       const int* rowptr, int64_t n_rows, int dense, float* out) {
+                       const int* rowptr, int64_t n_rows, int64_t n_entries, int dense,
+                       float* out) {
+  if (VEC == 4 && dense % 128 == 0 && !g_force_rowwise) {
+    // rows per warp: aim at ~32 plan entries per warp, at least 4 warps' worth of blocks per SM
+    int rw = kMaxRW;
+    if (n_entries > 0 && n_rows > 0) {
+      const double avg = (double)n_entries / (double)n_rows;
+      rw = (int)(32.0 / (avg > 0.5 ? avg : 0.5));
+      if (rw < 1) rw = 1;
+      if (rw > kMaxRW) rw = kMaxRW;
+    }
+    const unsigned nb = blocks_for(n_rows, (kThreads / 32) * rw);
+    if (b_val)
+      seg_gmr_stream_kernel<AGGR, true><<<nb, kThreads, 0, s>>>(a_val, c, a_scale, b_val, d,
+                                                                 rowptr, n_rows, dense, rw, out);
+    else
+      seg_gmr_stream_kernel<AGGR, false><<<nb, kThreads, 0, s>>>(a_val, c, a_scale, b_val, d,
+                                                                  rowptr, n_rows, dense, rw, out);
+    return;
+  }
   if (b_val)
     seg_gmr_kernel<AGGR, VEC, true><<<g.blocks, kThreads, 0, s>>>(
         a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, g.lpr, out);
@@ -350,8 +480,8 @@ extern "C" int pgh_device_info(int32_t* out5) {
 
 extern "C" int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float* a_scale,
                                const float* b_val, const int32_t* d, const int32_t* rowptr,
-                               int64_t n_rows, int64_t dense, int aggr, float* out,
-                               void* stream) {
+                               int64_t n_rows, int64_t n_entries, int64_t dense, int aggr,
+                               float* out, void* stream) {
   if (!a_val || !out) return arg_error("seg_gmr: a_val and out are required");
   if (n_rows < 0 || dense <= 0 || dense > (1 << 20)) return arg_error("seg_gmr: sizes");
   if (aggr < 0 || aggr > 3) return arg_error("seg_gmr: aggr");
@@ -359,10 +489,12 @@ extern "C" int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float
   const bool al = aligned16(a_val) && aligned16(out) && (!b_val || aligned16(b_val));
   const Geometry g = geometry(n_rows, dense, al);
   cudaStream_t s = as_stream(stream);
+  if (!rowptr) n_entries = n_rows;
 #define PGH_GMR(AG)                                                                       \
   if (g.vec == 4) launch_gmr<AG, 4>(g, s, a_val, c, a_scale, b_val, d, rowptr, n_rows,   \
-                                    (int)dense, out);                                     \
-  else launch_gmr<AG, 1>(g, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, (int)dense, out)
+                                    n_entries, (int)dense, out);                          \
+  else launch_gmr<AG, 1>(g, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, n_entries,   \
+                         (int)dense, out)
   switch (aggr) {
     case PGH_SUM: PGH_GMR(PGH_SUM); break;
     case PGH_MEAN: PGH_GMR(PGH_MEAN); break;

@@ -51,8 +51,12 @@ def _seg_gmr_cuda(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr):
         return torch.zeros((n_rows, dense), dtype=torch.float32, device=a_val.device)
     out = torch.empty((n_rows, dense), dtype=torch.float32, device=a_val.device)
     if n_rows and dense:
+        n_entries = 0
+        for idx in (c, d):
+            if idx is not None:
+                n_entries = idx.shape[0]
         call("pgh_seg_gmr_f32", ptr(a_val), ptr(c), ptr(a_scale), ptr(b_val), ptr(d),
-             ptr(rowptr), n_rows, dense, aggr, ptr(out), stream_ptr(a_val.device))
+             ptr(rowptr), n_rows, n_entries, dense, aggr, ptr(out), stream_ptr(a_val.device))
         _lib.count_launch()
     return out
 
