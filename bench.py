@@ -123,6 +123,11 @@ def oracle_train_throughput(args, steps, warmup, batch_graphs, seed=12345):
     from oracle import model_oracle as MO
     from oracle import pygho_oracle as O
     from pygho_b200.hodata.synthetic import make_batch
+    # all host threads the process may use (torchrun pins OMP_NUM_THREADS=1 by default)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     torch.manual_seed(0)
     hb = make_batch(batch_graphs, seed=seed)
     keys = {"SSWL": ["X___X___1___A___0", "X___A___1___X___0"], "NGNN": ["X___X___1___A___0"],

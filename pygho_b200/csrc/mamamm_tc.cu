@@ -1,11 +1,318 @@
-// tcgen05 / TMA tensor-core path of the 2-FWL contraction (placeholder until the UMMA
-// kernel lands; algo=1 reports "not available" so that callers fall back explicitly).
+// 2-FWL contraction on the 5th-generation tensor cores (tcgen05, TF32 in / FP32 accumulate).
+//
+//   out[b,i,k,c] = mask[b,i,k] * sum_j A'[b,i,j,c] * B'[b,j,k,c]
+//
+// The channel axis c is the contiguous one in memory and is a *batch* axis of the GEMM, so
+// the operands cannot be fed to UMMA in their global layout: a CTA takes one graph b and a
+// slab of 8 channels (one full 32 B sector per (i,j) position), reads the slab once with
+// 128-bit loads and transposes it on the fly into 8 per-channel K-major / no-swizzle UMMA
+// tiles in shared memory (core matrix = 8 rows x 16 B).  One elected thread then issues
+// M=128 x N=n_k(pad 16) x K=8 tcgen05.mma instructions, accumulators live in TMEM
+// (4 channels x N columns per round, 256 columns per CTA so two CTAs share an SM), and the
+// epilogue reads them back with tcgen05.ld (lane = output row), gathers 4 channels per
+// thread and writes masked 16 B pieces straight to global memory.
+//
+// Rows >= n_i of the M=128 tile and columns >= n_k of the N tile read whatever follows the
+// tile in shared memory: they only produce accumulator rows/columns that are never read.
+// The K padding (n_j -> multiple of 8) is zero-filled in both operands.
+//
+// HBM-bound by design (13 flop/B vs a ridge of ~200 flop/B): what matters is that every
+// byte is read once, in full sectors, and that loads of one CTA overlap the MMA/epilogue of
+// the other CTA on the SM.
 #include "common.cuh"
 
 namespace pgh {
-int mamamm_tc_launch(const float*, int, const float*, int, const unsigned char*, int64_t,
-                     int64_t, int64_t, int64_t, int64_t, float*, cudaStream_t) {
-  set_error("mamamm algo=1 (tcgen05) is not available in this build");
-  return -2;
+
+constexpr int kCS = 8;            // channels per CTA
+constexpr int kTcThreads = 256;
+constexpr int kCoreBytes = 128;   // one 8x4 fp32 core matrix
+constexpr int kTmemCols = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64))
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// kind::tf32 instruction descriptor: D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+// both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // bounded spin: a lost arrival traps instead of hanging the GPU
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+               : "r"(taddr));
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2);
+  v[3] = __uint_as_float(r3); v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5);
+  v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+
+struct TcGeom {
+  int n_i, n_j, n_k;          // logical extents of A' (n_i x n_j) and B' (n_j x n_k)
+  int k_pad, n_pad;           // K padded to 8, N padded to 16
+  int sbo;                    // bytes between 8-row groups (= k_pad/4 core matrices)
+  int ts_a, ts_b;             // bytes per channel tile
+  int off_b;                  // byte offset of the B tiles
+  int ch_round;               // channels whose accumulators fit TMEM at once
+  long long sa_i, sa_j;       // element strides of A' in units of `dense` floats
+  long long sb_j, sb_k;
+};
+
+// position (row, kcol) of a K-major no-swizzle tile -> byte offset
+__device__ __forceinline__ int tile_off(int row, int kcol, int sbo) {
+  return (row >> 3) * sbo + (kcol >> 2) * kCoreBytes + (row & 7) * 16 + (kcol & 3) * 4;
+}
+
+constexpr int kLU = 8;   // 128-bit loads in flight per thread in the load phase
+
+// Fill the 8 channel tiles of one operand.  Tile rows run over `n_rows` (i for A', k for B'),
+// the K index over [0, k_pad) with zeros beyond n_k_valid.  ROW_FAST selects which index
+// varies fastest across consecutive threads (positions are separate 32 B sectors either way;
+// the order only matters for shared-memory bank spread).
+template <bool ROW_FAST>
+__device__ __forceinline__ void load_tiles(const float* __restrict__ src, unsigned char* tiles,
+                                           int n_rows, int n_k_valid, int k_pad,
+                                           long long s_row, long long s_k, int dense, int ts,
+                                           int sbo, int tid) {
+  const int h = tid & 1;
+  const int fast_n = ROW_FAST ? n_rows : k_pad;
+  const int positions = n_rows * k_pad;
+  const int step = kTcThreads / 2;
+  int p = tid >> 1;
+  int fast = p % fast_n, slow = p / fast_n;
+  const int dfast = step % fast_n, dslow = step / fast_n;
+  const float* base = src + 4 * h;
+  unsigned char* tbase = tiles + (4 * h) * ts;
+  while (p < positions) {
+    float4 v[kLU];
+    int off[kLU];
+#pragma unroll
+    for (int u = 0; u < kLU; ++u) {
+      const int row = ROW_FAST ? fast : slow, kcol = ROW_FAST ? slow : fast;
+      const bool live = (p + u * step) < positions;
+      off[u] = live ? tile_off(row, kcol, sbo) : -1;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live && kcol < n_k_valid)
+        v[u] = __ldg(reinterpret_cast<const float4*>(
+            base + ((size_t)row * s_row + (size_t)kcol * s_k) * dense));
+      fast += dfast;
+      slow += dslow;
+      if (fast >= fast_n) { fast -= fast_n; ++slow; }
+    }
+#pragma unroll
+    for (int u = 0; u < kLU; ++u) {
+      if (off[u] >= 0) {
+        unsigned char* t = tbase + off[u];
+        *reinterpret_cast<float*>(t) = v[u].x;
+        *reinterpret_cast<float*>(t + ts) = v[u].y;
+        *reinterpret_cast<float*>(t + 2 * ts) = v[u].z;
+        *reinterpret_cast<float*>(t + 3 * ts) = v[u].w;
+      }
+    }
+    p += kLU * step;
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 2)
+mamamm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                 const unsigned char* __restrict__ mask, int dense, TcGeom g,
+                 float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long mbar_storage;
+  __shared__ uint32_t tmem_base_holder;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slabs = dense / kCS;
+  const int b = blockIdx.x / slabs;
+  const int c0 = (blockIdx.x % slabs) * kCS;
+  const uint32_t bar = smem_u32(&mbar_storage);
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_holder)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+
+  // ---- load phase: global (b, i, j, c0..c0+7) -> 8 per-channel UMMA tiles ------------
+  // item = (position, half): one 128-bit load of 4 channels, 4 scalar stores into 4 tiles.
+  // Loads are issued in batches of kLU before any store so that kLU requests per thread are
+  // in flight (the loop is otherwise a serial load -> store chain of DRAM latencies).
+  load_tiles<false>(A + (size_t)b * g.n_i * g.n_j * dense + c0, smem, g.n_i, g.n_j, g.k_pad,
+                    g.sa_i, g.sa_j, dense, g.ts_a, g.sbo, tid);
+  load_tiles<true>(B + (size_t)b * g.n_j * g.n_k * dense + c0, smem + g.off_b, g.n_k, g.n_j,
+                   g.k_pad, g.sb_k, g.sb_j, dense, g.ts_b, g.sbo, tid);
+  // make the generic-proxy smem writes visible to the tensor-core (async) proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_holder;
+
+  const uint32_t idesc = umma_idesc_tf32(128, g.n_pad);
+  const uint32_t smem_base = smem_u32(smem);
+  const int rounds = kCS / g.ch_round;
+  const int row = (warp & 3) * 32 + lane;               // TMEM lane == output row i
+  const bool row_ok = row < g.n_i;
+  const unsigned char* mrow = mask + ((size_t)b * g.n_i + (row_ok ? row : 0)) * g.n_k;
+  float* orow = out + (((size_t)b * g.n_i + (row_ok ? row : 0)) * g.n_k) * dense + c0;
+  const int kchunks = (g.n_k + 7) / 8;
+
+  for (int r = 0; r < rounds; ++r) {
+    if (tid == 0) {
+      for (int cc = 0; cc < g.ch_round; ++cc) {
+        const int ch = r * g.ch_round + cc;
+        const uint32_t ta = smem_base + ch * g.ts_a;
+        const uint32_t tb = smem_base + g.off_b + ch * g.ts_b;
+        const uint32_t td = tmem_base + (uint32_t)(cc * g.n_pad);
+        for (int ks = 0; ks < g.k_pad / 8; ++ks) {
+          // one K=8 step = 2 core matrices along K
+          const uint64_t da = umma_desc(ta + ks * 2 * kCoreBytes, kCoreBytes, g.sbo);
+          const uint64_t db = umma_desc(tb + ks * 2 * kCoreBytes, kCoreBytes, g.sbo);
+          umma_tf32(td, da, db, idesc, ks > 0 ? 1u : 0u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                   : "memory");
+    }
+    mbar_wait(bar, (uint32_t)(r & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // epilogue: warps w and w+4 share TMEM quarter (w & 3); they take alternate k-chunks
+    for (int kc = (warp >> 2); kc < kchunks; kc += 2) {
+      float v[4][8];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc < g.ch_round) {
+          const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
+                                 (uint32_t)(cc * g.n_pad + kc * 8);
+          tmem_ld8(taddr, v[cc]);
+        }
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row_ok) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int k = kc * 8 + kk;
+          if (k < g.n_k) {
+            const bool m = mrow[k] != 0;
+            float* o = orow + (size_t)k * dense + r * g.ch_round;
+            if (g.ch_round == 4) {
+              const float4 w = m ? make_float4(v[0][kk], v[1][kk], v[2][kk], v[3][kk])
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(o) = w;
+            } else {
+              for (int cc = 0; cc < g.ch_round; ++cc) o[cc] = m ? v[cc][kk] : 0.f;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+int mamamm_tc_launch(const float* A, int trans_a, const float* B, int trans_b,
+                     const unsigned char* mask, int64_t b, int64_t n_i, int64_t n_j,
+                     int64_t n_k, int64_t dense, float* out, cudaStream_t s) {
+  if (dense % kCS != 0) {
+    set_error("mamamm algo=1 needs dense %% 8 == 0");
+    return -2;
+  }
+  if (n_i > 128 || n_k > 64 || n_j > 128) {
+    set_error("mamamm algo=1 supports n_i <= 128, n_k <= 64, n_j <= 128");
+    return -2;
+  }
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
+       reinterpret_cast<uintptr_t>(out)) & 15) {
+    set_error("mamamm algo=1 needs 16-byte aligned tensors");
+    return -2;
+  }
+  TcGeom g;
+  g.n_i = (int)n_i; g.n_j = (int)n_j; g.n_k = (int)n_k;
+  g.k_pad = (int)((n_j + 7) / 8 * 8);
+  g.n_pad = (int)((n_k + 15) / 16 * 16);
+  g.sbo = g.k_pad / 4 * kCoreBytes;
+  const int groups_a = (int)((n_i + 7) / 8), groups_b = (int)((n_k + 7) / 8);
+  g.ts_a = groups_a * g.sbo;
+  g.ts_b = groups_b * g.sbo;
+  g.off_b = kCS * g.ts_a;
+  g.ch_round = (kTmemCols / g.n_pad >= 8) ? 8 : (kTmemCols / g.n_pad >= 4) ? 4 : 2;
+  if (g.ch_round == 8) g.ch_round = 4;   // epilogue gathers 4 channels per thread
+  g.sa_i = trans_a ? 1 : n_j;  g.sa_j = trans_a ? n_i : 1;
+  g.sb_j = trans_b ? 1 : n_k;  g.sb_k = trans_b ? n_j : 1;
+  // the M=128 / N=n_pad tiles read past the stored rows: keep every read inside the buffer
+  const int end_a = (kCS - 1) * g.ts_a + 16 * g.sbo;
+  const int end_b = g.off_b + (kCS - 1) * g.ts_b + (g.n_pad / 8) * g.sbo;
+  int total = g.off_b + kCS * g.ts_b;
+  if (end_a > total) total = end_a;
+  if (end_b > total) total = end_b;
+  total = (total + 127) / 128 * 128;
+  if (total > 227 * 1024) {
+    set_error("mamamm algo=1: tiles (%d bytes) exceed shared memory", total);
+    return -2;
+  }
+  static int configured = 0;
+  if (configured < total) {
+    PGH_CUDA(cudaFuncSetAttribute(mamamm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, total));
+    configured = total;
+  }
+  const unsigned grid = (unsigned)(b * (dense / kCS));
+  mamamm_tc_kernel<<<grid, kTcThreads, total, s>>>(A, B, mask, (int)dense, g, out);
+  return check_launch("mamamm_tc");
+}
+
 }  // namespace pgh

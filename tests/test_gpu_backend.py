@@ -432,3 +432,25 @@ def test_masked_pool_forward_backward(B, aggr, dims):
     close(r.data, ref, 2e-5)
     assert torch.equal(r.mask.cpu(), mask.any(dim=dims))
     close(dg.grad, ref_in.grad, 2e-5)
+
+
+@pytest.mark.parametrize("n,d", [(40, 128), (37, 64), (9, 8), (23, 16), (48, 8)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_mamamm_tcgen05_matches_fp32_kernel(n, d, ta, tb):
+    """tcgen05 TF32 path (algo 1) against the exact-fp32 kernel (algo 0): 1e-2 relative
+    (BASELINE.json: bf16/TF32 mamamm within a stated 1e-2), pads exactly zero."""
+    import pygho_b200.ops  # noqa: F401
+    gen = torch.Generator().manual_seed(n * 131 + d)
+    b = 5
+    sizes = torch.randint(max(2, n // 2), n + 1, (b,), generator=gen)
+    sizes[0] = n
+    ar = torch.arange(n)
+    mask = ((ar[None, :, None] < sizes[:, None, None]) & (ar[None, None, :] < sizes[:, None, None])).to(DEV)
+    A = (torch.randn((b, n, n, d), generator=gen).to(DEV) * mask.unsqueeze(-1)).contiguous()
+    Bm = (torch.randn((b, n, n, d), generator=gen).to(DEV) * mask.unsqueeze(-1)).contiguous()
+    ref = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, 0)
+    got = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, 1)
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 1e-2 * scale
+    assert float(got[~mask].abs().max()) == 0.0
+    torch.cuda.synchronize()
