@@ -159,10 +159,16 @@ int pgh_check_sorted_i64(const int64_t* key, int64_t n, int strict, int32_t* inf
  *   out[b,i,k,:] = mask[b,i,k] ? sum_j A'[b,i,j,:] * B'[b,j,k,:] : 0
  *   A' = A if !trans_a else A with dims 1,2 swapped (dim1==1); same for B (dim2==2).
  * Operand pads must already be zero (MaskedTensor keeps pads at padvalue 0).
+ * ext (optional, (b,3) int32) = per-graph valid extents (n_i, n_j, n_k): everything outside
+ * is known to be zero in the operands / masked in the output, so it is neither read nor
+ * multiplied (exact: the skipped terms are zeros).
  * algo 0 = CUDA-core tiled kernel (exact fp32), 1 = tcgen05 TF32 tensor-core kernel.   */
 int pgh_mamamm_f32(const float* A, int trans_a, const float* B, int trans_b,
-                   const uint8_t* mask, int64_t b, int64_t n_i, int64_t n_j, int64_t n_k,
-                   int64_t dense, int algo, float* out, void* stream);
+                   const uint8_t* mask, const int32_t* ext, int64_t b, int64_t n_i, int64_t n_j,
+                   int64_t n_k, int64_t dense, int algo, float* out, void* stream);
+/* ext2[g] = (1 + last valid row, 1 + last valid column) of a (b, n1, n2) mask */
+int pgh_mask_extents(const uint8_t* mask, int64_t b, int64_t n1, int64_t n2, int32_t* ext2,
+                     void* stream);
 
 /* masked pooling of (b, n1, n2, dense) over dim 1, dim 2 or both (backend/MaTensor.py:175-206)
  *   red_dims: 1 -> over n1 (out (b,n2,dense)), 2 -> over n2 (out (b,n1,dense)), 3 -> both (out (b,dense))

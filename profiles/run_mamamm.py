@@ -49,16 +49,20 @@ def ref_path(A, B):
 
 
 want = torch.einsum("bijd,bjkd->bikd", sets[0][0].double(), sets[0][1].double()) * mask.unsqueeze(-1)
+ext = torch.stack((sizes, sizes, sizes), 1).to(torch.int32).to(dev)
+valid_bytes = 4 * d * float((2 * sizes.double() ** 2).sum() + b * n * n) + b * n * n
 for algo in ALGOS:
-    try:
-        out = torch.ops.pygho_b200.mamamm(sets[0][0], False, sets[0][1], False, mask, algo)
-    except Exception as e:  # noqa: BLE001
-        print(f"algo {algo}: unavailable ({str(e)[:80]})")
-        continue
-    err = float((out.double() - want).abs().max() / want.abs().max())
-    us = timeit(lambda A, B: torch.ops.pygho_b200.mamamm(A, False, B, False, mask, algo))
-    print(f"algo {algo}: {us:8.1f} us  {alg_bytes / us / 1e3:7.1f} GB/s (algorithmic {alg_bytes / 1e6:.0f} MB)  "
-          f"{padded_flops / us / 1e6:6.2f} TFLOP/s padded, {useful_flops / us / 1e6:6.2f} useful  rel.err {err:.2e}")
+    for tag, e in (("full", None), ("ext ", ext)):
+        try:
+            out = torch.ops.pygho_b200.mamamm(sets[0][0], False, sets[0][1], False, mask, e, algo)
+        except Exception as ex:  # noqa: BLE001
+            print(f"algo {algo}: unavailable ({str(ex)[:80]})")
+            continue
+        err = float((out.double() - want).abs().max() / want.abs().max())
+        us = timeit(lambda A, B: torch.ops.pygho_b200.mamamm(A, False, B, False, mask, e, algo))
+        nbytes = alg_bytes if e is None else valid_bytes
+        print(f"algo {algo} {tag}: {us:8.1f} us  {nbytes / us / 1e3:7.1f} GB/s ({nbytes / 1e6:.0f} MB moved by design)  "
+              f"{padded_flops / us / 1e6:6.2f} TFLOP/s padded, {useful_flops / us / 1e6:6.2f} useful  rel.err {err:.2e}")
 us = timeit(ref_path)
 out = ref_path(*sets[0])
 err = float((out.double() - want).abs().max() / want.abs().max())

@@ -18,8 +18,9 @@ from .MaTensor import MaskedTensor
 
 
 def default_algo() -> int:
-    """0 = exact-fp32 CUDA-core kernel, 1 = tcgen05 TF32 tensor-core kernel."""
-    return int(os.environ.get("PYGHO_B200_MAMAMM_ALGO", "0"))
+    """0 = exact-fp32 CUDA-core kernel, 1 = tcgen05 TF32 tensor-core kernel (default; the
+    reference runs this contraction in TF32 too, example/zinc.py:30)."""
+    return int(os.environ.get("PYGHO_B200_MAMAMM_ALGO", "1"))
 
 
 def mamamm(A: MaskedTensor, dim1: int, B: MaskedTensor, dim2: int, mask: BoolTensor,
@@ -51,10 +52,12 @@ def mamamm(A: MaskedTensor, dim1: int, B: MaskedTensor, dim2: int, mask: BoolTen
     for s in dshape:
         dense *= int(s)
     # bring A to (b, R, n_j) or its transpose
+    m_a = m_b = None
     if ma == 3:
         trans_a = dim1 == 1
         a_rest = (tA.shape[2],) if trans_a else (tA.shape[1],)
         a3 = tA.reshape(b, tA.shape[1], tA.shape[2], dense)
+        m_a = A.mask
     else:
         assert dim1 == ma - 1, "for >2 tuple dims the contracted dim of A must be the last one"
         trans_a = False
@@ -64,6 +67,7 @@ def mamamm(A: MaskedTensor, dim1: int, B: MaskedTensor, dim2: int, mask: BoolTen
         trans_b = dim2 == 2
         b_rest = (tB.shape[1],) if trans_b else (tB.shape[2],)
         b3 = tB.reshape(b, tB.shape[1], tB.shape[2], dense)
+        m_b = B.mask
     else:
         assert dim2 == 1, "for >2 tuple dims the contracted dim of B must be dim 1"
         trans_b = False
@@ -71,6 +75,10 @@ def mamamm(A: MaskedTensor, dim1: int, B: MaskedTensor, dim2: int, mask: BoolTen
         b3 = tB.reshape(b, tB.shape[1], -1, dense)
     n_i = a3.shape[2] if trans_a else a3.shape[1]
     n_k = b3.shape[1] if trans_b else b3.shape[2]
-    out = MaMaMM.apply(a3, trans_a, b3, trans_b, mask.reshape(b, n_i, n_k), default_algo())
+    algo = default_algo()
+    if algo == 1 and (dense % 8 != 0 or n_i > 128 or n_k > 64 or a3.shape[1 if trans_a else 2] > 128):
+        algo = 0      # shapes outside the tensor-core kernel's tile limits
+    omask = mask if mask.ndim == 3 else mask.reshape(b, n_i, n_k)
+    out = MaMaMM.apply(a3, trans_a, m_a, b3, trans_b, m_b, omask, algo)
     out = out.reshape((b,) + a_rest + b_rest + tuple(dshape))
     return MaskedTensor(out, mask, 0.0, is_filled=True)

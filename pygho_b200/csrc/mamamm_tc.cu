@@ -89,12 +89,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 
 struct TcGeom {
-  int n_i, n_j, n_k;          // logical extents of A' (n_i x n_j) and B' (n_j x n_k)
-  int k_pad, n_pad;           // K padded to 8, N padded to 16
-  int sbo;                    // bytes between 8-row groups (= k_pad/4 core matrices)
-  int ts_a, ts_b;             // bytes per channel tile
+  int n_i, n_j, n_k;          // padded (tensor) extents of A' (n_i x n_j) and B' (n_j x n_k)
+  int sbo;                    // bytes between 8-row groups (= k_pad_max/4 core matrices)
+  int ts_a, ts_b;             // bytes per channel tile (odd multiple of 16 B: bank spread)
   int off_b;                  // byte offset of the B tiles
-  int ch_round;               // channels whose accumulators fit TMEM at once
+  int off_mask;               // byte offset of the staged (n_i x n_k) mask tile
   long long sa_i, sa_j;       // element strides of A' in units of `dense` floats
   long long sb_j, sb_k;
 };
@@ -104,41 +103,35 @@ __device__ __forceinline__ int tile_off(int row, int kcol, int sbo) {
   return (row >> 3) * sbo + (kcol >> 2) * kCoreBytes + (row & 7) * 16 + (kcol & 3) * 4;
 }
 
-constexpr int kLU = 8;   // 128-bit loads in flight per thread in the load phase
+constexpr int kLU = 4;   // units (one 128-bit load each) in flight per thread in the load phase
 
-// Fill the 8 channel tiles of one operand.  Tile rows run over `n_rows` (i for A', k for B'),
-// the K index over [0, k_pad) with zeros beyond n_k_valid.  ROW_FAST selects which index
-// varies fastest across consecutive threads (positions are separate 32 B sectors either way;
-// the order only matters for shared-memory bank spread).
-template <bool ROW_FAST>
+// Fill the 8 channel tiles of one operand for rows < n_rows and K columns < k_pad (zeros at
+// kcol >= n_k_valid).  A warp-wide unit is a 4-row x 4-kcol patch: lane = (r2, kq, h) with
+// h = channel half, kq = kcol & 3, r2 = row & 3, which puts the 32 lanes of every STS on 32
+// different banks (bank = kq + 4*r2 + 16*h) while each lane pair still reads one full 32 B
+// sector from global memory.
 __device__ __forceinline__ void load_tiles(const float* __restrict__ src, unsigned char* tiles,
                                            int n_rows, int n_k_valid, int k_pad,
                                            long long s_row, long long s_k, int dense, int ts,
-                                           int sbo, int tid) {
-  const int h = tid & 1;
-  const int fast_n = ROW_FAST ? n_rows : k_pad;
-  const int positions = n_rows * k_pad;
-  const int step = kTcThreads / 2;
-  int p = tid >> 1;
-  int fast = p % fast_n, slow = p / fast_n;
-  const int dfast = step % fast_n, dslow = step / fast_n;
+                                           int sbo, int warp, int lane) {
+  const int h = lane & 1, kq = (lane >> 1) & 3, r2 = lane >> 3;
+  const int kquads = k_pad >> 2, rquads = (n_rows + 3) >> 2;
+  const int units = kquads * rquads;
   const float* base = src + 4 * h;
   unsigned char* tbase = tiles + (4 * h) * ts;
-  while (p < positions) {
+  for (int u0 = warp; u0 < units; u0 += kLU * (kTcThreads / 32)) {
     float4 v[kLU];
     int off[kLU];
 #pragma unroll
     for (int u = 0; u < kLU; ++u) {
-      const int row = ROW_FAST ? fast : slow, kcol = ROW_FAST ? slow : fast;
-      const bool live = (p + u * step) < positions;
+      const int unit = u0 + u * (kTcThreads / 32);
+      const int row = (unit / kquads) * 4 + r2, kcol = (unit % kquads) * 4 + kq;
+      const bool live = unit < units && row < n_rows;
       off[u] = live ? tile_off(row, kcol, sbo) : -1;
       v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (live && kcol < n_k_valid)
         v[u] = __ldg(reinterpret_cast<const float4*>(
             base + ((size_t)row * s_row + (size_t)kcol * s_k) * dense));
-      fast += dfast;
-      slow += dslow;
-      if (fast >= fast_n) { fast -= fast_n; ++slow; }
     }
 #pragma unroll
     for (int u = 0; u < kLU; ++u) {
@@ -150,14 +143,44 @@ __device__ __forceinline__ void load_tiles(const float* __restrict__ src, unsign
         *reinterpret_cast<float*>(t + 3 * ts) = v[u].w;
       }
     }
-    p += kLU * step;
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void epilogue_round(uint32_t tmem_base, int warp, int n_pad, int n_k_valid,
+                                               bool row_ok, const unsigned char* mrow,
+                                               float* orow, int dense) {
+  const int kchunks = (n_k_valid + 7) / 8;
+  // warps w and w+4 share TMEM quarter (w & 3); they take alternate k-chunks
+  for (int kc = (warp >> 2); kc < kchunks; kc += 2) {
+    float v[CH][8];
+#pragma unroll
+    for (int cc = 0; cc < CH; ++cc)
+      tmem_ld8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cc * n_pad + kc * 8), v[cc]);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (row_ok) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const int k = kc * 8 + kk;
+        if (k < n_k_valid) {
+          const bool m = mrow[k] != 0;
+          float* o = orow + (size_t)k * dense;
+#pragma unroll
+          for (int q = 0; q < CH / 4; ++q) {
+            const float4 w = m ? make_float4(v[4 * q][kk], v[4 * q + 1][kk], v[4 * q + 2][kk], v[4 * q + 3][kk])
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(o + 4 * q) = w;
+          }
+        }
+      }
+    }
   }
 }
 
 __global__ void __launch_bounds__(kTcThreads, 2)
 mamamm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                 const unsigned char* __restrict__ mask, int dense, TcGeom g,
-                 float* __restrict__ out) {
+                 const unsigned char* __restrict__ mask, const int* __restrict__ ext, int dense,
+                 TcGeom g, float* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar_storage;
   __shared__ uint32_t tmem_base_holder;
@@ -167,6 +190,27 @@ mamamm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
   const int b = blockIdx.x / slabs;
   const int c0 = (blockIdx.x % slabs) * kCS;
   const uint32_t bar = smem_u32(&mbar_storage);
+
+  // valid extents of this graph (operand pads are zero, so only [0,ni) x [0,nj) x [0,nk) matters)
+  int ni = g.n_i, nj = g.n_j, nk = g.n_k;
+  if (ext) {
+    ni = min(max(__ldg(ext + 3 * b), 0), g.n_i);
+    nj = min(max(__ldg(ext + 3 * b + 1), 0), g.n_j);
+    nk = min(max(__ldg(ext + 3 * b + 2), 0), g.n_k);
+  }
+  float* ob = out + (size_t)b * g.n_i * g.n_k * dense + c0;
+
+  // zeros outside the valid rectangle (fire-and-forget stores, overlap with everything below)
+  {
+    const int h = tid & 1;
+    const bool empty = ni == 0 || nj == 0 || nk == 0;
+    for (int p = tid >> 1; p < g.n_i * g.n_k; p += kTcThreads / 2) {
+      const int i = p / g.n_k, k = p - i * g.n_k;
+      if (empty || i >= ni || k >= nk)
+        *reinterpret_cast<float4*>(ob + (size_t)p * dense + 4 * h) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (empty) return;
+  }
 
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -180,14 +224,20 @@ mamamm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
-  // ---- load phase: global (b, i, j, c0..c0+7) -> 8 per-channel UMMA tiles ------------
-  // item = (position, half): one 128-bit load of 4 channels, 4 scalar stores into 4 tiles.
-  // Loads are issued in batches of kLU before any store so that kLU requests per thread are
-  // in flight (the loop is otherwise a serial load -> store chain of DRAM latencies).
-  load_tiles<false>(A + (size_t)b * g.n_i * g.n_j * dense + c0, smem, g.n_i, g.n_j, g.k_pad,
-                    g.sa_i, g.sa_j, dense, g.ts_a, g.sbo, tid);
-  load_tiles<true>(B + (size_t)b * g.n_j * g.n_k * dense + c0, smem + g.off_b, g.n_k, g.n_j,
-                   g.k_pad, g.sb_k, g.sb_j, dense, g.ts_b, g.sbo, tid);
+  const int k_pad = (nj + 7) & ~7;            // K steps of 8, zero padded
+  const int n_pad = max((nk + 15) & ~15, 16); // UMMA N (multiple of 16 at M = 128)
+  const int ch_round = (kCS * n_pad <= kTmemCols) ? 8 : 4;
+
+  // ---- load phase: global (b, i, j, c0..c0+7) -> 8 per-channel UMMA tiles ----------------
+  load_tiles(A + (size_t)b * g.n_i * g.n_j * dense + c0, smem, ni, nj, k_pad, g.sa_i, g.sa_j,
+             dense, g.ts_a, g.sbo, warp, lane);
+  load_tiles(B + (size_t)b * g.n_j * g.n_k * dense + c0, smem + g.off_b, nk, nj, k_pad, g.sb_k,
+             g.sb_j, dense, g.ts_b, g.sbo, warp, lane);
+  // the mask rows are staged too: the epilogue must not pay a global-load latency per store
+  {
+    const unsigned char* mb = mask + (size_t)b * g.n_i * g.n_k;
+    for (int t = tid; t < ni * g.n_k; t += kTcThreads) smem[g.off_mask + t] = __ldg(mb + t);
+  }
   // make the generic-proxy smem writes visible to the tensor-core (async) proxy
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -195,23 +245,22 @@ mamamm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_holder;
 
-  const uint32_t idesc = umma_idesc_tf32(128, g.n_pad);
+  const uint32_t idesc = umma_idesc_tf32(128, n_pad);
   const uint32_t smem_base = smem_u32(smem);
-  const int rounds = kCS / g.ch_round;
+  const int rounds = kCS / ch_round;
   const int row = (warp & 3) * 32 + lane;               // TMEM lane == output row i
-  const bool row_ok = row < g.n_i;
-  const unsigned char* mrow = mask + ((size_t)b * g.n_i + (row_ok ? row : 0)) * g.n_k;
-  float* orow = out + (((size_t)b * g.n_i + (row_ok ? row : 0)) * g.n_k) * dense + c0;
-  const int kchunks = (g.n_k + 7) / 8;
+  const bool row_ok = row < ni;
+  const unsigned char* mrow = smem + g.off_mask + (row_ok ? row : 0) * g.n_k;
+  float* orow = ob + ((size_t)(row_ok ? row : 0) * g.n_k) * dense;
 
   for (int r = 0; r < rounds; ++r) {
     if (tid == 0) {
-      for (int cc = 0; cc < g.ch_round; ++cc) {
-        const int ch = r * g.ch_round + cc;
+      for (int cc = 0; cc < ch_round; ++cc) {
+        const int ch = r * ch_round + cc;
         const uint32_t ta = smem_base + ch * g.ts_a;
         const uint32_t tb = smem_base + g.off_b + ch * g.ts_b;
-        const uint32_t td = tmem_base + (uint32_t)(cc * g.n_pad);
-        for (int ks = 0; ks < g.k_pad / 8; ++ks) {
+        const uint32_t td = tmem_base + (uint32_t)(cc * n_pad);
+        for (int ks = 0; ks < k_pad / 8; ++ks) {
           // one K=8 step = 2 core matrices along K
           const uint64_t da = umma_desc(ta + ks * 2 * kCoreBytes, kCoreBytes, g.sbo);
           const uint64_t db = umma_desc(tb + ks * 2 * kCoreBytes, kCoreBytes, g.sbo);
@@ -223,37 +272,10 @@ mamamm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
     }
     mbar_wait(bar, (uint32_t)(r & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // epilogue: warps w and w+4 share TMEM quarter (w & 3); they take alternate k-chunks
-    for (int kc = (warp >> 2); kc < kchunks; kc += 2) {
-      float v[4][8];
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        if (cc < g.ch_round) {
-          const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) +
-                                 (uint32_t)(cc * g.n_pad + kc * 8);
-          tmem_ld8(taddr, v[cc]);
-        }
-      }
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row_ok) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const int k = kc * 8 + kk;
-          if (k < g.n_k) {
-            const bool m = mrow[k] != 0;
-            float* o = orow + (size_t)k * dense + r * g.ch_round;
-            if (g.ch_round == 4) {
-              const float4 w = m ? make_float4(v[0][kk], v[1][kk], v[2][kk], v[3][kk])
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-              *reinterpret_cast<float4*>(o) = w;
-            } else {
-              for (int cc = 0; cc < g.ch_round; ++cc) o[cc] = m ? v[cc][kk] : 0.f;
-            }
-          }
-        }
-      }
-    }
+    if (ch_round == 8)
+      epilogue_round<8>(tmem_base, warp, n_pad, nk, row_ok, mrow, orow, dense);
+    else
+      epilogue_round<4>(tmem_base, warp, n_pad, nk, row_ok, mrow, orow + r * 4, dense);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -266,8 +288,8 @@ mamamm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
 }
 
 int mamamm_tc_launch(const float* A, int trans_a, const float* B, int trans_b,
-                     const unsigned char* mask, int64_t b, int64_t n_i, int64_t n_j,
-                     int64_t n_k, int64_t dense, float* out, cudaStream_t s) {
+                     const unsigned char* mask, const int* ext, int64_t b, int64_t n_i,
+                     int64_t n_j, int64_t n_k, int64_t dense, float* out, cudaStream_t s) {
   if (dense % kCS != 0) {
     set_error("mamamm algo=1 needs dense %% 8 == 0");
     return -2;
@@ -283,24 +305,25 @@ int mamamm_tc_launch(const float* A, int trans_a, const float* B, int trans_b,
   }
   TcGeom g;
   g.n_i = (int)n_i; g.n_j = (int)n_j; g.n_k = (int)n_k;
-  g.k_pad = (int)((n_j + 7) / 8 * 8);
-  g.n_pad = (int)((n_k + 15) / 16 * 16);
-  g.sbo = g.k_pad / 4 * kCoreBytes;
+  const int k_pad = (int)((n_j + 7) / 8 * 8);
+  const int n_pad = (int)((n_k + 15) / 16 * 16);
+  g.sbo = k_pad / 4 * kCoreBytes;
   const int groups_a = (int)((n_i + 7) / 8), groups_b = (int)((n_k + 7) / 8);
-  g.ts_a = groups_a * g.sbo;
-  g.ts_b = groups_b * g.sbo;
-  g.off_b = kCS * g.ts_a;
-  g.ch_round = (kTmemCols / g.n_pad >= 8) ? 8 : (kTmemCols / g.n_pad >= 4) ? 4 : 2;
-  if (g.ch_round == 8) g.ch_round = 4;   // epilogue gathers 4 channels per thread
+  // +16 B: four tile strides = 16 banks, so the two channel halves never share a bank
+  g.ts_a = groups_a * g.sbo + 16;
+  g.ts_b = groups_b * g.sbo + 16;
+  g.off_b = (kCS * g.ts_a + 127) / 128 * 128;
   g.sa_i = trans_a ? 1 : n_j;  g.sa_j = trans_a ? n_i : 1;
   g.sb_j = trans_b ? 1 : n_k;  g.sb_k = trans_b ? n_j : 1;
   // the M=128 / N=n_pad tiles read past the stored rows: keep every read inside the buffer
   const int end_a = (kCS - 1) * g.ts_a + 16 * g.sbo;
-  const int end_b = g.off_b + (kCS - 1) * g.ts_b + (g.n_pad / 8) * g.sbo;
+  const int end_b = g.off_b + (kCS - 1) * g.ts_b + (n_pad / 8) * g.sbo;
   int total = g.off_b + kCS * g.ts_b;
   if (end_a > total) total = end_a;
   if (end_b > total) total = end_b;
   total = (total + 127) / 128 * 128;
+  g.off_mask = total;
+  total += (int)((n_i * n_k + 127) / 128 * 128);
   if (total > 227 * 1024) {
     set_error("mamamm algo=1: tiles (%d bytes) exceed shared memory", total);
     return -2;
@@ -311,7 +334,7 @@ int mamamm_tc_launch(const float* A, int trans_a, const float* B, int trans_b,
     configured = total;
   }
   const unsigned grid = (unsigned)(b * (dense / kCS));
-  mamamm_tc_kernel<<<grid, kTcThreads, total, s>>>(A, B, mask, (int)dense, g, out);
+  mamamm_tc_kernel<<<grid, kTcThreads, total, s>>>(A, B, mask, ext, (int)dense, g, out);
   return check_launch("mamamm_tc");
 }
 

@@ -17,9 +17,11 @@ constexpr int kTI = 4, kTK = 4;
 __global__ void __launch_bounds__(256)
 mamamm_simt_kernel(const float* __restrict__ A, long long sAi, long long sAj,
                    const float* __restrict__ B, long long sBj, long long sBk,
-                   const unsigned char* __restrict__ mask, int n_i, int n_j, int n_k, int dense,
-                   float* __restrict__ out) {
+                   const unsigned char* __restrict__ mask, const int* __restrict__ ext, int n_i,
+                   int n_j, int n_k, int dense, float* __restrict__ out) {
   const int b = blockIdx.x;
+  // valid extents: operand pads are zero, so the j loop can stop at the valid extent
+  const int nj_valid = ext ? min(max(ext[3 * b + 1], 0), n_j) : n_j;
   const int ch = blockIdx.y * 32 + (threadIdx.x & 31);
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const bool ch_ok = ch < dense;
@@ -36,7 +38,7 @@ mamamm_simt_kernel(const float* __restrict__ A, long long sAi, long long sAj,
 #pragma unroll
       for (int y = 0; y < kTK; ++y) acc[x][y] = 0.f;
     if (ch_ok) {
-      for (int j = 0; j < n_j; ++j) {
+      for (int j = 0; j < nj_valid; ++j) {
         float a[kTI], bb[kTK];
 #pragma unroll
         for (int x = 0; x < kTI; ++x)
@@ -149,28 +151,54 @@ __global__ void masked_fill_kernel(const float* __restrict__ data,
 }
 
 int mamamm_tc_launch(const float* A, int trans_a, const float* B, int trans_b,
-                     const unsigned char* mask, int64_t b, int64_t n_i, int64_t n_j,
-                     int64_t n_k, int64_t dense, float* out, cudaStream_t s);
+                     const unsigned char* mask, const int* ext, int64_t b, int64_t n_i,
+                     int64_t n_j, int64_t n_k, int64_t dense, float* out, cudaStream_t s);
+
+// ext[b] = (1 + last row with a valid entry, 1 + last column with a valid entry) of a
+// (b, n1, n2) mask; one CTA per graph
+__global__ void mask_extents_kernel(const unsigned char* __restrict__ mask, int n1, int n2,
+                                    int* __restrict__ ext) {
+  __shared__ int rmax, cmax;
+  if (threadIdx.x == 0) { rmax = 0; cmax = 0; }
+  __syncthreads();
+  const unsigned char* m = mask + (size_t)blockIdx.x * n1 * n2;
+  int r = 0, c = 0;
+  for (int p = threadIdx.x; p < n1 * n2; p += blockDim.x)
+    if (m[p]) { r = max(r, p / n2 + 1); c = max(c, p % n2 + 1); }
+  atomicMax(&rmax, r);
+  atomicMax(&cmax, c);
+  __syncthreads();
+  if (threadIdx.x == 0) { ext[2 * blockIdx.x] = rmax; ext[2 * blockIdx.x + 1] = cmax; }
+}
 
 }  // namespace pgh
 
 using namespace pgh;
 
+extern "C" int pgh_mask_extents(const uint8_t* mask, int64_t b, int64_t n1, int64_t n2,
+                                int32_t* ext, void* stream) {
+  if (!mask || !ext) return arg_error("mask_extents: null pointer");
+  if (b <= 0) return 0;
+  mask_extents_kernel<<<(unsigned)b, 256, 0, as_stream(stream)>>>(mask, (int)n1, (int)n2, ext);
+  return check_launch("mask_extents");
+}
+
 extern "C" int pgh_mamamm_f32(const float* A, int trans_a, const float* B, int trans_b,
-                              const uint8_t* mask, int64_t b, int64_t n_i, int64_t n_j,
-                              int64_t n_k, int64_t dense, int algo, float* out, void* stream) {
+                              const uint8_t* mask, const int32_t* ext, int64_t b, int64_t n_i,
+                              int64_t n_j, int64_t n_k, int64_t dense, int algo, float* out,
+                              void* stream) {
   if (!A || !B || !mask || !out) return arg_error("mamamm: null pointer");
   if (b < 0 || n_i <= 0 || n_j <= 0 || n_k <= 0 || dense <= 0) return arg_error("mamamm: sizes");
   if (b == 0) return 0;
   cudaStream_t s = as_stream(stream);
-  if (algo == 1) return mamamm_tc_launch(A, trans_a, B, trans_b, mask, b, n_i, n_j, n_k, dense, out, s);
+  if (algo == 1) return mamamm_tc_launch(A, trans_a, B, trans_b, mask, ext, b, n_i, n_j, n_k, dense, out, s);
   if (algo != 0) return arg_error("mamamm: algo");
   // A' (b, n_i, n_j): stored (b, n_i, n_j) or, transposed, (b, n_j, n_i)
   const long long sAi = trans_a ? 1 : n_j, sAj = trans_a ? n_i : 1;
   const long long sBj = trans_b ? 1 : n_k, sBk = trans_b ? n_j : 1;
   dim3 grid((unsigned)b, (unsigned)((dense + 31) / 32));
-  mamamm_simt_kernel<<<grid, 256, 0, s>>>(A, sAi, sAj, B, sBj, sBk, mask, (int)n_i, (int)n_j,
-                                          (int)n_k, (int)dense, out);
+  mamamm_simt_kernel<<<grid, 256, 0, s>>>(A, sAi, sAj, B, sBj, sBk, mask, ext, (int)n_i,
+                                          (int)n_j, (int)n_k, (int)dense, out);
   return check_launch("mamamm_simt");
 }
 

@@ -140,10 +140,11 @@ def _inv_count_fake(rowptr):
 
 
 # -------------------------------------------------------------------------- masked
-_LIB.define("mamamm(Tensor A, bool trans_a, Tensor B, bool trans_b, Tensor mask, int algo) -> Tensor")
+_LIB.define("mamamm(Tensor A, bool trans_a, Tensor B, bool trans_b, Tensor mask, Tensor? ext, "
+            "int algo) -> Tensor")
 
 
-def _mamamm_cuda(A, trans_a, B, trans_b, mask, algo):
+def _mamamm_cuda(A, trans_a, B, trans_b, mask, ext, algo):
     A, B = _f32c(A), _f32c(B)
     mask = mask.contiguous()
     b = A.shape[0]
@@ -153,12 +154,14 @@ def _mamamm_cuda(A, trans_a, B, trans_b, mask, algo):
         raise ValueError(f"mamamm: incompatible shapes {tuple(A.shape)} x {tuple(B.shape)}")
     if tuple(mask.shape) != (b, n_i, n_k):
         raise ValueError(f"mamamm: mask shape {tuple(mask.shape)} != {(b, n_i, n_k)}")
+    if ext is not None and (ext.dtype != torch.int32 or tuple(ext.shape) != (b, 3)):
+        raise ValueError("mamamm: ext must be an int32 tensor of shape (batch, 3)")
     dense = A.shape[3]
     out = torch.empty((b, n_i, n_k, dense), dtype=torch.float32, device=A.device)
     if out.numel():
         call("pgh_mamamm_f32", ptr(A), int(trans_a), ptr(B), int(trans_b),
-             ptr(mask.view(torch.uint8)), b, n_i, n_j, n_k, dense, algo, ptr(out),
-             stream_ptr(A.device))
+             ptr(mask.view(torch.uint8)), ptr(ext.contiguous() if ext is not None else None),
+             b, n_i, n_j, n_k, dense, algo, ptr(out), stream_ptr(A.device))
         _lib.count_launch()
     return out
 
@@ -167,10 +170,32 @@ _LIB.impl("mamamm", _mamamm_cuda, "CUDA")
 
 
 @torch.library.register_fake("pygho_b200::mamamm")
-def _mamamm_fake(A, trans_a, B, trans_b, mask, algo):
+def _mamamm_fake(A, trans_a, B, trans_b, mask, ext, algo):
     n_i = A.shape[2] if trans_a else A.shape[1]
     n_k = B.shape[1] if trans_b else B.shape[2]
     return A.new_empty((A.shape[0], n_i, n_k, A.shape[3]))
+
+
+_LIB.define("mask_extents(Tensor mask) -> Tensor")
+
+
+def _mask_extents_cuda(mask):
+    mask = mask.contiguous()
+    b, n1, n2 = mask.shape
+    ext = torch.empty((b, 2), dtype=torch.int32, device=mask.device)
+    if b:
+        call("pgh_mask_extents", ptr(mask.view(torch.uint8)), b, n1, n2, ptr(ext),
+             stream_ptr(mask.device))
+        _lib.count_launch()
+    return ext
+
+
+_LIB.impl("mask_extents", _mask_extents_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::mask_extents")
+def _mask_extents_fake(mask):
+    return mask.new_empty((mask.shape[0], 2), dtype=torch.int32)
 
 
 _LIB.define("masked_pool(Tensor data, Tensor mask, int red_dims, int aggr) -> (Tensor, Tensor)")
@@ -318,38 +343,94 @@ def seg_gmr(a_val: Optional[Tensor], b_val: Optional[Tensor], plan, aggr: str) -
     return SegGmr.apply(a_val, b_val, plan, code)
 
 
+def mask_extents(mask: Optional[Tensor]) -> Optional[Tensor]:
+    """(b, 2) int32 = 1 + last valid row / column of every graph of a (b, n1, n2) mask;
+    cached on the mask tensor (masks are shared by all layers of a model)."""
+    if mask is None:
+        return None
+    cache = getattr(mask, "_pgh_cache", None)
+    if cache is None:
+        cache = {}
+        mask._pgh_cache = cache
+    e = cache.get("ext2")
+    if e is None:
+        e = _ops.mask_extents(mask)
+        cache["ext2"] = e
+    return e
+
+
+_EXT3_CACHE = {}
+
+
+def _ext3(eX: Optional[Tensor], tx: bool, eY: Optional[Tensor], ty: bool, eM: Optional[Tensor],
+          shape) -> Optional[Tensor]:
+    """Per-graph (n_i, n_j, n_k) of X' @ Y' masked by M from the (rows, cols) extents of the
+    stored operands; ``None`` extents mean "full"."""
+    if eX is None and eY is None and eM is None:
+        return None
+    key = (id(eX), tx, id(eY), ty, id(eM), shape)
+    hit = _EXT3_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    b, n_i, n_j, n_k = shape
+    ref = eX if eX is not None else eY if eY is not None else eM
+
+    def oriented(e, trans, rows, cols):
+        if e is None:
+            return ref.new_full((b,), rows), ref.new_full((b,), cols)
+        return (e[:, 1], e[:, 0]) if trans else (e[:, 0], e[:, 1])
+
+    rX, cX = oriented(eX, tx, n_i, n_j)
+    rY, cY = oriented(eY, ty, n_j, n_k)
+    rM, cM = oriented(eM, False, n_i, n_k)
+    ext = torch.stack((torch.minimum(rX, rM), torch.minimum(cX, rY), torch.minimum(cY, cM)),
+                      dim=1).contiguous()
+    if len(_EXT3_CACHE) > 64:
+        _EXT3_CACHE.clear()
+    _EXT3_CACHE[key] = (ext, eX, eY, eM)      # keep the keyed tensors alive
+    return ext
+
+
+def _mm(X, tx, eX, Y, ty, eY, mask, eM, algo):
+    b = X.shape[0]
+    n_i, n_j = (X.shape[2], X.shape[1]) if tx else (X.shape[1], X.shape[2])
+    n_k = Y.shape[1] if ty else Y.shape[2]
+    return _ops.mamamm(X, tx, Y, ty, mask, _ext3(eX, tx, eY, ty, eM, (b, n_i, n_j, n_k)), algo)
+
+
 class MaMaMM(torch.autograd.Function):
-    """out = mask * (A' @ B') per channel; A' / B' optionally transposed in dims (1, 2)."""
+    """out = mask * (A' @ B') per channel; A' / B' optionally transposed in dims (1, 2).
+    ``mA`` / ``mB`` are the operands' own masks (or None): their per-graph extents bound
+    what the kernels read and multiply -- exact, because operand pads are zero."""
 
     @staticmethod
-    def forward(ctx, A, trans_a, B, trans_b, mask, algo):
+    def forward(ctx, A, trans_a, mA, B, trans_b, mB, mask, algo):
+        eA, eB, eM = mask_extents(mA), mask_extents(mB), mask_extents(mask)
         ctx.save_for_backward(A, B, mask)
-        ctx.cfg = (trans_a, trans_b, algo)
-        return _ops.mamamm(A, trans_a, B, trans_b, mask, algo)
+        ctx.cfg = (trans_a, trans_b, algo, eA, eB, eM)
+        return _mm(A, trans_a, eA, B, trans_b, eB, mask, eM, algo)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         A, B, mask = ctx.saved_tensors
-        trans_a, trans_b, algo = ctx.cfg
+        trans_a, trans_b, algo, eA, eB, eM = ctx.cfg
         # out is masked in the epilogue -> its gradient only exists where mask is True
         g = _ops.masked_fill_rows(g.contiguous(), mask, 0.0)
-        ones_a = _ones_mask(A)
-        ones_b = _ones_mask(B)
         g_a = g_b = None
         if ctx.needs_input_grad[0]:
             # dA'[i,j] = sum_k g[i,k] B'[j,k]  -> g @ B'^T ; stored transposed if trans_a
             if not trans_a:
-                g_a = _ops.mamamm(g, False, B, not trans_b, ones_a, algo)
+                g_a = _mm(g, False, eM, B, not trans_b, eB, _ones_mask(A), None, algo)
             else:
-                g_a = _ops.mamamm(B, trans_b, g, True, ones_a, algo)
-        if ctx.needs_input_grad[2]:
+                g_a = _mm(B, trans_b, eB, g, True, eM, _ones_mask(A), None, algo)
+        if ctx.needs_input_grad[3]:
             # dB'[j,k] = sum_i A'[i,j] g[i,k] -> A'^T @ g ; stored transposed if trans_b
             if not trans_b:
-                g_b = _ops.mamamm(A, not trans_a, g, False, ones_b, algo)
+                g_b = _mm(A, not trans_a, eA, g, False, eM, _ones_mask(B), None, algo)
             else:
-                g_b = _ops.mamamm(g, True, A, trans_a, ones_b, algo)
-        return g_a, None, g_b, None, None, None
+                g_b = _mm(g, True, eM, A, trans_a, eA, _ones_mask(B), None, algo)
+        return g_a, None, None, g_b, None, None, None, None
 
 
 _ONES_CACHE = {}

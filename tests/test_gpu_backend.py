@@ -364,13 +364,15 @@ def test_full_size_properties(B):
 
 
 # -------------------------------------------------------------------------------- masked
-def test_masked_golden(B, golden):
+@pytest.mark.parametrize("algo,tol", [(0, 1e-5), (1, 1e-2)])
+def test_masked_golden(B, golden, monkeypatch, algo, tol):
+    monkeypatch.setenv("PYGHO_B200_MAMAMM_ALGO", str(algo))
     g = golden("masked")
     A, Bm, mask = T(g["A"]), T(g["B"]), T(g["mask"])
     MA, MB = B.MaskedTensor(A, mask), B.MaskedTensor(Bm, mask)
     for d1 in (1, 2):
         for d2 in (1, 2):
-            close(B.mamamm(MA, d1, MB, d2, mask).data, g[f"mm_{d1}{d2}"])
+            close(B.mamamm(MA, d1, MB, d2, mask).data, g[f"mm_{d1}{d2}"], tol)
     for aggr in ("sum", "mean", "max"):
         for dims in ((1,), (2,), (1, 2)):
             tag = "".join(map(str, dims))
@@ -392,8 +394,10 @@ def test_masked_constructor_fills_pads(B):
     assert float(mt.fill_masked(5.0).sum()) == 16.0 + 5.0 * (72 - 16)
 
 
+@pytest.mark.parametrize("algo,tol", [(0, 2e-5), (1, 1e-2)])
 @pytest.mark.parametrize("d1,d2", [(2, 1), (1, 1), (1, 2), (2, 2)])
-def test_mamamm_forward_backward(B, d1, d2):
+def test_mamamm_forward_backward(B, monkeypatch, d1, d2, algo, tol):
+    monkeypatch.setenv("PYGHO_B200_MAMAMM_ALGO", str(algo))
     gen = torch.Generator().manual_seed(d1 * 3 + d2)
     b, n, d = 5, 11, 40
     sizes = torch.randint(3, n + 1, (b,), generator=gen)
@@ -409,9 +413,9 @@ def test_mamamm_forward_backward(B, d1, d2):
     mk = mask.to(DEV)
     out = B.mamamm(B.MaskedTensor(ag, mk), d1, B.MaskedTensor(bg, mk), d2, mk)
     (out.data * w.to(DEV)).sum().backward()
-    close(out.data, ref, 2e-5)
-    close(ag.grad, ar_.grad, 2e-5)
-    close(bg.grad, br_.grad, 2e-5)
+    close(out.data, ref, tol)
+    close(ag.grad, ar_.grad, tol)
+    close(bg.grad, br_.grad, tol)
 
 
 @pytest.mark.parametrize("aggr", AGGRS)
@@ -448,9 +452,15 @@ def test_mamamm_tcgen05_matches_fp32_kernel(n, d, ta, tb):
     mask = ((ar[None, :, None] < sizes[:, None, None]) & (ar[None, None, :] < sizes[:, None, None])).to(DEV)
     A = (torch.randn((b, n, n, d), generator=gen).to(DEV) * mask.unsqueeze(-1)).contiguous()
     Bm = (torch.randn((b, n, n, d), generator=gen).to(DEV) * mask.unsqueeze(-1)).contiguous()
-    ref = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, 0)
-    got = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, 1)
+    ref = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, None, 0)
     scale = float(ref.abs().max())
-    assert float((got - ref).abs().max()) <= 1e-2 * scale
-    assert float(got[~mask].abs().max()) == 0.0
+    ext = torch.stack((sizes, sizes, sizes), 1).to(torch.int32).to(DEV)
+    for e in (None, ext):
+        got = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, e, 1)
+        assert float((got - ref).abs().max()) <= 1e-2 * scale
+        assert float(got[~mask].abs().max()) == 0.0
+        # the fp32 kernel with extents is bit-identical to the one without
+        assert torch.equal(torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, e, 0), ref)
+    from pygho_b200.ops import mask_extents
+    assert torch.equal(mask_extents(mask).cpu(), torch.stack((sizes, sizes), 1).to(torch.int32))
     torch.cuda.synchronize()
