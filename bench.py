@@ -223,11 +223,16 @@ def roofline_spspmm(dd_list, hidden, device, peaks):
     us = e0.elapsed_time(e1) * 1e3 / iters
     achieved = alg_bytes / (us * 1e-6) / 1e9
     peak = peaks.get("hbm_gbs")
-    return {"bound": "hbm", "kernel": "seg_gmr_kernel<sum,vec4,B> (spspmm fwd, key X___X___1___A___0)",
+    traffic = None
+    try:  # dram bytes of this launch from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))["traffic"]
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": "seg_gmr_stream_kernel<sum,B> (spspmm fwd, key X___X___1___A___0)",
             "achieved": achieved, "peak": peak if peak else 6650.0, "unit": "GB/s",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peak
             else "fallback 6650 GB/s (B200_PROFILING.md)",
-            "frac": achieved / (peak if peak else 6650.0), "traffic": None,
+            "frac": achieved / (peak if peak else 6650.0), "traffic": traffic,
             "us_per_launch": us, "algorithmic_bytes": alg_bytes,
             "rows": nX, "triples": T, "operand_sets": nsets, "l2_bytes": l2}
 
