@@ -57,6 +57,13 @@ int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float* a_scale,
                     int64_t n_rows, int64_t n_entries, int64_t dense, int aggr, float* out,
                     void* stream);
 
+/* Same with explicit row strides (in floats) so operands / the output may be column slices
+ * of wider row-major tensors (e.g. one third of a concatenated feature buffer). */
+int pgh_seg_gmr_ld_f32(const float* a_val, int64_t lda, const int32_t* c, const float* a_scale,
+                       const float* b_val, int64_t ldb, const int32_t* d, const int32_t* rowptr,
+                       int64_t n_rows, int64_t n_entries, int64_t dense, int aggr, float* out,
+                       int64_t ldo, void* stream);
+
 /* max/min backward, step 1: gscaled[r,:] = grad[r,:] / (#{t in seg(r): A(t)*B(t) == out[r,:]}
  *                                                       + [out[r,:] == 0])
  * (torch's scatter_reduce amax/amin backward splits the gradient evenly among ties and
@@ -185,6 +192,27 @@ int pgh_masked_pool_bwd_f32(const float* data, const uint8_t* mask, const float*
 /* out = mask ? data : value  (MaskedTensor.fill_masked, backend/MaTensor.py:113-128) */
 int pgh_masked_fill_f32(const float* data, const uint8_t* mask, int64_t rows, int64_t dense,
                         float value, float* out, void* stream);
+
+/* ------------------------------------------------------- tuplewise MLP */
+
+/* BatchNorm1d (training mode, statistics over ALL tuples of the batch) fused with the
+ * activation that follows it in the reference MLP block Linear -> BatchNorm -> act
+ * (honn/utils.py:46-61, 85-142).  act: 0 identity, 1 SiLU, 2 ReLU.  C % 4 == 0, C <= 1024.
+ *   stats : mean[c], rstd[c] = 1/sqrt(biased var + eps); optional running-stat update
+ *   fwd   : z = act(gamma * (y - mean) * rstd + beta)
+ *   bwd   : dy (gradient w.r.t. the Linear output), dgamma, dbeta and, if dbias != NULL, the
+ *           column sums of dy (the Linear bias gradient, mathematically 0 before a BatchNorm)
+ * ws: pgh_bn_ws_bytes(rows, C) bytes of scratch for the deterministic two-stage reductions. */
+size_t pgh_bn_ws_bytes(int64_t rows, int64_t C);
+int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, float eps, float momentum,
+                     float* mean, float* rstd, float* running_mean, float* running_var, void* ws,
+                     size_t ws_bytes, void* stream);
+int pgh_bn_act_fwd_f32(const float* y, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, int64_t rows, int64_t C, int act, float* z, void* stream);
+int pgh_bn_act_bwd_f32(const float* dz, const float* y, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, int64_t rows, int64_t C, int act,
+                       float* dy, float* dgamma, float* dbeta, float* dbias, void* ws,
+                       size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

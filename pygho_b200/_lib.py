@@ -23,6 +23,7 @@ SIGNATURES = {
     "pgh_abi_version": (_i, []),
     "pgh_device_info": (_i, [_p]),
     "pgh_seg_gmr_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p, _p]),
+    "pgh_seg_gmr_ld_f32": (_i, [_p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i, _p, _i64, _p]),
     "pgh_seg_tie_scale_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "pgh_seg_select_bwd_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "pgh_inv_count_f32": (_i, [_p, _i64, _p, _p]),
@@ -53,6 +54,10 @@ SIGNATURES = {
     "pgh_masked_pool_f32": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i, _i, _p, _p, _p]),
     "pgh_masked_pool_bwd_f32": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i, _p, _p]),
     "pgh_masked_fill_f32": (_i, [_p, _p, _i64, _i64, _f, _p, _p]),
+    "pgh_bn_ws_bytes": (_sz, [_i64, _i64]),
+    "pgh_bn_stats_f32": (_i, [_p, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _sz, _p]),
+    "pgh_bn_act_fwd_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _p, _p]),
+    "pgh_bn_act_bwd_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 AGGR_CODE = {"sum": 0, "mean": 1, "max": 2, "min": 3, "amax": 2, "amin": 3}

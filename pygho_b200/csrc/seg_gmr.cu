@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreads)
 seg_gmr_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
                const float* __restrict__ a_scale, const float* __restrict__ b_val,
                const int* __restrict__ d, const int* __restrict__ rowptr, long long n_rows,
-               int dense, int lpr, float* __restrict__ out) {
+               int dense, int lda, int ldb, int ldo, int lpr, float* __restrict__ out) {
   const Lane L = lane_setup(rowptr, n_rows, lpr);
   const int colstep = lpr * VEC;
   for (int col0 = 0; col0 < dense; col0 += colstep) {
@@ -124,8 +124,8 @@ seg_gmr_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           if (ok[u]) {
-            ldv<VEC>(a_val + (size_t)cc[u] * dense + col, av[u]);
-            if (HAS_B) ldv<VEC>(b_val + (size_t)dd[u] * dense + col, bv[u]);
+            ldv<VEC>(a_val + (size_t)cc[u] * lda + col, av[u]);
+            if (HAS_B) ldv<VEC>(b_val + (size_t)dd[u] * ldb + col, bv[u]);
           }
         }
 #pragma unroll
@@ -149,7 +149,7 @@ seg_gmr_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
         if (L.len == 0) acc[v] = 0.f;
         else if (AGGR == PGH_MEAN) acc[v] = acc[v] / (float)L.len;
       }
-      stv<VEC>(out + (size_t)L.row * dense + col, acc);
+      stv<VEC>(out + (size_t)L.row * ldo + col, acc);
     }
   }
 }
@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(kThreads)
 seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
                       const float* __restrict__ a_scale, const float* __restrict__ b_val,
                       const int* __restrict__ d, const int* __restrict__ rowptr,
-                      long long n_rows, int dense, int rw, float* __restrict__ out) {
+                      long long n_rows, int dense, int lda, int ldb, int ldo, int rw,
+                      float* __restrict__ out) {
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -184,7 +185,7 @@ seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c
   for (int col = lane * 4; col < dense; col += 128) {
     const float* __restrict__ a_col = a_val + col;
     const float* __restrict__ b_col = HAS_B ? b_val + col : nullptr;
-    float* __restrict__ o_col = out + (size_t)r0 * dense + col;
+    float* __restrict__ o_col = out + (size_t)r0 * ldo + col;
     float4 acc = make_float4(init, init, init, init);
     int cur = 0;                                    // local index of the row being reduced
     int cur_beg = e_beg;
@@ -199,7 +200,7 @@ seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c
       const float n_ = (float)len_;                                                     \
       r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);                 \
     }                                                                                   \
-    *reinterpret_cast<float4*>(o_col + (size_t)cur * dense) = r_;                       \
+    *reinterpret_cast<float4*>(o_col + (size_t)cur * ldo) = r_;                         \
     acc = make_float4(init, init, init, init);                                          \
     ++cur;                                                                              \
     cur_beg = cur_end;                                                                  \
@@ -226,10 +227,10 @@ seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c
           const int kk = min(k + u, chunk - 1);
           const int cc = __shfl_sync(kFull, ci, kk);
           ss[u] = __shfl_sync(kFull, sc, kk);
-          av[u] = __ldg(reinterpret_cast<const float4*>(a_col + (size_t)cc * dense));
+          av[u] = __ldg(reinterpret_cast<const float4*>(a_col + (size_t)cc * lda));
           if (HAS_B) {
             const int dd = __shfl_sync(kFull, di, kk);
-            bv[u] = __ldg(reinterpret_cast<const float4*>(b_col + (size_t)dd * dense));
+            bv[u] = __ldg(reinterpret_cast<const float4*>(b_col + (size_t)dd * ldb));
           }
         }
 #pragma unroll
@@ -430,8 +431,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 template <int AGGR, int VEC>
 static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, const int* c,
                        const float* a_scale, const float* b_val, const int* d,
-                       const int* rowptr, int64_t n_rows, int64_t n_entries, int dense,
-                       float* out) {
+                       const int* rowptr, int64_t n_rows, int64_t n_entries, int dense, int lda,
+                       int ldb, int ldo, float* out) {
   if (VEC == 4 && dense % 128 == 0 && !g_force_rowwise) {
     // rows per warp: aim at ~32 plan entries per warp, at least 4 warps' worth of blocks per SM
     int rw = kMaxRW;
@@ -443,19 +444,19 @@ static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, co
     }
     const unsigned nb = blocks_for(n_rows, (kThreads / 32) * rw);
     if (b_val)
-      seg_gmr_stream_kernel<AGGR, true><<<nb, kThreads, 0, s>>>(a_val, c, a_scale, b_val, d,
-                                                                 rowptr, n_rows, dense, rw, out);
+      seg_gmr_stream_kernel<AGGR, true><<<nb, kThreads, 0, s>>>(
+          a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, out);
     else
-      seg_gmr_stream_kernel<AGGR, false><<<nb, kThreads, 0, s>>>(a_val, c, a_scale, b_val, d,
-                                                                  rowptr, n_rows, dense, rw, out);
+      seg_gmr_stream_kernel<AGGR, false><<<nb, kThreads, 0, s>>>(
+          a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, out);
     return;
   }
   if (b_val)
     seg_gmr_kernel<AGGR, VEC, true><<<g.blocks, kThreads, 0, s>>>(
-        a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, g.lpr, out);
+        a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, g.lpr, out);
   else
     seg_gmr_kernel<AGGR, VEC, false><<<g.blocks, kThreads, 0, s>>>(
-        a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, g.lpr, out);
+        a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, g.lpr, out);
 }
 
 }  // namespace pgh
@@ -478,23 +479,29 @@ extern "C" int pgh_device_info(int32_t* out5) {
   return 0;
 }
 
-extern "C" int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float* a_scale,
-                               const float* b_val, const int32_t* d, const int32_t* rowptr,
-                               int64_t n_rows, int64_t n_entries, int64_t dense, int aggr,
-                               float* out, void* stream) {
+extern "C" int pgh_seg_gmr_ld_f32(const float* a_val, int64_t lda, const int32_t* c,
+                                  const float* a_scale, const float* b_val, int64_t ldb,
+                                  const int32_t* d, const int32_t* rowptr, int64_t n_rows,
+                                  int64_t n_entries, int64_t dense, int aggr, float* out,
+                                  int64_t ldo, void* stream) {
   if (!a_val || !out) return arg_error("seg_gmr: a_val and out are required");
   if (n_rows < 0 || dense <= 0 || dense > (1 << 20)) return arg_error("seg_gmr: sizes");
   if (aggr < 0 || aggr > 3) return arg_error("seg_gmr: aggr");
+  if (lda < dense || ldo < dense || (b_val && ldb < dense) || lda > 0x7fffffff ||
+      ldb > 0x7fffffff || ldo > 0x7fffffff)
+    return arg_error("seg_gmr: leading dimensions");
   if (n_rows == 0) return 0;
-  const bool al = aligned16(a_val) && aligned16(out) && (!b_val || aligned16(b_val));
+  const bool al = aligned16(a_val) && aligned16(out) && (!b_val || aligned16(b_val)) &&
+                  lda % 4 == 0 && ldo % 4 == 0 && (!b_val || ldb % 4 == 0);
   const Geometry g = geometry(n_rows, dense, al);
   cudaStream_t s = as_stream(stream);
   if (!rowptr) n_entries = n_rows;
+  const int la = (int)lda, lb = (int)(b_val ? ldb : dense), lo = (int)ldo;
 #define PGH_GMR(AG)                                                                       \
   if (g.vec == 4) launch_gmr<AG, 4>(g, s, a_val, c, a_scale, b_val, d, rowptr, n_rows,   \
-                                    n_entries, (int)dense, out);                          \
+                                    n_entries, (int)dense, la, lb, lo, out);              \
   else launch_gmr<AG, 1>(g, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, n_entries,   \
-                         (int)dense, out)
+                         (int)dense, la, lb, lo, out)
   switch (aggr) {
     case PGH_SUM: PGH_GMR(PGH_SUM); break;
     case PGH_MEAN: PGH_GMR(PGH_MEAN); break;
@@ -503,6 +510,14 @@ extern "C" int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float
   }
 #undef PGH_GMR
   return check_launch("seg_gmr");
+}
+
+extern "C" int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float* a_scale,
+                               const float* b_val, const int32_t* d, const int32_t* rowptr,
+                               int64_t n_rows, int64_t n_entries, int64_t dense, int aggr,
+                               float* out, void* stream) {
+  return pgh_seg_gmr_ld_f32(a_val, dense, c, a_scale, b_val, dense, d, rowptr, n_rows, n_entries,
+                            dense, aggr, out, dense, stream);
 }
 
 extern "C" int pgh_seg_tie_scale_f32(const float* a_val, const int32_t* c, const float* b_val,

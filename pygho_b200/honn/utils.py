@@ -98,4 +98,45 @@ class MLP(nn.Module):
         self.lins = nn.Sequential(*layers)
 
     def forward(self, x: Tensor):
-        return self.lins(x)
+        if not _fusable(self.lins, x):
+            return self.lins(x)
+        # Linear -> BatchNorm(train) -> SiLU/ReLU blocks go through the fused kernels
+        # (pygho_b200/csrc/fused_mlp.cu); anything else runs module by module.
+        from ..ops import ACT_CODE, LinearBNAct
+        mods = list(self.lins)
+        shape = x.shape
+        h = x.reshape(-1, shape[-1])
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            blk = _match_block(mods, i)
+            if blk is not None:
+                bn, act = blk
+                if bn.track_running_stats:
+                    bn.num_batches_tracked.add_(1)
+                h = LinearBNAct.apply(h, m.weight, m.bias, bn.weight, bn.bias, bn.running_mean,
+                                      bn.running_var, bn.momentum, bn.eps, ACT_CODE[act])
+                i += 3
+            else:
+                h = m(h)
+                i += 1
+        return h.reshape(shape[:-1] + (h.shape[-1],))
+
+
+def _match_block(mods, i):
+    """(BatchNorm1d, act name) if mods[i:i+3] is Linear, BatchNorm(train, affine), SiLU/ReLU."""
+    if i + 2 >= len(mods) or not isinstance(mods[i], nn.Linear) or type(mods[i + 1]) is not BatchNorm:
+        return None
+    bn = mods[i + 1].norm
+    act = {nn.SiLU: "silu", nn.ReLU: "relu"}.get(type(mods[i + 2]))
+    if act is None or not bn.training or bn.momentum is None or bn.num_features % 4 \
+            or bn.num_features > 1024:
+        return None
+    return bn, act
+
+
+def _fusable(lins, x: Tensor) -> bool:
+    import torch
+    return (isinstance(lins, nn.Sequential) and x.is_cuda and x.dtype == torch.float32
+            and x.numel() > 0 and torch.is_grad_enabled() is not None
+            and any(_match_block(list(lins), i) is not None for i in range(len(lins))))

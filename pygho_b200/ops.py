@@ -43,22 +43,41 @@ _LIB.define("seg_gmr(Tensor a_val, Tensor? c, Tensor? a_scale, Tensor? b_val, Te
             "Tensor? rowptr, int n_rows, int aggr) -> Tensor")
 
 
-def _seg_gmr_cuda(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr):
-    a_val, b_val, a_scale = _f32c(a_val), _f32c(b_val), _f32c(a_scale)
+def _rows2d(t: Optional[Tensor]) -> Optional[Tensor]:
+    """float32 (rows, dense) whose rows are contiguous; the row stride may exceed dense
+    (column slice of a wider buffer).  Anything else is copied."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"pygho_b200 kernels are float32; got {t.dtype}")
+    if t.ndim == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1] and t.stride(0) % 4 == 0 \
+            and t.data_ptr() % 16 == 0:
+        return t
+    return t.contiguous()
+
+
+def _seg_gmr_into(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out):
+    a_val, b_val, a_scale = _rows2d(a_val), _rows2d(b_val), _f32c(a_scale)
     c, d, rowptr = _i32c(c), _i32c(d), _i32c(rowptr)
     dense = a_val.shape[1]
     if a_val.shape[0] == 0 or (b_val is not None and b_val.shape[0] == 0):
-        return torch.zeros((n_rows, dense), dtype=torch.float32, device=a_val.device)
-    out = torch.empty((n_rows, dense), dtype=torch.float32, device=a_val.device)
+        out.zero_()
+        return out
     if n_rows and dense:
         n_entries = 0
         for idx in (c, d):
             if idx is not None:
                 n_entries = idx.shape[0]
-        call("pgh_seg_gmr_f32", ptr(a_val), ptr(c), ptr(a_scale), ptr(b_val), ptr(d),
-             ptr(rowptr), n_rows, n_entries, dense, aggr, ptr(out), stream_ptr(a_val.device))
+        call("pgh_seg_gmr_ld_f32", ptr(a_val), a_val.stride(0), ptr(c), ptr(a_scale), ptr(b_val),
+             b_val.stride(0) if b_val is not None else dense, ptr(d), ptr(rowptr), n_rows,
+             n_entries, dense, aggr, ptr(out), out.stride(0), stream_ptr(a_val.device))
         _lib.count_launch()
     return out
+
+
+def _seg_gmr_cuda(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr):
+    out = torch.empty((n_rows, a_val.shape[1]), dtype=torch.float32, device=a_val.device)
+    return _seg_gmr_into(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out)
 
 
 _LIB.impl("seg_gmr", _seg_gmr_cuda, "CUDA")
@@ -67,6 +86,25 @@ _LIB.impl("seg_gmr", _seg_gmr_cuda, "CUDA")
 @torch.library.register_fake("pygho_b200::seg_gmr")
 def _seg_gmr_fake(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr):
     return a_val.new_empty((n_rows, a_val.shape[1]))
+
+
+_LIB.define("seg_gmr_out(Tensor a_val, Tensor? c, Tensor? a_scale, Tensor? b_val, Tensor? d, "
+            "Tensor? rowptr, int n_rows, int aggr, Tensor(a!) out) -> ()")
+
+
+def _seg_gmr_out_cuda(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out):
+    if out.dtype != torch.float32 or out.ndim != 2 or out.stride(1) != 1 or out.stride(0) % 4 \
+            or out.data_ptr() % 16 or tuple(out.shape) != (n_rows, a_val.shape[1]):
+        raise ValueError("seg_gmr_out: out must be a float32 (n_rows, dense) row-contiguous view")
+    _seg_gmr_into(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out)
+
+
+_LIB.impl("seg_gmr_out", _seg_gmr_out_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::seg_gmr_out")
+def _seg_gmr_out_fake(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out):
+    return None
 
 
 _LIB.define("seg_tie_scale(Tensor a_val, Tensor? c, Tensor? b_val, Tensor? d, Tensor? rowptr, "
@@ -277,6 +315,85 @@ def _masked_fill_fake(data, mask, value):
     return torch.empty_like(data)
 
 
+# ---------------------------------------------------------------- fused BatchNorm + act
+_LIB.define("bn_stats(Tensor y, float eps, float momentum, Tensor? running_mean, "
+            "Tensor? running_var) -> (Tensor, Tensor)")
+
+
+def _bn_ws(rows, C, device):
+    n = int(_lib.load().pgh_bn_ws_bytes(int(rows), int(C)))
+    return torch.empty((n,), dtype=torch.uint8, device=device)
+
+
+def _bn_stats_cuda(y, eps, momentum, running_mean, running_var):
+    y = _f32c(y)
+    rows, C = y.shape
+    mean = torch.empty((C,), dtype=torch.float32, device=y.device)
+    rstd = torch.empty_like(mean)
+    ws = _bn_ws(rows, C, y.device)
+    call("pgh_bn_stats_f32", ptr(y), rows, C, float(eps), float(momentum), ptr(mean), ptr(rstd),
+         ptr(running_mean), ptr(running_var), ptr(ws), ws.numel(), stream_ptr(y.device))
+    _lib.count_launch(2)
+    return mean, rstd
+
+
+_LIB.impl("bn_stats", _bn_stats_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::bn_stats")
+def _bn_stats_fake(y, eps, momentum, running_mean, running_var):
+    return y.new_empty((y.shape[1],)), y.new_empty((y.shape[1],))
+
+
+_LIB.define("bn_act_fwd(Tensor y, Tensor mean, Tensor rstd, Tensor? gamma, Tensor? beta, int act) -> Tensor")
+
+
+def _bn_act_fwd_cuda(y, mean, rstd, gamma, beta, act):
+    y = _f32c(y)
+    rows, C = y.shape
+    z = torch.empty_like(y)
+    call("pgh_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(rstd), ptr(_f32c(gamma)), ptr(_f32c(beta)),
+         rows, C, act, ptr(z), stream_ptr(y.device))
+    _lib.count_launch()
+    return z
+
+
+_LIB.impl("bn_act_fwd", _bn_act_fwd_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::bn_act_fwd")
+def _bn_act_fwd_fake(y, mean, rstd, gamma, beta, act):
+    return torch.empty_like(y)
+
+
+_LIB.define("bn_act_bwd(Tensor dz, Tensor y, Tensor mean, Tensor rstd, Tensor? gamma, Tensor? beta, "
+            "int act, bool want_bias) -> (Tensor, Tensor, Tensor, Tensor)")
+
+
+def _bn_act_bwd_cuda(dz, y, mean, rstd, gamma, beta, act, want_bias):
+    dz, y = _f32c(dz), _f32c(y)
+    rows, C = y.shape
+    dy = torch.empty_like(y)
+    dgamma = torch.empty((C,), dtype=torch.float32, device=y.device)
+    dbeta = torch.empty_like(dgamma)
+    dbias = torch.empty_like(dgamma) if want_bias else None
+    ws = _bn_ws(rows, C, y.device)
+    call("pgh_bn_act_bwd_f32", ptr(dz), ptr(y), ptr(mean), ptr(rstd), ptr(_f32c(gamma)),
+         ptr(_f32c(beta)), rows, C, act, ptr(dy), ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(ws),
+         ws.numel(), stream_ptr(y.device))
+    _lib.count_launch(4 if want_bias else 3)
+    return dy, dgamma, dbeta, (dbias if want_bias else dgamma.new_zeros((0,)))
+
+
+_LIB.impl("bn_act_bwd", _bn_act_bwd_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::bn_act_bwd")
+def _bn_act_bwd_fake(dz, y, mean, rstd, gamma, beta, act, want_bias):
+    C = y.shape[1]
+    return torch.empty_like(y), y.new_empty((C,)), y.new_empty((C,)), y.new_empty((C if want_bias else 0,))
+
+
 _ops = torch.ops.pygho_b200
 
 
@@ -305,9 +422,9 @@ class SegGmr(torch.autograd.Function):
     def backward(ctx, g: Tensor):
         plan, aggr = ctx.plan, ctx.aggr
         need_a, need_b = ctx.needs_input_grad[0], ctx.has_b and ctx.needs_input_grad[1]
-        g = g.contiguous()
         g_a = g_b = None
         if aggr >= 2:
+            g = g.contiguous()
             a_val, b_val, out = ctx.saved_tensors
             ga = plan.group("a")
             gs = _ops.seg_tie_scale(a_val, ga.first, b_val,
@@ -475,3 +592,36 @@ class MaskedFill(torch.autograd.Function):
     def backward(ctx, g):
         (mask,) = ctx.saved_tensors
         return _ops.masked_fill_rows(g.contiguous(), mask, 0.0), None, None
+
+
+ACT_CODE = {"none": 0, "silu": 1, "relu": 2}
+
+
+class LinearBNAct(torch.autograd.Function):
+    """z = act(BatchNorm_train(x @ W^T + b)) for 2-D x: the reference MLP block
+    (honn/utils.py:85-142) with the normalisation/activation passes fused.  The GEMMs stay
+    with cuBLAS (torch.addmm / mm); only the HBM-bound elementwise + reduction work is ours.
+    Saves x and the Linear output y; the normalised tensor is recomputed in the backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, momentum, eps, act):
+        y = torch.nn.functional.linear(x, weight, bias)
+        mean, rstd = _ops.bn_stats(y, eps, momentum, running_mean, running_var)
+        z = _ops.bn_act_fwd(y, mean, rstd, gamma, beta, act)
+        ctx.save_for_backward(x, weight, y, mean, rstd, gamma, beta)
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        return z
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dz):
+        x, weight, y, mean, rstd, gamma, beta = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dy, dgamma, dbeta, dbias = _ops.bn_act_bwd(dz, y, mean, rstd, gamma, beta, ctx.act,
+                                                   ctx.has_bias and need[2])
+        dx = dy.mm(weight) if need[0] else None
+        dw = dy.t().mm(x) if need[1] else None
+        return (dx, dw, dbias if (ctx.has_bias and need[2]) else None,
+                dgamma if (gamma is not None and need[3]) else None,
+                dbeta if (beta is not None and need[4]) else None, None, None, None, None, None)

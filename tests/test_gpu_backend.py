@@ -464,3 +464,26 @@ def test_mamamm_tcgen05_matches_fp32_kernel(n, d, ta, tb):
     from pygho_b200.ops import mask_extents
     assert torch.equal(mask_extents(mask).cpu(), torch.stack((sizes, sizes), 1).to(torch.int32))
     torch.cuda.synchronize()
+
+
+def test_seg_gmr_strided_operands_and_out_slice():
+    """Operands / output that are column slices of wider buffers (row stride > dense):
+    same bits as the contiguous call, no copies needed."""
+    from pygho_b200 import plans as P
+    import pygho_b200.ops  # noqa: F401
+    ops = torch.ops.pygho_b200
+    for d in (128, 8):
+        acd, a, b = _rand_problem(5, d=d)
+        a, b = a.to(DEV), b.to(DEV)
+        plan = P.plan_from_acd(acd.to(DEV), 97, a.shape[0], b.shape[0])
+        g = plan.group("a")
+        ref = ops.seg_gmr(a, g.first, None, b, g.second, g.rowptr, 97, 0)
+        wide_a = torch.randn(a.shape[0], 3 * d, device=DEV)
+        wide_b = torch.randn(b.shape[0], 2 * d, device=DEV)
+        wide_a[:, d:2 * d] = a
+        wide_b[:, d:] = b
+        got = ops.seg_gmr(wide_a[:, d:2 * d], g.first, None, wide_b[:, d:], g.second, g.rowptr, 97, 0)
+        assert torch.equal(got, ref)
+        buf = torch.full((97, 3 * d), 7.0, device=DEV)
+        ops.seg_gmr_out(a, g.first, None, b, g.second, g.rowptr, 97, 0, buf[:, 2 * d:])
+        assert torch.equal(buf[:, 2 * d:], ref) and float(buf[:, :2 * d].min()) == 7.0

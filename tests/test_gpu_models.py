@@ -174,3 +174,42 @@ def test_ma_model_runs_and_masks():
         pred = model(ma_datadict(hb, DEV))
         assert pred.shape == (4, 1) and bool(torch.isfinite(pred).all())
         pred.sum().backward()
+
+
+@pytest.mark.parametrize("rows,cin,cout,act", [(1000, 24, 8, "silu"), (4097, 128, 128, "silu"),
+                                               (3001, 384, 384, "silu"), (777, 16, 12, "relu")])
+def test_fused_linear_bn_act_matches_torch(rows, cin, cout, act):
+    """MLP block through the fused kernels vs the same modules run one by one by torch:
+    output, running statistics and every gradient."""
+    from pygho_b200.honn.utils import MLP
+    torch.manual_seed(rows)
+    mlp = MLP(cin, cout, 2, True, norm="bn", act=act, normparam=0.3).to(DEV)
+    with torch.no_grad():
+        for m in mlp.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.5, 0.5)
+    ref = copy.deepcopy(mlp)
+    x = torch.randn(rows, cin, device=DEV) * 2 + 0.7
+    xr = x.clone().requires_grad_(True)
+    xf = x.clone().requires_grad_(True)
+    w = torch.randn(rows, cout, device=DEV)
+    out_ref = ref.lins(xr)                    # plain torch path (Sequential, module by module)
+    (out_ref * w).sum().backward()
+    out = mlp(xf)                             # fused path
+    (out * w).sum().backward()
+    close(out, out_ref, 2e-5)
+    close(xf.grad, xr.grad, 5e-5)
+    for (k, p), (_, q) in zip(mlp.named_parameters(), ref.named_parameters()):
+        if k.endswith("bias") and "norm" not in k:
+            # a Linear bias in front of a training-mode BatchNorm has gradient sum(dy) == 0
+            # exactly; both implementations return rounding noise of the size of one ulp of
+            # sum(|dy|), which cannot agree digit by digit
+            assert float(p.grad.abs().max()) < 2e-3 and float(q.grad.abs().max()) < 2e-3
+            continue
+        close(p.grad, q.grad, 1e-4)
+    for (k, p), (_, q) in zip(mlp.named_buffers(), ref.named_buffers()):
+        close(p.float(), q.float(), 1e-5)
+    # eval mode falls back to the stock modules and agrees
+    mlp.eval(), ref.eval()
+    close(mlp(x), ref.lins(x), 1e-5)
