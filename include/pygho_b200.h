@@ -58,11 +58,13 @@ int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float* a_scale,
                     void* stream);
 
 /* Same with explicit row strides (in floats) so operands / the output may be column slices
- * of wider row-major tensors (e.g. one third of a concatenated feature buffer). */
+ * of wider row-major tensors (e.g. one third of a concatenated feature buffer);
+ * accumulate != 0 (sum / mean only) adds the result to what `out` already holds, which is
+ * how several gradient contributions to one operand are summed without extra passes. */
 int pgh_seg_gmr_ld_f32(const float* a_val, int64_t lda, const int32_t* c, const float* a_scale,
                        const float* b_val, int64_t ldb, const int32_t* d, const int32_t* rowptr,
-                       int64_t n_rows, int64_t n_entries, int64_t dense, int aggr, float* out,
-                       int64_t ldo, void* stream);
+                       int64_t n_rows, int64_t n_entries, int64_t dense, int aggr, int accumulate,
+                       float* out, int64_t ldo, void* stream);
 
 /* max/min backward, step 1: gscaled[r,:] = grad[r,:] / (#{t in seg(r): A(t)*B(t) == out[r,:]}
  *                                                       + [out[r,:] == 0])

@@ -102,18 +102,37 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ y, long long r
   }
 }
 
+// Second stage of every reduction: block = 32 channels x 32 partial lanes; lane ty sums the
+// partials ty, ty+32, ... in double, then the 32 lanes are combined in a fixed order.
+__device__ __forceinline__ void combine_partials(const float* __restrict__ part, int blocks,
+                                                 size_t block_stride, int off0, int off1, int c,
+                                                 bool ok, double& s, double& q) {
+  __shared__ double sm[2][32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  double a = 0.0, b2 = 0.0;
+  if (ok)
+    for (int b = ty; b < blocks; b += 32) {
+      a += (double)part[(size_t)b * block_stride + off0 + c];
+      if (off1 >= 0) b2 += (double)part[(size_t)b * block_stride + off1 + c];
+    }
+  sm[0][ty][tx] = a;
+  sm[1][ty][tx] = b2;
+  __syncthreads();
+  s = 0.0;
+  q = 0.0;
+  if (ty == 0)
+    for (int t = 0; t < 32; ++t) { s += sm[0][t][tx]; q += sm[1][t][tx]; }
+}
+
 __global__ void bn_stats_final_kernel(const float* __restrict__ y, const float* __restrict__ part,
                                       int blocks, long long rows, int C, float eps, float momentum,
                                       float* __restrict__ mean, float* __restrict__ rstd,
                                       float* __restrict__ running_mean,
                                       float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < blocks; ++b) {
-    s += (double)part[(size_t)b * 2 * C + c];
-    q += (double)part[(size_t)b * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  combine_partials(part, blocks, (size_t)2 * C, 0, C, c, c < C, s, q);
+  if (threadIdx.y != 0 || c >= C) return;
   const double n = (double)rows;
   const double ms = s / n;                       // mean of (y - shift)
   double var = q / n - ms * ms;                  // biased variance
@@ -184,17 +203,14 @@ __global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const flo
   }
 }
 
-// sums the partials in block order; writes dbeta = S1, dgamma = S2 and the per-channel means
+// writes dbeta = S1, dgamma = S2 and the per-channel means used by the apply pass
 __global__ void bn_bwd_final_kernel(const float* __restrict__ part, int blocks, long long rows, int C,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
                                     float* __restrict__ m1, float* __restrict__ m2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < blocks; ++b) {
-    s += (double)part[(size_t)b * 2 * C + c];
-    q += (double)part[(size_t)b * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  combine_partials(part, blocks, (size_t)2 * C, 0, C, c, c < C, s, q);
+  if (threadIdx.y != 0 || c >= C) return;
   if (dbeta) dbeta[c] = (float)s;
   if (dgamma) dgamma[c] = (float)q;
   m1[c] = (float)(s / (double)rows);
@@ -246,11 +262,10 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const floa
 
 __global__ void colsum_final_kernel(const float* __restrict__ part, int blocks, int C,
                                     float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += (double)part[(size_t)b * C + c];
-  out[c] = (float)s;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  combine_partials(part, blocks, (size_t)C, 0, -1, c, c < C, s, q);
+  if (threadIdx.y == 0 && c < C) out[c] = (float)s;
 }
 
 static bool bn_ok(int64_t rows, int64_t C) {
@@ -279,7 +294,7 @@ extern "C" int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, float e
   float* part = reinterpret_cast<float*>(ws);
   const size_t smem = (size_t)g.c4 * g.ty * 2 * sizeof(float4);
   bn_stats_partial_kernel<<<g.blocks, dim3(g.c4, g.ty), smem, s>>>(y, rows, (int)C, g.rows_per_block, part);
-  bn_stats_final_kernel<<<blocks_for(C, 128), 128, 0, s>>>(y, part, g.blocks, rows, (int)C, eps, momentum,
+  bn_stats_final_kernel<<<blocks_for(C, 32), dim3(32, 32), 0, s>>>(y, part, g.blocks, rows, (int)C, eps, momentum,
                                                             mean, rstd, running_mean, running_var);
   return check_launch("bn_stats");
 }
@@ -324,13 +339,13 @@ extern "C" int pgh_bn_act_bwd_f32(const float* dz, const float* y, const float* 
 #define PGH_BWD(A)                                                                                   \
   bn_act_bwd_reduce_kernel<A><<<g.blocks, blk, smem, s>>>(dz, y, mean, rstd, gamma, beta, rows,     \
                                                            (int)C, g.rows_per_block, part);          \
-  bn_bwd_final_kernel<<<blocks_for(C, 128), 128, 0, s>>>(part, g.blocks, rows, (int)C, dgamma,      \
+  bn_bwd_final_kernel<<<blocks_for(C, 32), dim3(32, 32), 0, s>>>(part, g.blocks, rows, (int)C, dgamma,      \
                                                           dbeta, m1, m2);                            \
   bn_act_bwd_apply_kernel<A><<<g.blocks, blk, smem, s>>>(dz, y, mean, rstd, gamma, beta, m1, m2,    \
                                                           rows, (int)C, g.rows_per_block, dy,        \
                                                           dbias ? part : nullptr)
   if (act == 1) { PGH_BWD(1); } else if (act == 2) { PGH_BWD(2); } else { PGH_BWD(0); }
 #undef PGH_BWD
-  if (dbias) colsum_final_kernel<<<blocks_for(C, 128), 128, 0, s>>>(part, g.blocks, (int)C, dbias);
+  if (dbias) colsum_final_kernel<<<blocks_for(C, 32), dim3(32, 32), 0, s>>>(part, g.blocks, (int)C, dbias);
   return check_launch("bn_act_bwd");
 }

@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(kThreads)
 seg_gmr_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
                const float* __restrict__ a_scale, const float* __restrict__ b_val,
                const int* __restrict__ d, const int* __restrict__ rowptr, long long n_rows,
-               int dense, int lda, int ldb, int ldo, int lpr, float* __restrict__ out) {
+               int dense, int lda, int ldb, int ldo, int lpr, int accum,
+               float* __restrict__ out) {
   const Lane L = lane_setup(rowptr, n_rows, lpr);
   const int colstep = lpr * VEC;
   for (int col0 = 0; col0 < dense; col0 += colstep) {
@@ -149,6 +150,12 @@ seg_gmr_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
         if (L.len == 0) acc[v] = 0.f;
         else if (AGGR == PGH_MEAN) acc[v] = acc[v] / (float)L.len;
       }
+      if (accum) {
+        float old[VEC];
+        ldv<VEC>(out + (size_t)L.row * ldo + col, old);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(old[v], acc[v]);
+      }
       stv<VEC>(out + (size_t)L.row * ldo + col, acc);
     }
   }
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kThreads)
 seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
                       const float* __restrict__ a_scale, const float* __restrict__ b_val,
                       const int* __restrict__ d, const int* __restrict__ rowptr,
-                      long long n_rows, int dense, int lda, int ldb, int ldo, int rw,
+                      long long n_rows, int dense, int lda, int ldb, int ldo, int rw, int accum,
                       float* __restrict__ out) {
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -199,6 +206,11 @@ seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c
     else if (AGGR == PGH_MEAN) {                                                        \
       const float n_ = (float)len_;                                                     \
       r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);                 \
+    }                                                                                   \
+    if (accum) {                                                                        \
+      const float4 o_ = *reinterpret_cast<const float4*>(o_col + (size_t)cur * ldo);    \
+      r_ = make_float4(__fadd_rn(o_.x, r_.x), __fadd_rn(o_.y, r_.y),                    \
+                       __fadd_rn(o_.z, r_.z), __fadd_rn(o_.w, r_.w));                   \
     }                                                                                   \
     *reinterpret_cast<float4*>(o_col + (size_t)cur * ldo) = r_;                         \
     acc = make_float4(init, init, init, init);                                          \
@@ -432,7 +444,7 @@ template <int AGGR, int VEC>
 static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, const int* c,
                        const float* a_scale, const float* b_val, const int* d,
                        const int* rowptr, int64_t n_rows, int64_t n_entries, int dense, int lda,
-                       int ldb, int ldo, float* out) {
+                       int ldb, int ldo, int accum, float* out) {
   if (VEC == 4 && dense % 128 == 0 && !g_force_rowwise) {
     // rows per warp: aim at ~32 plan entries per warp, at least 4 warps' worth of blocks per SM
     int rw = kMaxRW;
@@ -445,18 +457,18 @@ static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, co
     const unsigned nb = blocks_for(n_rows, (kThreads / 32) * rw);
     if (b_val)
       seg_gmr_stream_kernel<AGGR, true><<<nb, kThreads, 0, s>>>(
-          a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, out);
+          a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
     else
       seg_gmr_stream_kernel<AGGR, false><<<nb, kThreads, 0, s>>>(
-          a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, out);
+          a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
     return;
   }
   if (b_val)
     seg_gmr_kernel<AGGR, VEC, true><<<g.blocks, kThreads, 0, s>>>(
-        a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, g.lpr, out);
+        a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, g.lpr, accum, out);
   else
     seg_gmr_kernel<AGGR, VEC, false><<<g.blocks, kThreads, 0, s>>>(
-        a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, g.lpr, out);
+        a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, g.lpr, accum, out);
 }
 
 }  // namespace pgh
@@ -482,11 +494,12 @@ extern "C" int pgh_device_info(int32_t* out5) {
 extern "C" int pgh_seg_gmr_ld_f32(const float* a_val, int64_t lda, const int32_t* c,
                                   const float* a_scale, const float* b_val, int64_t ldb,
                                   const int32_t* d, const int32_t* rowptr, int64_t n_rows,
-                                  int64_t n_entries, int64_t dense, int aggr, float* out,
-                                  int64_t ldo, void* stream) {
+                                  int64_t n_entries, int64_t dense, int aggr, int accumulate,
+                                  float* out, int64_t ldo, void* stream) {
   if (!a_val || !out) return arg_error("seg_gmr: a_val and out are required");
   if (n_rows < 0 || dense <= 0 || dense > (1 << 20)) return arg_error("seg_gmr: sizes");
   if (aggr < 0 || aggr > 3) return arg_error("seg_gmr: aggr");
+  if (accumulate && aggr > 1) return arg_error("seg_gmr: accumulate needs sum or mean");
   if (lda < dense || ldo < dense || (b_val && ldb < dense) || lda > 0x7fffffff ||
       ldb > 0x7fffffff || ldo > 0x7fffffff)
     return arg_error("seg_gmr: leading dimensions");
@@ -499,9 +512,9 @@ extern "C" int pgh_seg_gmr_ld_f32(const float* a_val, int64_t lda, const int32_t
   const int la = (int)lda, lb = (int)(b_val ? ldb : dense), lo = (int)ldo;
 #define PGH_GMR(AG)                                                                       \
   if (g.vec == 4) launch_gmr<AG, 4>(g, s, a_val, c, a_scale, b_val, d, rowptr, n_rows,   \
-                                    n_entries, (int)dense, la, lb, lo, out);              \
+                                    n_entries, (int)dense, la, lb, lo, accumulate, out);  \
   else launch_gmr<AG, 1>(g, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, n_entries,   \
-                         (int)dense, la, lb, lo, out)
+                         (int)dense, la, lb, lo, accumulate, out)
   switch (aggr) {
     case PGH_SUM: PGH_GMR(PGH_SUM); break;
     case PGH_MEAN: PGH_GMR(PGH_MEAN); break;
@@ -517,7 +530,7 @@ extern "C" int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float
                                int64_t n_rows, int64_t n_entries, int64_t dense, int aggr,
                                float* out, void* stream) {
   return pgh_seg_gmr_ld_f32(a_val, dense, c, a_scale, b_val, dense, d, rowptr, n_rows, n_entries,
-                            dense, aggr, out, dense, stream);
+                            dense, aggr, 0, out, dense, stream);
 }
 
 extern "C" int pgh_seg_tie_scale_f32(const float* a_val, const int32_t* c, const float* b_val,

@@ -42,9 +42,39 @@ class SSWLConv(Module):
         self.lin = MLP(3 * indim, outdim, **mlp)
 
     def forward(self, A: AnyTensor, X: AnyTensor, datadict: dict) -> AnyTensor:
+        fused = self._fused_cat(A, X, datadict)
+        if fused is not None:
+            return X.tuplewiseapply(lambda _v: self.lin(fused))
         inside = self.aggr1.forward(A, X, datadict, X)
         across = self.aggr2.forward(A, X, datadict, X)
         return X.catvalue([inside, across], True).tuplewiseapply(self.lin)
+
+    def _fused_cat(self, A, X, datadict):
+        """[X, X(x)A, A(x)X] written into one buffer by the two spspmm launches (sparse mode,
+        precomputed plans, sum/mean, 2-D float32 values); None -> generic path."""
+        from ..backend.SpTensor import SparseTensor as _Sp
+        from ..honn.SpOperator import KEYSEP
+        if not (isinstance(A, _Sp) and isinstance(X, _Sp)):
+            return None
+        m1, m2 = self.aggr1.mod, self.aggr2.mod
+        if m1.use_mpnn or m2.use_mpnn or m1.aggr != m2.aggr or m1.aggr not in ("sum", "mean"):
+            return None
+        acd1 = datadict.get(m1.precomputekey + KEYSEP + "acd")
+        acd2 = datadict.get(m2.precomputekey + KEYSEP + "acd")
+        xv, av = X.values, A.values
+        if acd1 is None or acd2 is None or xv is None or av is None or xv.ndim != 2 \
+                or xv.shape[1:] != av.shape[1:] or xv.dtype != av.dtype or not xv.is_cuda \
+                or xv.shape[1] % 4:
+            return None
+        import torch
+        if xv.dtype != torch.float32:
+            return None
+        from .. import plans as P
+        from ..ops import SswlAggregate
+        plan_xa = P.plan_from_acd(acd1, X.nnz, X.nnz, A.nnz)
+        plan_ax = P.plan_from_acd(acd2, X.nnz, A.nnz, X.nnz)
+        return SswlAggregate.apply(xv.contiguous(), av.contiguous(), plan_xa, plan_ax,
+                                   0 if m1.aggr == "sum" else 1)
 
 
 class I2Conv(Module):

@@ -56,12 +56,13 @@ def _rows2d(t: Optional[Tensor]) -> Optional[Tensor]:
     return t.contiguous()
 
 
-def _seg_gmr_into(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out):
+def _seg_gmr_into(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out, accumulate=False):
     a_val, b_val, a_scale = _rows2d(a_val), _rows2d(b_val), _f32c(a_scale)
     c, d, rowptr = _i32c(c), _i32c(d), _i32c(rowptr)
     dense = a_val.shape[1]
     if a_val.shape[0] == 0 or (b_val is not None and b_val.shape[0] == 0):
-        out.zero_()
+        if not accumulate:
+            out.zero_()
         return out
     if n_rows and dense:
         n_entries = 0
@@ -70,7 +71,8 @@ def _seg_gmr_into(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out):
                 n_entries = idx.shape[0]
         call("pgh_seg_gmr_ld_f32", ptr(a_val), a_val.stride(0), ptr(c), ptr(a_scale), ptr(b_val),
              b_val.stride(0) if b_val is not None else dense, ptr(d), ptr(rowptr), n_rows,
-             n_entries, dense, aggr, ptr(out), out.stride(0), stream_ptr(a_val.device))
+             n_entries, dense, aggr, int(accumulate), ptr(out), out.stride(0),
+             stream_ptr(a_val.device))
         _lib.count_launch()
     return out
 
@@ -89,21 +91,21 @@ def _seg_gmr_fake(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr):
 
 
 _LIB.define("seg_gmr_out(Tensor a_val, Tensor? c, Tensor? a_scale, Tensor? b_val, Tensor? d, "
-            "Tensor? rowptr, int n_rows, int aggr, Tensor(a!) out) -> ()")
+            "Tensor? rowptr, int n_rows, int aggr, Tensor(a!) out, bool accumulate) -> ()")
 
 
-def _seg_gmr_out_cuda(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out):
+def _seg_gmr_out_cuda(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out, accumulate):
     if out.dtype != torch.float32 or out.ndim != 2 or out.stride(1) != 1 or out.stride(0) % 4 \
             or out.data_ptr() % 16 or tuple(out.shape) != (n_rows, a_val.shape[1]):
         raise ValueError("seg_gmr_out: out must be a float32 (n_rows, dense) row-contiguous view")
-    _seg_gmr_into(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out)
+    _seg_gmr_into(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out, accumulate)
 
 
 _LIB.impl("seg_gmr_out", _seg_gmr_out_cuda, "CUDA")
 
 
 @torch.library.register_fake("pygho_b200::seg_gmr_out")
-def _seg_gmr_out_fake(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out):
+def _seg_gmr_out_fake(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out, accumulate):
     return None
 
 
@@ -592,6 +594,49 @@ class MaskedFill(torch.autograd.Function):
     def backward(ctx, g):
         (mask,) = ctx.saved_tensors
         return _ops.masked_fill_rows(g.contiguous(), mask, 0.0), None, None
+
+
+class SswlAggregate(torch.autograd.Function):
+    """``cat([X, X (x) A, A (x) X], -1)`` of one SSWL layer (reference Conv.py:97-103) built in
+    ONE buffer: the two spspmm launches write their column slice directly, and the three
+    gradient contributions to X (two to A) are accumulated by the kernels themselves instead of
+    materialising temporaries and adding them.  sum / mean aggregation."""
+
+    @staticmethod
+    def forward(ctx, Xv, Av, plan_xa, plan_ax, aggr):
+        n, d = Xv.shape
+        cat = torch.empty((n, 3 * d), dtype=torch.float32, device=Xv.device)
+        cat[:, :d].copy_(Xv)
+        g1, g2 = plan_xa.group("a"), plan_ax.group("a")
+        _ops.seg_gmr_out(Xv, g1.first, None, Av, g1.second, g1.rowptr, n, aggr, cat[:, d:2 * d], False)
+        _ops.seg_gmr_out(Av, g2.first, None, Xv, g2.second, g2.rowptr, n, aggr, cat[:, 2 * d:], False)
+        ctx.save_for_backward(Xv, Av)
+        ctx.cfg = (plan_xa, plan_ax, aggr)
+        return cat
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        Xv, Av = ctx.saved_tensors
+        plan_xa, plan_ax, aggr = ctx.cfg
+        n, d = Xv.shape
+        nA = Av.shape[0]
+        g0, g1, g2 = g[:, :d], g[:, d:2 * d], g[:, 2 * d:]
+        s1 = plan_xa.inv_count() if aggr == 1 else None
+        s2 = plan_ax.inv_count() if aggr == 1 else None
+        gX = gA = None
+        if ctx.needs_input_grad[0]:
+            gX = g0.contiguous() if not g0.is_contiguous() else g0.clone()
+            c = plan_xa.group("c")       # X is operand A of X (x) A
+            _ops.seg_gmr_out(g1, c.first, s1, Av, c.second, c.rowptr, n, 0, gX, True)
+            dd = plan_ax.group("d")      # X is operand B of A (x) X
+            _ops.seg_gmr_out(g2, dd.first, s2, Av, dd.second, dd.rowptr, n, 0, gX, True)
+        if ctx.needs_input_grad[1]:
+            dd = plan_xa.group("d")      # A is operand B of X (x) A
+            gA = _ops.seg_gmr(g1, dd.first, s1, Xv, dd.second, dd.rowptr, nA, 0)
+            c = plan_ax.group("c")       # A is operand A of A (x) X
+            _ops.seg_gmr_out(g2, c.first, s2, Xv, c.second, c.rowptr, nA, 0, gA, True)
+        return gX, gA, None, None, None
 
 
 ACT_CODE = {"none": 0, "silu": 1, "relu": 2}

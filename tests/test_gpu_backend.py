@@ -485,5 +485,8 @@ def test_seg_gmr_strided_operands_and_out_slice():
         got = ops.seg_gmr(wide_a[:, d:2 * d], g.first, None, wide_b[:, d:], g.second, g.rowptr, 97, 0)
         assert torch.equal(got, ref)
         buf = torch.full((97, 3 * d), 7.0, device=DEV)
-        ops.seg_gmr_out(a, g.first, None, b, g.second, g.rowptr, 97, 0, buf[:, 2 * d:])
+        ops.seg_gmr_out(a, g.first, None, b, g.second, g.rowptr, 97, 0, buf[:, 2 * d:], False)
         assert torch.equal(buf[:, 2 * d:], ref) and float(buf[:, :2 * d].min()) == 7.0
+        # accumulate: out += result
+        ops.seg_gmr_out(a, g.first, None, b, g.second, g.rowptr, 97, 0, buf[:, 2 * d:], True)
+        assert torch.equal(buf[:, 2 * d:], ref + ref)
