@@ -642,6 +642,24 @@ class SswlAggregate(torch.autograd.Function):
 ACT_CODE = {"none": 0, "silu": 1, "relu": 2}
 
 
+def _tall_skinny_tn(a: Tensor, b: Tensor, chunks: int = 64) -> Tensor:
+    """a^T @ b for (rows, m) and (rows, n) with rows >> m, n (weight gradients over all
+    tuples).  cuBLAS does not split K for this shape and leaves most SMs idle; cutting the
+    rows into `chunks` slabs turns it into one batched GEMM that fills the GPU, followed by a
+    tiny reduction over the slabs."""
+    rows = a.shape[0]
+    if rows < 64 * chunks or a.shape[1] > 1024 or b.shape[1] > 1024:
+        return a.t().mm(b)
+    per = rows // chunks
+    main = per * chunks
+    part = torch.bmm(a[:main].view(chunks, per, a.shape[1]).transpose(1, 2),
+                     b[:main].view(chunks, per, b.shape[1]))
+    out = part.sum(0)
+    if main < rows:
+        out.addmm_(a[main:].t(), b[main:])
+    return out
+
+
 class LinearBNAct(torch.autograd.Function):
     """z = act(BatchNorm_train(x @ W^T + b)) for 2-D x: the reference MLP block
     (honn/utils.py:85-142) with the normalisation/activation passes fused.  The GEMMs stay
@@ -666,7 +684,7 @@ class LinearBNAct(torch.autograd.Function):
         dy, dgamma, dbeta, dbias = _ops.bn_act_bwd(dz, y, mean, rstd, gamma, beta, ctx.act,
                                                    ctx.has_bias and need[2])
         dx = dy.mm(weight) if need[0] else None
-        dw = dy.t().mm(x) if need[1] else None
+        dw = _tall_skinny_tn(dy, x) if need[1] else None
         return (dx, dw, dbias if (ctx.has_bias and need[2]) else None,
                 dgamma if (gamma is not None and need[3]) else None,
                 dbeta if (beta is not None and need[4]) else None, None, None, None, None, None)
