@@ -134,9 +134,14 @@ class MaskedTensor:
         hi = lo + len(dims)
         outer, red, inner = _prod(keptshape[:lo]), _prod(keptshape[lo:hi]), _prod(keptshape[hi:])
         dense = _prod(self.denseshape)
-        out, omask = MaskedPool.apply(data.reshape(outer, red, inner, dense).contiguous(),
-                                      mask.reshape(outer, red, inner).contiguous(), 1,
-                                      AGGR_CODE[aggr])
+        d4 = data.reshape(outer, red, inner, dense)
+        pad = (-dense) % 4       # the kernels move 128-bit channel groups; rare odd widths are padded
+        if pad:
+            d4 = torch.nn.functional.pad(d4, (0, pad))
+        out, omask = MaskedPool.apply(d4.contiguous(), mask.reshape(outer, red, inner).contiguous(),
+                                      1, AGGR_CODE[aggr])
+        if pad:
+            out = out[..., :dense]
         oshape = keptshape[:lo] + ([1] * len(dims) if keepdim else []) + keptshape[hi:]
         if keepdim and dims != list(range(dims[0], dims[-1] + 1)):
             raise NotImplementedError("keepdim with non-adjacent dims")

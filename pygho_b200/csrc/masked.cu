@@ -64,82 +64,128 @@ mamamm_simt_kernel(const float* __restrict__ A, long long sAi, long long sAj,
 }
 
 // ------------------------------------------------------------------ masked pooling
-// data (b, n1, n2, dense).  One thread per (b, kept index, channel); the reduced extent
-// is walked with stride so that a warp always touches one contiguous line.
+// View (outer, red, inner, dense): reduce the middle extent.  A thread owns 4 channels of one
+// (outer, inner) output row and walks the reduced extent 4 rows at a time (4 independent
+// 128-bit loads + 4 mask bytes in flight); a warp covers 128 consecutive channels, so every
+// request is a contiguous 512 B piece of a row.  HBM bound: one read of the input.
+struct PoolView {
+  long long outer;
+  int red, inner, c4;
+};
+
 template <int AGGR>
-__global__ void masked_pool_kernel(const float* __restrict__ data,
-                                   const unsigned char* __restrict__ mask, int n1, int n2,
-                                   int dense, int red, float* __restrict__ out,
-                                   unsigned char* __restrict__ out_mask, long long total) {
+__global__ void masked_pool_kernel(const float4* __restrict__ data,
+                                   const unsigned char* __restrict__ mask, PoolView v,
+                                   float4* __restrict__ out, unsigned char* __restrict__ out_mask,
+                                   long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int ch = (int)(idx % dense);
-  long long rest = idx / dense;
-  // kept extent: red==1 -> n2, red==2 -> n1, red==3 -> 1
-  const int nkeep = red == 1 ? n2 : red == 2 ? n1 : 1;
-  const int keep = (int)(rest % nkeep);
-  const long long b = rest / nkeep;
-  const int nred = red == 1 ? n1 : red == 2 ? n2 : n1 * n2;
-  float acc = AGGR == PGH_MAX ? -INFINITY : AGGR == PGH_MIN ? INFINITY : 0.f;
+  const int ch = (int)(idx % v.c4);
+  const long long rest = idx / v.c4;               // (outer, inner) flattened
+  const int in = (int)(rest % v.inner);
+  const long long o = rest / v.inner;
+  const float init = AGGR == PGH_MAX ? -INFINITY : AGGR == PGH_MIN ? INFINITY : 0.f;
+  float4 acc = make_float4(init, init, init, init);
   int cnt = 0;
-  for (int r = 0; r < nred; ++r) {
-    long long pos;  // position in (n1, n2)
-    if (red == 1) pos = (long long)r * n2 + keep;
-    else if (red == 2) pos = (long long)keep * n2 + r;
-    else pos = r;
-    pos += b * n1 * n2;
-    if (mask[pos]) {
-      const float v = __ldg(data + pos * dense + ch);
-      ++cnt;
-      if (AGGR == PGH_MAX) acc = fmaxf(acc, v);
-      else if (AGGR == PGH_MIN) acc = fminf(acc, v);
-      else acc += v;
-    }
+  const long long base = o * v.red * v.inner + in;  // position of r = 0
+  const unsigned char* mp = mask + base;
+  const float4* dp = data + base * v.c4 + ch;
+  const long long pstep = v.inner, dstep = (long long)v.inner * v.c4;
+  auto take = [&](const float4& x) {
+    if (AGGR == PGH_MAX) acc = make_float4(fmaxf(acc.x, x.x), fmaxf(acc.y, x.y), fmaxf(acc.z, x.z), fmaxf(acc.w, x.w));
+    else if (AGGR == PGH_MIN) acc = make_float4(fminf(acc.x, x.x), fminf(acc.y, x.y), fminf(acc.z, x.z), fminf(acc.w, x.w));
+    else acc = make_float4(acc.x + x.x, acc.y + x.y, acc.z + x.z, acc.w + x.w);
+  };
+  int r = 0;
+  for (; r + 4 <= v.red; r += 4) {
+    unsigned char m[4];
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m[u] = __ldg(mp + (r + u) * pstep);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (m[u]) x[u] = __ldg(dp + (r + u) * dstep);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (m[u]) { take(x[u]); ++cnt; }
   }
-  if (cnt == 0) acc = 0.f;
-  else if (AGGR == PGH_MEAN) acc = acc / (float)cnt;
-  if ((AGGR == PGH_MAX || AGGR == PGH_MIN) && isinf(acc)) acc = 0.f;  // filterinf, MaTensor.py:8-31
+  for (; r < v.red; ++r)
+    if (__ldg(mp + r * pstep)) { take(__ldg(dp + r * dstep)); ++cnt; }
+  if (cnt == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  else if (AGGR == PGH_MEAN) {
+    const float n = (float)cnt;
+    acc = make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
+  }
+  if (AGGR == PGH_MAX || AGGR == PGH_MIN) {         // filterinf, MaTensor.py:8-31
+    if (isinf(acc.x)) acc.x = 0.f;
+    if (isinf(acc.y)) acc.y = 0.f;
+    if (isinf(acc.z)) acc.z = 0.f;
+    if (isinf(acc.w)) acc.w = 0.f;
+  }
   out[idx] = acc;
   if (out_mask && ch == 0) out_mask[rest] = cnt > 0;
 }
 
 template <int AGGR>
-__global__ void masked_pool_bwd_kernel(const float* __restrict__ data,
+__global__ void masked_pool_bwd_kernel(const float4* __restrict__ data,
                                        const unsigned char* __restrict__ mask,
-                                       const float* __restrict__ outp,
-                                       const float* __restrict__ g_out, int n1, int n2,
-                                       int dense, int red, float* __restrict__ g_data,
-                                       long long total) {
+                                       const float4* __restrict__ outp,
+                                       const float4* __restrict__ g_out, PoolView v,
+                                       float4* __restrict__ g_data, long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int ch = (int)(idx % dense);
-  long long rest = idx / dense;
-  const int nkeep = red == 1 ? n2 : red == 2 ? n1 : 1;
-  const int keep = (int)(rest % nkeep);
-  const long long b = rest / nkeep;
-  const int nred = red == 1 ? n1 : red == 2 ? n2 : n1 * n2;
-  const float g = g_out[idx];
-  const float o = (AGGR == PGH_MAX || AGGR == PGH_MIN) ? outp[idx] : 0.f;
-  int cnt = 0;
-  for (int r = 0; r < nred; ++r) {
-    long long pos = red == 1 ? (long long)r * n2 + keep : red == 2 ? (long long)keep * n2 + r : r;
-    pos += b * n1 * n2;
-    if (mask[pos]) {
-      if (AGGR == PGH_MAX || AGGR == PGH_MIN) cnt += (__ldg(data + pos * dense + ch) == o) ? 1 : 0;
-      else ++cnt;
+  const int ch = (int)(idx % v.c4);
+  const long long rest = idx / v.c4;
+  const int in = (int)(rest % v.inner);
+  const long long o = rest / v.inner;
+  const long long base = o * v.red * v.inner + in;
+  const unsigned char* mp = mask + base;
+  const float4* dp = data + base * v.c4 + ch;
+  float4* gp = g_data + base * v.c4 + ch;
+  const long long pstep = v.inner, dstep = (long long)v.inner * v.c4;
+  const float4 g = g_out[idx];
+  constexpr bool kExt = (AGGR == PGH_MAX || AGGR == PGH_MIN);
+  const float4 ov = kExt ? outp[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w = g;
+  if (AGGR != PGH_SUM) {
+    // mean: 1/#valid ; max/min: 1/#ties per channel (torch.amax backward splits evenly)
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int r = 0; r < v.red; ++r) {
+      if (!__ldg(mp + r * pstep)) continue;
+      if (kExt) {
+        const float4 x = __ldg(dp + r * dstep);
+        c0 += x.x == ov.x; c1 += x.y == ov.y; c2 += x.z == ov.z; c3 += x.w == ov.w;
+      } else {
+        ++c0;
+      }
     }
+    if (!kExt) c1 = c2 = c3 = c0;
+    w = make_float4(c0 ? g.x / (float)c0 : 0.f, c1 ? g.y / (float)c1 : 0.f,
+                    c2 ? g.z / (float)c2 : 0.f, c3 ? g.w / (float)c3 : 0.f);
   }
-  const float w = (AGGR == PGH_SUM) ? g : (cnt > 0 ? g / (float)cnt : 0.f);
-  for (int r = 0; r < nred; ++r) {
-    long long pos = red == 1 ? (long long)r * n2 + keep : red == 2 ? (long long)keep * n2 + r : r;
-    pos += b * n1 * n2;
-    float v = 0.f;
-    if (mask[pos]) {
-      if (AGGR == PGH_MAX || AGGR == PGH_MIN) v = (__ldg(data + pos * dense + ch) == o) ? w : 0.f;
-      else v = w;
+  for (int r = 0; r < v.red; ++r) {
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (__ldg(mp + r * pstep)) {
+      if (kExt) {
+        const float4 x = __ldg(dp + r * dstep);
+        val = make_float4(x.x == ov.x ? w.x : 0.f, x.y == ov.y ? w.y : 0.f,
+                          x.z == ov.z ? w.z : 0.f, x.w == ov.w ? w.w : 0.f);
+      } else {
+        val = w;
+      }
     }
-    g_data[pos * dense + ch] = v;
+    gp[r * dstep] = val;
   }
+}
+
+static int pool_view(int64_t b, int64_t n1, int64_t n2, int64_t dense, int red_dims, PoolView& v) {
+  if (dense % 4) return arg_error("masked_pool: dense % 4 != 0");
+  v.c4 = (int)(dense / 4);
+  if (red_dims == 1) { v.outer = b; v.red = (int)n1; v.inner = (int)n2; }
+  else if (red_dims == 2) { v.outer = b * n1; v.red = (int)n2; v.inner = 1; }
+  else if (red_dims == 3) { v.outer = b; v.red = (int)(n1 * n2); v.inner = 1; }
+  else return arg_error("masked_pool: red_dims");
+  return 0;
 }
 
 __global__ void masked_fill_kernel(const float* __restrict__ data,
@@ -206,13 +252,15 @@ extern "C" int pgh_masked_pool_f32(const float* data, const uint8_t* mask, int64
                                    int64_t n2, int64_t dense, int red_dims, int aggr, float* out,
                                    uint8_t* out_mask, void* stream) {
   if (!data || !mask || !out) return arg_error("masked_pool: null pointer");
-  if (red_dims < 1 || red_dims > 3) return arg_error("masked_pool: red_dims");
-  const int64_t nkeep = red_dims == 1 ? n2 : red_dims == 2 ? n1 : 1;
-  const long long total = (long long)b * nkeep * dense;
+  PoolView v;
+  if (int e = pool_view(b, n1, n2, dense, red_dims, v)) return e;
+  if ((reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return arg_error("masked_pool: tensors must be 16-byte aligned");
+  const long long total = v.outer * v.inner * v.c4;
   if (total <= 0) return 0;
   cudaStream_t s = as_stream(stream);
   const unsigned nb = blocks_for(total, 256);
-#define PGH_POOL(AG) masked_pool_kernel<AG><<<nb, 256, 0, s>>>(data, mask, (int)n1, (int)n2, (int)dense, red_dims, out, out_mask, total)
+#define PGH_POOL(AG) masked_pool_kernel<AG><<<nb, 256, 0, s>>>((const float4*)data, mask, v, (float4*)out, out_mask, total)
   switch (aggr) {
     case PGH_SUM: PGH_POOL(PGH_SUM); break;
     case PGH_MEAN: PGH_POOL(PGH_MEAN); break;
@@ -229,14 +277,17 @@ extern "C" int pgh_masked_pool_bwd_f32(const float* data, const uint8_t* mask, c
                                        int64_t dense, int red_dims, int aggr, float* g_data,
                                        void* stream) {
   if (!data || !mask || !g_out || !g_data) return arg_error("masked_pool_bwd: null pointer");
-  if (red_dims < 1 || red_dims > 3) return arg_error("masked_pool_bwd: red_dims");
   if ((aggr == PGH_MAX || aggr == PGH_MIN) && !out) return arg_error("masked_pool_bwd: out needed");
-  const int64_t nkeep = red_dims == 1 ? n2 : red_dims == 2 ? n1 : 1;
-  const long long total = (long long)b * nkeep * dense;
+  PoolView v;
+  if (int e = pool_view(b, n1, n2, dense, red_dims, v)) return e;
+  if ((reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(g_out) |
+       reinterpret_cast<uintptr_t>(g_data) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return arg_error("masked_pool_bwd: tensors must be 16-byte aligned");
+  const long long total = v.outer * v.inner * v.c4;
   if (total <= 0) return 0;
   cudaStream_t s = as_stream(stream);
   const unsigned nb = blocks_for(total, 256);
-#define PGH_POOLB(AG) masked_pool_bwd_kernel<AG><<<nb, 256, 0, s>>>(data, mask, out, g_out, (int)n1, (int)n2, (int)dense, red_dims, g_data, total)
+#define PGH_POOLB(AG) masked_pool_bwd_kernel<AG><<<nb, 256, 0, s>>>((const float4*)data, mask, (const float4*)out, (const float4*)g_out, v, (float4*)g_data, total)
   switch (aggr) {
     case PGH_SUM: PGH_POOLB(PGH_SUM); break;
     case PGH_MEAN: PGH_POOLB(PGH_MEAN); break;

@@ -169,7 +169,7 @@ seg_gmr_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
 // warp-uniform (every lane handles the same entry, lanes = columns), so the flush of a
 // finished row is a plain uniform branch and one coalesced 512 B store.
 constexpr int kMaxRW = 16;  // rows per warp upper bound (<= 31: lane i holds rowptr[r0 + i])
-constexpr int kSU = 4;      // plan entries in flight per lane (2 * kSU 128-bit loads)
+// plan entries in flight per lane: 4 with two operands (8 x 128-bit loads), 8 with one
 
 template <int AGGR, bool HAS_B>
 __global__ void __launch_bounds__(kThreads)
@@ -179,6 +179,7 @@ seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c
                       long long n_rows, int dense, int lda, int ldb, int ldo, int rw, int accum,
                       float* __restrict__ out) {
   constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kSU = HAS_B ? 4 : 8;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const long long r0 = warp * rw;

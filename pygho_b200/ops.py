@@ -69,6 +69,8 @@ def _seg_gmr_into(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out, accumu
         for idx in (c, d):
             if idx is not None:
                 n_entries = idx.shape[0]
+        if n_entries == 0 and rowptr is not None:
+            n_entries = a_val.shape[0]          # identity index: one entry per operand row
         call("pgh_seg_gmr_ld_f32", ptr(a_val), a_val.stride(0), ptr(c), ptr(a_scale), ptr(b_val),
              b_val.stride(0) if b_val is not None else dense, ptr(d), ptr(rowptr), n_rows,
              n_entries, dense, aggr, int(accumulate), ptr(out), out.stride(0),
