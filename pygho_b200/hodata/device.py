@@ -71,6 +71,62 @@ def sp_datadict(hb: HostBatch, device, keys: Iterable[str] = (),
     return dd
 
 
+def prefetch_plans(datadict: dict, keys: Iterable[str], backward: bool = True) -> None:
+    """Build (and cache on the ``acd`` tensors) the CSR groupings the kernels will ask for,
+    so that the first layer of the model does not pay for them."""
+    nX, nA = datadict["X"].nnz, datadict["A"].nnz
+    for key in keys:
+        _op0, op1, _d1, op2, _d2 = parse_key(key)
+        n1 = nA if op1 == "A" else nX
+        n2 = nA if op2 == "A" else nX
+        P.plan_from_acd(datadict[key + KEYSEP + "acd"], nX, n1, n2).prefetch(backward)
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device feeding (the role of the reference's
+    ``IterWrapper``: ``.to(device)`` + batch transform, hodata/Wrapper.py:90-98).
+
+    ``next()`` returns the datadict of the current batch and immediately issues, on a side
+    stream, the pinned-memory copies, SparseTensor wrapping and CSR regrouping of the NEXT
+    batch, so they overlap the training step that is about to be launched."""
+
+    def __init__(self, host_batches, device, keys, pinned: Optional[dict] = None):
+        self.hbs, self.device, self.keys = list(host_batches), device, list(keys)
+        self.pinned = {} if pinned is None else pinned
+        self.stream = torch.cuda.Stream(device)
+        self.pos = 0
+        self._ready = self._inflight = None
+        self._issue()
+
+    def _issue(self):
+        hb = self.hbs[self.pos % len(self.hbs)]
+        self.pos += 1
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            dd = sp_datadict(hb, self.device, self.keys, self.pinned)
+            prefetch_plans(dd, self.keys)
+        self._ready = dd
+
+    def get(self) -> dict:
+        """Datadict of the current batch (waits, on the device, for its copies)."""
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return self._ready
+
+    def advance(self) -> None:
+        """Issue the next batch's copies and plan regrouping on the side stream.  Call it
+        right after the training step has been launched: the host work overlaps the step's
+        execution.  The caller must synchronise with that step (e.g. read the loss back)
+        before the following ``advance()``: the buffers of the batch before it are released
+        here and reused."""
+        self._inflight = self._ready
+        self._issue()
+
+    def next(self) -> dict:
+        dd = self.get()
+        self.advance()
+        return dd
+
+
 def attach_host_plans(hb: HostBatch, datadict: dict, keys: Iterable[str]) -> None:
     """Copy the device-built plans back into the host batch (done once per batch when a
     dataset is prepared), so later epochs ship them like the reference's loader does."""
