@@ -103,40 +103,67 @@ __device__ __forceinline__ int tile_off(int row, int kcol, int sbo) {
   return (row >> 3) * sbo + (kcol >> 2) * kCoreBytes + (row & 7) * 16 + (kcol & 3) * 4;
 }
 
-constexpr int kLU = 4;   // units (one 128-bit load each) in flight per thread in the load phase
+constexpr int kLU = 10;  // 128-bit loads in flight per thread in the load phase
 
-// Fill the 8 channel tiles of one operand for rows < n_rows and K columns < k_pad (zeros at
-// kcol >= n_k_valid).  A warp-wide unit is a 4-row x 4-kcol patch: lane = (r2, kq, h) with
-// h = channel half, kq = kcol & 3, r2 = row & 3, which puts the 32 lanes of every STS on 32
-// different banks (bank = kq + 4*r2 + 16*h) while each lane pair still reads one full 32 B
-// sector from global memory.
-__device__ __forceinline__ void load_tiles(const float* __restrict__ src, unsigned char* tiles,
-                                           int n_rows, int n_k_valid, int k_pad,
-                                           long long s_row, long long s_k, int dense, int ts,
-                                           int sbo, int warp, int lane) {
+struct OperandView {
+  const float* src;      // + 4 * half
+  unsigned char* tiles;  // + (4 * half) * ts
+  int n_rows, ts;
+  long long s_row, s_k;
+};
+
+// Fill the 8 channel tiles of BOTH operands for rows < n_rows and K columns < k_pad (zeros at
+// kcol >= nj).  A warp-wide unit is a 4-row x 4-kcol patch of one operand: lane = (r2, kq, h)
+// with h = channel half, kq = kcol & 3, r2 = row & 3, which puts the 32 lanes of every STS on
+// 32 different banks (bank = kq + 4*r2 + 16*h) while each lane pair still reads one full 32 B
+// sector from global memory.  Units of A and B are interleaved over the warps and up to kLU
+// loads per thread are issued before the first store, so a typical graph (n ~ 23: 72 units,
+// 9 per warp) costs ONE global-memory latency for the whole load phase.
+__device__ __forceinline__ void load_tiles(const OperandView& va, const OperandView& vb, int nj,
+                                           int k_pad, int dense, int sbo, int warp, int lane) {
   const int h = lane & 1, kq = (lane >> 1) & 3, r2 = lane >> 3;
-  const int kquads = k_pad >> 2, rquads = (n_rows + 3) >> 2;
-  const int units = kquads * rquads;
-  const float* base = src + 4 * h;
-  unsigned char* tbase = tiles + (4 * h) * ts;
-  for (int u0 = warp; u0 < units; u0 += kLU * (kTcThreads / 32)) {
+  const int kquads = k_pad >> 2;
+  const int units_a = kquads * ((va.n_rows + 3) >> 2);
+  const int units = units_a + kquads * ((vb.n_rows + 3) >> 2);
+  constexpr int kWarps = kTcThreads / 32;
+  // (patch row, patch column) of unit = warp + k * kWarps, advanced without divisions
+  const int dq = kWarps / kquads, dr = kWarps % kquads;
+  for (int u0 = warp; u0 < units; u0 += kLU * kWarps) {
     float4 v[kLU];
-    int off[kLU];
+    int off[kLU];   // byte offset from smem base of channel tile (4*h), -1 = nothing to store
+    int unit = u0;
+    bool is_b = unit >= units_a;
+    int local = is_b ? unit - units_a : unit;
+    int pq = local / kquads, pr = local - pq * kquads;
 #pragma unroll
     for (int u = 0; u < kLU; ++u) {
-      const int unit = u0 + u * (kTcThreads / 32);
-      const int row = (unit / kquads) * 4 + r2, kcol = (unit % kquads) * 4 + kq;
-      const bool live = unit < units && row < n_rows;
-      off[u] = live ? tile_off(row, kcol, sbo) : -1;
+      const bool in_range = unit < units;
+      const OperandView& w = is_b ? vb : va;
+      const int row = pq * 4 + r2, kcol = pr * 4 + kq;
+      const bool live = in_range && row < w.n_rows;
+      off[u] = live ? (int)(w.tiles - va.tiles) + (4 * h) * w.ts + tile_off(row, kcol, sbo) : -1;
       v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live && kcol < n_k_valid)
+      if (live && kcol < nj)
         v[u] = __ldg(reinterpret_cast<const float4*>(
-            base + ((size_t)row * s_row + (size_t)kcol * s_k) * dense));
+            w.src + 4 * h + ((size_t)row * w.s_row + (size_t)kcol * w.s_k) * dense));
+      // next unit of this warp
+      unit += kWarps;
+      if (!is_b && unit >= units_a) {
+        is_b = true;
+        local = unit - units_a;
+        pq = local / kquads;
+        pr = local - pq * kquads;
+      } else {
+        pq += dq;
+        pr += dr;
+        if (pr >= kquads) { pr -= kquads; ++pq; }
+      }
     }
 #pragma unroll
     for (int u = 0; u < kLU; ++u) {
       if (off[u] >= 0) {
-        unsigned char* t = tbase + off[u];
+        const int ts = (u0 + u * kWarps) >= units_a ? vb.ts : va.ts;
+        unsigned char* t = va.tiles + off[u];
         *reinterpret_cast<float*>(t) = v[u].x;
         *reinterpret_cast<float*>(t + ts) = v[u].y;
         *reinterpret_cast<float*>(t + 2 * ts) = v[u].z;
@@ -204,10 +231,15 @@ mamamm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
   {
     const int h = tid & 1;
     const bool empty = ni == 0 || nj == 0 || nk == 0;
-    for (int p = tid >> 1; p < g.n_i * g.n_k; p += kTcThreads / 2) {
-      const int i = p / g.n_k, k = p - i * g.n_k;
+    const int step = kTcThreads / 2, di = step / g.n_k, dk = step - di * g.n_k;
+    int p = tid >> 1;
+    int i = p / g.n_k, k = p - i * g.n_k;
+    for (; p < g.n_i * g.n_k; p += step) {
       if (empty || i >= ni || k >= nk)
         *reinterpret_cast<float4*>(ob + (size_t)p * dense + 4 * h) = make_float4(0.f, 0.f, 0.f, 0.f);
+      i += di;
+      k += dk;
+      if (k >= g.n_k) { k -= g.n_k; ++i; }
     }
     if (empty) return;
   }
@@ -229,14 +261,26 @@ mamamm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
   const int ch_round = (kCS * n_pad <= kTmemCols) ? 8 : 4;
 
   // ---- load phase: global (b, i, j, c0..c0+7) -> 8 per-channel UMMA tiles ----------------
-  load_tiles(A + (size_t)b * g.n_i * g.n_j * dense + c0, smem, ni, nj, k_pad, g.sa_i, g.sa_j,
-             dense, g.ts_a, g.sbo, warp, lane);
-  load_tiles(B + (size_t)b * g.n_j * g.n_k * dense + c0, smem + g.off_b, nk, nj, k_pad, g.sb_k,
-             g.sb_j, dense, g.ts_b, g.sbo, warp, lane);
-  // the mask rows are staged too: the epilogue must not pay a global-load latency per store
+  // the mask rows are staged too (the epilogue must not pay a global-load latency per store);
+  // their loads are issued first so that they overlap the operand loads
   {
     const unsigned char* mb = mask + (size_t)b * g.n_i * g.n_k;
-    for (int t = tid; t < ni * g.n_k; t += kTcThreads) smem[g.off_mask + t] = __ldg(mb + t);
+    unsigned char mv[8];
+    const int total = ni * g.n_k;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tid + q * kTcThreads;
+      mv[q] = t < total ? __ldg(mb + t) : 0;
+    }
+    OperandView va{A + (size_t)b * g.n_i * g.n_j * dense + c0, smem, ni, g.ts_a, g.sa_i, g.sa_j};
+    OperandView vb{B + (size_t)b * g.n_j * g.n_k * dense + c0, smem + g.off_b, nk, g.ts_b, g.sb_k, g.sb_j};
+    load_tiles(va, vb, nj, k_pad, dense, g.sbo, warp, lane);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tid + q * kTcThreads;
+      if (t < total) smem[g.off_mask + t] = mv[q];
+    }
+    for (int t = tid + 8 * kTcThreads; t < total; t += kTcThreads) smem[g.off_mask + t] = __ldg(mb + t);
   }
   // make the generic-proxy smem writes visible to the tensor-core (async) proxy
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -171,15 +171,14 @@ seg_gmr_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
 constexpr int kMaxRW = 16;  // rows per warp upper bound (<= 31: lane i holds rowptr[r0 + i])
 // plan entries in flight per lane: 4 with two operands (8 x 128-bit loads), 8 with one
 
-template <int AGGR, bool HAS_B>
-__global__ void __launch_bounds__(kThreads)
+template <int AGGR, bool HAS_B, int kSU, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
                       const float* __restrict__ a_scale, const float* __restrict__ b_val,
                       const int* __restrict__ d, const int* __restrict__ rowptr,
                       long long n_rows, int dense, int lda, int ldb, int ldo, int rw, int accum,
                       float* __restrict__ out) {
   constexpr unsigned kFull = 0xffffffffu;
-  constexpr int kSU = HAS_B ? 4 : 8;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const long long r0 = warp * rw;
@@ -456,12 +455,29 @@ static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, co
       if (rw > kMaxRW) rw = kMaxRW;
     }
     const unsigned nb = blocks_for(n_rows, (kThreads / 32) * rw);
-    if (b_val)
-      seg_gmr_stream_kernel<AGGR, true><<<nb, kThreads, 0, s>>>(
+    // measured on B200 (profiles/README.md): 4 entries in flight at 64 registers (4 CTAs/SM)
+    // is best for the short rows of the SSWL keys, 2 entries at 48 registers (5 CTAs/SM) for
+    // long rows (the 2-FWL key, ~8 entries per row); PYGHO_B200_GMR_VARIANT overrides
+    static const int forced = [] { const char* e = getenv("PYGHO_B200_GMR_VARIANT"); return e ? atoi(e) : -1; }();
+    int variant = forced;
+    if (variant < 0) variant = (n_entries > 6 * n_rows) ? 3 : 2;
+    if (b_val) {
+      if (variant == 1)
+        seg_gmr_stream_kernel<AGGR, true, 8, 1><<<nb, kThreads, 0, s>>>(
+            a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
+      else if (variant == 2)
+        seg_gmr_stream_kernel<AGGR, true, 4, 4><<<nb, kThreads, 0, s>>>(
+            a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
+      else if (variant == 3)
+        seg_gmr_stream_kernel<AGGR, true, 2, 5><<<nb, kThreads, 0, s>>>(
+            a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
+      else
+        seg_gmr_stream_kernel<AGGR, true, 4, 1><<<nb, kThreads, 0, s>>>(
+            a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
+    } else {
+      seg_gmr_stream_kernel<AGGR, false, 8, 1><<<nb, kThreads, 0, s>>>(
           a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
-    else
-      seg_gmr_stream_kernel<AGGR, false><<<nb, kThreads, 0, s>>>(
-          a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
+    }
     return;
   }
   if (b_val)

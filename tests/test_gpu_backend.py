@@ -490,3 +490,74 @@ def test_seg_gmr_strided_operands_and_out_slice():
         # accumulate: out += result
         ops.seg_gmr_out(a, g.first, None, b, g.second, g.rowptr, 97, 0, buf[:, 2 * d:], True)
         assert torch.equal(buf[:, 2 * d:], ref + ref)
+
+
+def test_spspmpnn_with_message_function(B, golden):
+    """spspmpnn (reference Spspmm.py:334-380): a GAT-like message function that mixes the
+    three gathered operands; values and gradients against the torch restatement."""
+    g = golden("spspmm")
+    Nn = int(g["N"])
+    ei_c, tid_c, acd_c = (torch.from_numpy(g[k]) for k in ("edge_index", "tupleid", "XA_acd"))
+    Av, Xv = torch.from_numpy(g["Av"]), torch.from_numpy(g["Xv"])
+
+    def msg(a, b, c, idx):
+        return torch.tanh(a + c) * b
+
+    xr, ar = Xv.clone().requires_grad_(True), Av.clone().requires_grad_(True)
+    m = msg(xr[acd_c[1]], ar[acd_c[2]], xr[acd_c[0]], acd_c[0])
+    ref = TO.scatter_reduce(m, acd_c[0], tid_c.shape[1], "sum")
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(0))
+    (ref * w).sum().backward()
+    xg, ag = Xv.to(DEV).requires_grad_(True), Av.to(DEV).requires_grad_(True)
+    X = B.SparseTensor(tid_c.to(DEV), xg, (Nn, Nn, 8), True)
+    A = B.SparseTensor(ei_c.to(DEV), ag, (Nn, Nn, 8), True)
+    out = B.spspmpnn(X, 1, A, 0, X, acd_c.to(DEV), msg, "sum")
+    (out.values * w.to(DEV)).sum().backward()
+    close(out.values, ref, 2e-5)
+    close(xg.grad, xr.grad, 5e-5)
+    close(ag.grad, ar.grad, 5e-5)
+    # through the operator wrapper (honn/SpOperator.py message_func path)
+    from pygho_b200.honn.SpOperator import OpMessagePassingOnSubg2D
+    op = OpMessagePassingOnSubg2D("sum", message_func=msg)
+    out2 = op(A, X, {op.precomputekey + "___acd": acd_c.to(DEV)}, X)
+    close(out2.values, ref, 2e-5)
+
+
+def test_diag_add_and_sparse_unpool(B, golden):
+    g = golden("spspmm")
+    Nn = int(g["N"])
+    tid, Xv = T(g["tupleid"]), T(g["Xv"])
+    X = B.SparseTensor(tid, Xv, (Nn, Nn, 8), True)
+    close(X.diag([0, 1]), O.sp_diag_dense(g["tupleid"], g["Xv"], (Nn, Nn), [0, 1]))
+    from pygho_b200.honn.TensorOp import OpDiag2D
+    close(OpDiag2D("S")(X), O.sp_diag_dense(g["tupleid"], g["Xv"], (Nn, Nn), [0, 1]))
+    # add with a different sparsity pattern -> concatenate + coalesce (SpTensor.py:507-514)
+    sub = tid[:, ::3].contiguous()
+    Y = B.SparseTensor(sub.flip(1).contiguous(), Xv[::3].flip(0).contiguous(), (Nn, Nn, 8), False)
+    assert torch.equal(Y.indices, sub)                       # coalesce sorted it back
+    Z = X.add(Y, False)
+    want_i, want_v = O.coalesce(np.concatenate([g["tupleid"], g["tupleid"][:, ::3]], 1),
+                                np.concatenate([g["Xv"], g["Xv"][::3]], 0), "sum")
+    assert np.array_equal(N(Z.indices), want_i)
+    close(Z.values, want_v)
+    # same-pattern ops
+    close(X.add(X, True).values, 2 * g["Xv"])
+    assert X.catvalue([X, X], True).shape == (Nn, Nn, 24)
+    d = X.diagonalapply(lambda v, flag: v * flag.unsqueeze(-1))
+    eq = (g["tupleid"][0] == g["tupleid"][1])[:, None]
+    close(d.values, g["Xv"] * eq)
+
+
+def test_dense_node_message_passing(B):
+    """DD OpNodeMessagePassing (broken in the reference, Q3): A (b,n,n,d) x (b,n,d)."""
+    from pygho_b200.honn.TensorOp import OpNodeMessagePassing
+    gen = torch.Generator().manual_seed(1)
+    b, n, d = 3, 6, 8
+    sizes = torch.tensor([6, 4, 5])
+    ar = torch.arange(n)
+    m1 = ar[None, :] < sizes[:, None]
+    m2 = m1[:, :, None] & m1[:, None, :]
+    A = torch.randn(b, n, n, d, generator=gen) * m2.unsqueeze(-1)
+    x = torch.randn(b, n, d, generator=gen) * m1.unsqueeze(-1)
+    out = OpNodeMessagePassing("DD")(B.MaskedTensor(A.to(DEV), m2.to(DEV)), B.MaskedTensor(x.to(DEV), m1.to(DEV)))
+    close(out.data, torch.einsum("bijd,bjd->bid", A, x) * m1.unsqueeze(-1), 1e-2)
