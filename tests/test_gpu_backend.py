@@ -250,7 +250,7 @@ def _rand_problem(seed, n_out=97, n_a=61, n_b=43, T_=700, d=12, ties=False):
 
 
 @pytest.mark.parametrize("aggr", AGGRS)
-@pytest.mark.parametrize("d", [1, 3, 8, 12, 128, 200])
+@pytest.mark.parametrize("d", [1, 3, 8, 12, 128, 200, 256, 384])
 @pytest.mark.parametrize("ties", [False, True])
 def test_seg_gmr_forward_backward_vs_torch(aggr, d, ties):
     """Unsorted random plan, every aggregation and width: values and both operand
@@ -561,3 +561,35 @@ def test_dense_node_message_passing(B):
     x = torch.randn(b, n, d, generator=gen) * m1.unsqueeze(-1)
     out = OpNodeMessagePassing("DD")(B.MaskedTensor(A.to(DEV), m2.to(DEV)), B.MaskedTensor(x.to(DEV), m1.to(DEV)))
     close(out.data, torch.einsum("bijd,bjd->bid", A, x) * m1.unsqueeze(-1), 1e-2)
+
+
+def test_ragged_and_degenerate_plans():
+    """Rows without entries, one giant row, a single graph, duplicated triples: the
+    streaming and the row-wise kernels agree with the oracle."""
+    from pygho_b200 import plans as P
+    from pygho_b200.ops import seg_gmr
+    gen = torch.Generator().manual_seed(11)
+    n_out, n_a, n_b = 300, 50, 40
+    for d in (128, 20):
+        a = torch.randn(n_a, d, generator=gen)
+        b = torch.randn(n_b, d, generator=gen)
+        rows = torch.cat([torch.full((700,), 7), torch.randint(100, 120, (200,), generator=gen),
+                          torch.tensor([299, 299, 0])])            # rows 8..99, 120..298 empty
+        acd = torch.stack([rows, torch.randint(0, n_a, rows.shape, generator=gen),
+                           torch.randint(0, n_b, rows.shape, generator=gen)])
+        acd = torch.cat([acd, acd[:, :50]], dim=1)                  # duplicated triples
+        plan = P.plan_from_acd(acd.to(DEV), n_out, n_a, n_b)
+        for aggr in AGGRS:
+            got = seg_gmr(a.to(DEV), b.to(DEV), plan, aggr)
+            close(got, O.spspmm(a.numpy(), b.numpy(), acd.numpy(), n_out, aggr), 2e-5)
+            assert float(got[8:100].abs().max()) == 0.0             # empty rows are exactly 0
+
+
+def test_single_graph_batch(B):
+    from pygho_b200.hodata.device import sp_datadict
+    from pygho_b200.hodata.synthetic import make_batch
+    hb = make_batch(1, seed=3)
+    dd = sp_datadict(hb, DEV, ["X___X___1___A___0"])
+    acd = dd["X___X___1___A___0___acd"]
+    want = O.filterind(hb.tupleid, *O.spspmm_ind(hb.tupleid, 1, hb.edge_index, 0))
+    assert np.array_equal(canon(acd), want)
