@@ -39,6 +39,9 @@ const char* pgh_last_error(void);
 int pgh_abi_version(void);
 /* fills {device ordinal, SM count, L2 bytes, cc major, cc minor}; host pointer */
 int pgh_device_info(int32_t* out5);
+/* run-time tuning knobs (never change results, only the work split): key 0 = seg_gmr kernel
+ * variant (-1 built-in choice), key 1 = ring kernel plan entries per warp; host call */
+int pgh_set_tuning(int key, int value);
 
 /* ------------------------------------------------------------------ value kernels */
 

@@ -271,6 +271,177 @@ seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Ring variant (dense % 128 == 0): same work split and the same sequential reduction order
+// as the streaming kernel, but the value rows travel global -> shared memory with cp.async
+// (LDGSTS, 16 B per lane = one 512 B row per warp instruction) into a per-lane FIFO of NS
+// stages, so the number of rows in flight is bounded by shared memory (NS x 1 KB per warp)
+// instead of registers.  A lane only ever reads back the 16 B it copied itself, so the
+// pipeline needs no barrier at all: cp.async.wait_group is per thread.  The plan of the
+// NEXT 32 entries is prefetched into registers while the current 32 are streamed, which
+// removes the plan-load bubble of the register-staged kernel.
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(saddr)
+               : "memory");
+  return v;
+}
+
+template <int AGGR, bool HAS_B, int NS, int U, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+seg_gmr_ring_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
+                    const float* __restrict__ a_scale, const float* __restrict__ b_val,
+                    const int* __restrict__ d, const int* __restrict__ rowptr,
+                    long long n_rows, int dense, int lda, int ldb, int ldo, int rw, int accum,
+                    float* __restrict__ out) {
+  static_assert(NS % U == 0 && 32 % U == 0 && NS <= 32, "ring geometry");
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int OPS = HAS_B ? 2 : 1;
+  constexpr int NG = NS / U;                        // commit groups in flight
+  extern __shared__ __align__(16) unsigned char ring_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const long long warp = (long long)blockIdx.x * WARPS + wib;
+  const long long r0 = warp * rw;
+  if (r0 >= n_rows) return;
+  const int nr = (int)min((long long)rw, n_rows - r0);
+  int rp = 0;
+  if (lane <= nr) rp = rowptr ? __ldg(rowptr + r0 + lane) : (int)(r0 + lane);
+  const int e_beg = __shfl_sync(kFull, rp, 0);
+  const int e_end = __shfl_sync(kFull, rp, nr);
+  // stage s, operand o of this lane: ring + (s * OPS + o) * 512
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(ring_smem) +
+                        (uint32_t)((wib * NS * OPS) * 32 + lane) * 16u;
+  const float init = (AGGR == PGH_MAX) ? -INFINITY : (AGGR == PGH_MIN) ? INFINITY : 0.f;
+  for (int col = lane * 4; col < dense; col += 128) {
+    const float* __restrict__ a_col = a_val + col;
+    const float* __restrict__ b_col = HAS_B ? b_val + col : nullptr;
+    float* __restrict__ o_col = out + (size_t)r0 * ldo + col;
+    float4 acc = make_float4(init, init, init, init);
+    int cur = 0;
+    int cur_beg = e_beg;
+    int cur_end = __shfl_sync(kFull, rp, 1);
+#define PGH_FLUSH()                                                                     \
+  do {                                                                                  \
+    const int len_ = cur_end - cur_beg;                                                 \
+    float4 r_ = acc;                                                                    \
+    if (len_ == 0) r_ = make_float4(0.f, 0.f, 0.f, 0.f);                                \
+    else if (AGGR == PGH_MEAN) {                                                        \
+      const float n_ = (float)len_;                                                     \
+      r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);                 \
+    }                                                                                   \
+    if (accum) {                                                                        \
+      const float4 o_ = *reinterpret_cast<const float4*>(o_col + (size_t)cur * ldo);    \
+      r_ = make_float4(__fadd_rn(o_.x, r_.x), __fadd_rn(o_.y, r_.y),                    \
+                       __fadd_rn(o_.z, r_.z), __fadd_rn(o_.w, r_.w));                   \
+    }                                                                                   \
+    *reinterpret_cast<float4*>(o_col + (size_t)cur * ldo) = r_;                         \
+    acc = make_float4(init, init, init, init);                                          \
+    ++cur;                                                                              \
+    cur_beg = cur_end;                                                                  \
+    cur_end = __shfl_sync(kFull, rp, min(cur + 1, 31));                                 \
+  } while (0)
+    // plan registers: chunk holding the consume pointer (0) and the one after it (1)
+    int ci0 = 0, di0 = 0, ci1 = 0, di1 = 0;
+    float sc0 = 1.f, sc1 = 1.f;
+#define PGH_LOAD_PLAN(BASE, CI, DI, SC)                                                 \
+  do {                                                                                  \
+    const int t_ = (BASE) + lane;                                                       \
+    CI = 0; DI = 0; SC = 1.f;                                                           \
+    if (t_ < e_end) {                                                                   \
+      CI = c ? __ldg(c + t_) : t_;                                                      \
+      if (HAS_B) DI = d ? __ldg(d + t_) : t_;                                           \
+      if (a_scale) SC = __ldg(a_scale + CI);                                            \
+    }                                                                                   \
+  } while (0)
+    PGH_LOAD_PLAN(e_beg, ci0, di0, sc0);
+    PGH_LOAD_PLAN(e_beg + 32, ci1, di1, sc1);
+    int chunk_base = e_beg;                         // first entry of chunk 0's registers
+    int ti = e_beg;                                 // next entry to issue
+// issue one commit group: entries ti .. ti+U-1 into the slots they map to
+#define PGH_ISSUE()                                                                     \
+  do {                                                                                  \
+    _Pragma("unroll") for (int u_ = 0; u_ < U; ++u_) {                                  \
+      const int t_ = ti + u_;                                                           \
+      if (t_ < e_end) {                                                                 \
+        const int off_ = t_ - chunk_base;                                               \
+        const int cc_ = __shfl_sync(kFull, off_ < 32 ? ci0 : ci1, off_ & 31);           \
+        const uint32_t slot_ = ring + (uint32_t)((((t_ - e_beg) % NS) * OPS) * 512);    \
+        cp_async16(slot_, a_col + (size_t)cc_ * lda);                                   \
+        if (HAS_B) {                                                                    \
+          const int dd_ = __shfl_sync(kFull, off_ < 32 ? di0 : di1, off_ & 31);         \
+          cp_async16(slot_ + 512u, b_col + (size_t)dd_ * ldb);                          \
+        }                                                                               \
+      }                                                                                 \
+    }                                                                                   \
+    cp_async_commit();                                                                  \
+    ti += U;                                                                            \
+  } while (0)
+#pragma unroll
+    for (int g = 0; g < NG; ++g) PGH_ISSUE();
+    for (int tc = e_beg; tc < e_end; tc += U) {
+      cp_async_wait<NG - 1>();
+      float4 av[U], bv[U];
+      float ss[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = min(tc + u, e_end - 1);
+        const uint32_t slot = ring + (uint32_t)((((t - e_beg) % NS) * OPS) * 512);
+        av[u] = lds128(slot);
+        if (HAS_B) bv[u] = lds128(slot + 512u);
+        ss[u] = a_scale ? __shfl_sync(kFull, sc0, (t - chunk_base) & 31) : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (tc + u < e_end) {
+          const int tt = tc + u;
+          while (tt >= cur_end) PGH_FLUSH();
+          float4 m = av[u];
+          if (a_scale)
+            m = make_float4(__fmul_rn(m.x, ss[u]), __fmul_rn(m.y, ss[u]), __fmul_rn(m.z, ss[u]),
+                            __fmul_rn(m.w, ss[u]));
+          if (HAS_B)
+            m = make_float4(__fmul_rn(m.x, bv[u].x), __fmul_rn(m.y, bv[u].y),
+                            __fmul_rn(m.z, bv[u].z), __fmul_rn(m.w, bv[u].w));
+          if (AGGR == PGH_MAX)
+            acc = make_float4(fmaxf(acc.x, m.x), fmaxf(acc.y, m.y), fmaxf(acc.z, m.z), fmaxf(acc.w, m.w));
+          else if (AGGR == PGH_MIN)
+            acc = make_float4(fminf(acc.x, m.x), fminf(acc.y, m.y), fminf(acc.z, m.z), fminf(acc.w, m.w));
+          else
+            acc = make_float4(__fadd_rn(acc.x, m.x), __fadd_rn(acc.y, m.y),
+                              __fadd_rn(acc.z, m.z), __fadd_rn(acc.w, m.w));
+        }
+      }
+      // the slots just read are free again: refill them (the LDS results above have been
+      // consumed, so the reads completed before these copies are issued)
+      PGH_ISSUE();
+      if (tc + U - chunk_base >= 32) {              // consume pointer enters the next chunk
+        chunk_base += 32;
+        ci0 = ci1; di0 = di1; sc0 = sc1;
+        PGH_LOAD_PLAN(chunk_base + 32, ci1, di1, sc1);
+      }
+    }
+    cp_async_wait<0>();
+    while (cur < nr) PGH_FLUSH();
+#undef PGH_ISSUE
+#undef PGH_LOAD_PLAN
+#undef PGH_FLUSH
+  }
+}
+
 // gscaled[r,:] = grad[r,:] / (#entries of seg(r) whose product equals out[r,:])
 template <int VEC, bool HAS_B>
 __global__ void __launch_bounds__(kThreads)
@@ -440,6 +611,61 @@ static Geometry geometry(int64_t n_rows, int64_t dense, bool aligned) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+
+// run-time tuning knobs (pgh_set_tuning): [0] seg_gmr variant (-1 = built-in choice),
+// [1] ring kernel: target plan entries per warp, [2..7] reserved
+static int g_tune[8] = {-1, 16, 0, 0, 0, 0, 0, 0};
+
+template <int AGGR, bool HAS_B, int NS, int U, int WARPS>
+static void launch_ring_t(cudaStream_t s, const float* a_val, const int* c, const float* a_scale,
+                          const float* b_val, const int* d, const int* rowptr, int64_t n_rows,
+                          int dense, int lda, int ldb, int ldo, int rw, int accum, float* out) {
+  constexpr int smem = WARPS * NS * (HAS_B ? 2 : 1) * 512;
+  auto kern = seg_gmr_ring_kernel<AGGR, HAS_B, NS, U, WARPS>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  const unsigned nb = blocks_for(n_rows, WARPS * rw);
+  kern<<<nb, WARPS * 32, smem, s>>>(a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb,
+                                    ldo, rw, accum, out);
+}
+
+template <int AGGR>
+static void launch_ring(int variant, cudaStream_t s, const float* a_val, const int* c,
+                        const float* a_scale, const float* b_val, const int* d,
+                        const int* rowptr, int64_t n_rows, int64_t n_entries, int dense, int lda,
+                        int ldb, int ldo, int accum, float* out) {
+  int rw = 16;
+  if (n_entries > 0 && n_rows > 0) {
+    const double avg = (double)n_entries / (double)n_rows;
+    rw = (int)((double)g_tune[1] / (avg > 0.5 ? avg : 0.5));
+  }
+  if (rw < 1) rw = 1;
+  if (rw > 31) rw = 31;
+#define PGH_RING(NS, U, W)                                                                   \
+  do {                                                                                       \
+    if (b_val) launch_ring_t<AGGR, true, NS, U, W>(s, a_val, c, a_scale, b_val, d, rowptr,   \
+                                                   n_rows, dense, lda, ldb, ldo, rw, accum,  \
+                                                   out);                                     \
+    else launch_ring_t<AGGR, false, NS, U, W>(s, a_val, c, a_scale, b_val, d, rowptr,        \
+                                              n_rows, dense, lda, ldb, ldo, rw, accum, out); \
+  } while (0)
+  switch (variant) {
+    case 11: PGH_RING(8, 4, 8); break;
+    case 12: PGH_RING(8, 2, 8); break;
+    case 13: PGH_RING(8, 2, 4); break;
+    case 14: PGH_RING(4, 2, 8); break;
+    case 15: PGH_RING(4, 2, 4); break;
+    case 16: PGH_RING(8, 1, 4); break;
+    case 17: PGH_RING(16, 2, 8); break;
+    case 18: PGH_RING(4, 4, 8); break;
+    default: PGH_RING(16, 4, 4); break;
+  }
+#undef PGH_RING
+}
+
 template <int AGGR, int VEC>
 static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, const int* c,
                        const float* a_scale, const float* b_val, const int* d,
@@ -451,6 +677,9 @@ static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, co
     if (n_entries > 0 && n_rows > 0) {
       const double avg = (double)n_entries / (double)n_rows;
       rw = (int)(32.0 / (avg > 0.5 ? avg : 0.5));
+      // small problems: keep >= 4 CTAs per SM in the grid rather than long per-warp streams
+      const int64_t cap = n_rows / (int64_t)(kSMs * 4 * (kThreads / 32));
+      if (rw > cap) rw = (int)cap;
       if (rw < 1) rw = 1;
       if (rw > kMaxRW) rw = kMaxRW;
     }
@@ -459,7 +688,13 @@ static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, co
     // is best for the short rows of the SSWL keys, 2 entries at 48 registers (5 CTAs/SM) for
     // long rows (the 2-FWL key, ~8 entries per row); PYGHO_B200_GMR_VARIANT overrides
     static const int forced = [] { const char* e = getenv("PYGHO_B200_GMR_VARIANT"); return e ? atoi(e) : -1; }();
-    int variant = forced;
+    int variant = g_tune[0] >= 0 ? g_tune[0] : forced;
+    // single operand (pooling, unpooling, coalesce): the cp.async ring wins (bench_gmr.py)
+    if (variant < 0 && !b_val) variant = 13;
+    if (variant >= 10) {
+      launch_ring<AGGR>(variant, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, n_entries, dense, lda, ldb, ldo, accum, out);
+      return;
+    }
     if (variant < 0) variant = (n_entries > 6 * n_rows) ? 3 : 2;
     if (b_val) {
       if (variant == 1)
@@ -494,6 +729,12 @@ using namespace pgh;
 
 extern "C" const char* pgh_last_error(void) { return pgh::g_err; }
 extern "C" int pgh_abi_version(void) { return 1; }
+
+extern "C" int pgh_set_tuning(int key, int value) {
+  if (key < 0 || key >= 8) return arg_error("set_tuning: key");
+  pgh::g_tune[key] = value;
+  return 0;
+}
 
 extern "C" int pgh_device_info(int32_t* out5) {
   int dev = 0;
