@@ -31,8 +31,12 @@ import threading
 import time
 
 # batches differ in size from step to step: growable segments keep the caching allocator from
-# falling back to cudaMalloc/cudaFree (device-synchronising) when a block does not fit
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+# falling back to cudaMalloc/cudaFree (device-synchronising) when a block does not fit, and
+# size classes of 1/8 power of two let batches of slightly different sizes reuse each other's
+# blocks instead of fragmenting the pool (every growth is a cuMemMap stall of 10-100 ms,
+# profiles/e2e_trace.py)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF",
+                      "expandable_segments:True,roundup_power2_divisions:8")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

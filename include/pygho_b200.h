@@ -42,6 +42,9 @@ int pgh_device_info(int32_t* out5);
 /* run-time tuning knobs (never change results, only the work split): key 0 = seg_gmr kernel
  * variant (-1 built-in choice), key 1 = ring kernel plan entries per warp; host call */
 int pgh_set_tuning(int key, int value);
+/* profiling hook: device buffer of n_words uint64 that the pipelined mamamm kernel fills
+ * with %globaltimer stamps of its three warp roles (CTA 0 only); NULL switches it off */
+int pgh_debug_trace(void* device_buf, int64_t n_words);
 
 /* ------------------------------------------------------------------ value kernels */
 
@@ -174,7 +177,10 @@ int pgh_check_sorted_i64(const int64_t* key, int64_t n, int strict, int32_t* inf
  * ext (optional, (b,3) int32) = per-graph valid extents (n_i, n_j, n_k): everything outside
  * is known to be zero in the operands / masked in the output, so it is neither read nor
  * multiplied (exact: the skipped terms are zeros).
- * algo 0 = CUDA-core tiled kernel (exact fp32), 1 = tcgen05 TF32 tensor-core kernel.   */
+ * algo 0 = CUDA-core tiled kernel (exact fp32), 1 = tcgen05 TF32 tensor-core kernel with one
+ * CTA per (graph, 8-channel slab), 2 = the same tiles and MMAs in a persistent
+ * warp-specialised pipeline (same bits as 1; falls back to 1 when two tile stages do not fit
+ * in shared memory).                                                                      */
 int pgh_mamamm_f32(const float* A, int trans_a, const float* B, int trans_b,
                    const uint8_t* mask, const int32_t* ext, int64_t b, int64_t n_i, int64_t n_j,
                    int64_t n_k, int64_t dense, int algo, float* out, void* stream);

@@ -245,7 +245,11 @@ for aggr in ("sum", "max"):
         return r.masked_fill(torch.isinf(r), 0)
 
     tr = timeit(ref_pool, 5)
-    report(f"masked pool {aggr} dim 2 ({b},{n},{n},{d})", t, tr, 4 * d * (b * n * n + b * n) + b * n * n)
+    # masked-out positions are never read (the kernel tests the mask first): count the bytes
+    # of valid positions only, like mamamm above; the SURVEY 8d figure with pads is in the note
+    pool_valid = 4 * d * float((sizes.double() ** 2).sum() + b * n) + b * n * n
+    report(f"masked pool {aggr} dim 2 ({b},{n},{n},{d})", t, tr, pool_valid,
+           f"{(4 * d * (b * n * n + b * n) + b * n * n) / 1e6:.0f} MB if pads were read")
 
 if args.md:
     with open(args.md, "w") as f:

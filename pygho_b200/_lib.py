@@ -23,6 +23,7 @@ SIGNATURES = {
     "pgh_abi_version": (_i, []),
     "pgh_device_info": (_i, [_p]),
     "pgh_set_tuning": (_i, [_i, _i]),
+    "pgh_debug_trace": (_i, [_p, _i64]),
     "pgh_seg_gmr_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p, _p]),
     "pgh_seg_gmr_ld_f32": (_i, [_p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i, _i, _p, _i64, _p]),
     "pgh_seg_tie_scale_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),

@@ -18,8 +18,9 @@ from .MaTensor import MaskedTensor
 
 
 def default_algo() -> int:
-    """0 = exact-fp32 CUDA-core kernel, 1 = tcgen05 TF32 tensor-core kernel (default; the
-    reference runs this contraction in TF32 too, example/zinc.py:30)."""
+    """0 = exact-fp32 CUDA-core kernel, 1 = tcgen05 TF32 tensor-core kernel with one CTA per
+    (graph, channel slab), 2 = the same tiles and MMAs in a persistent warp-specialised
+    pipeline.  Default 1 (the reference runs this contraction in TF32 too, example/zinc.py:30)."""
     return int(os.environ.get("PYGHO_B200_MAMAMM_ALGO", "1"))
 
 
@@ -76,7 +77,7 @@ def mamamm(A: MaskedTensor, dim1: int, B: MaskedTensor, dim2: int, mask: BoolTen
     n_i = a3.shape[2] if trans_a else a3.shape[1]
     n_k = b3.shape[1] if trans_b else b3.shape[2]
     algo = default_algo()
-    if algo == 1 and (dense % 8 != 0 or n_i > 128 or n_k > 64 or a3.shape[1 if trans_a else 2] > 128):
+    if algo in (1, 2) and (dense % 8 != 0 or n_i > 128 or n_k > 64 or a3.shape[1 if trans_a else 2] > 128):
         algo = 0      # shapes outside the tensor-core kernel's tile limits
     omask = mask if mask.ndim == 3 else mask.reshape(b, n_i, n_k)
     out = MaMaMM.apply(a3, trans_a, m_a, b3, trans_b, m_b, omask, algo)

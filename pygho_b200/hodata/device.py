@@ -88,7 +88,12 @@ class DevicePrefetcher:
 
     ``next()`` returns the datadict of the current batch and immediately issues, on a side
     stream, the pinned-memory copies, SparseTensor wrapping and CSR regrouping of the NEXT
-    batch, so they overlap the training step that is about to be launched."""
+    batch, so they overlap the training step that is about to be launched.
+
+    The side stream never waits for the compute stream: everything it touches is allocated
+    on it (its own allocator pool), and a batch's buffers only go back to that pool in
+    ``advance()`` one step after the batch was consumed -- by which time the caller has
+    synchronised with that step (see ``advance``)."""
 
     def __init__(self, host_batches, device, keys, pinned: Optional[dict] = None):
         self.hbs, self.device, self.keys = list(host_batches), device, list(keys)
@@ -101,7 +106,6 @@ class DevicePrefetcher:
     def _issue(self):
         hb = self.hbs[self.pos % len(self.hbs)]
         self.pos += 1
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             dd = sp_datadict(hb, self.device, self.keys, self.pinned)
             prefetch_plans(dd, self.keys)

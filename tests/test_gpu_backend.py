@@ -364,7 +364,7 @@ def test_full_size_properties(B):
 
 
 # -------------------------------------------------------------------------------- masked
-@pytest.mark.parametrize("algo,tol", [(0, 1e-5), (1, 1e-2)])
+@pytest.mark.parametrize("algo,tol", [(0, 1e-5), (1, 1e-2), (2, 1e-2)])
 def test_masked_golden(B, golden, monkeypatch, algo, tol):
     monkeypatch.setenv("PYGHO_B200_MAMAMM_ALGO", str(algo))
     g = golden("masked")
@@ -394,7 +394,7 @@ def test_masked_constructor_fills_pads(B):
     assert float(mt.fill_masked(5.0).sum()) == 16.0 + 5.0 * (72 - 16)
 
 
-@pytest.mark.parametrize("algo,tol", [(0, 2e-5), (1, 1e-2)])
+@pytest.mark.parametrize("algo,tol", [(0, 2e-5), (1, 1e-2), (2, 1e-2)])
 @pytest.mark.parametrize("d1,d2", [(2, 1), (1, 1), (1, 2), (2, 2)])
 def test_mamamm_forward_backward(B, monkeypatch, d1, d2, algo, tol):
     monkeypatch.setenv("PYGHO_B200_MAMAMM_ALGO", str(algo))
@@ -441,7 +441,7 @@ def test_masked_pool_forward_backward(B, aggr, dims):
 @pytest.mark.parametrize("n,d", [(40, 128), (37, 64), (9, 8), (23, 16), (48, 8)])
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
 def test_mamamm_tcgen05_matches_fp32_kernel(n, d, ta, tb):
-    """tcgen05 TF32 path (algo 1) against the exact-fp32 kernel (algo 0): 1e-2 relative
+    """tcgen05 TF32 paths (algo 1, 2) against the exact-fp32 kernel (algo 0): 1e-2 relative
     (BASELINE.json: bf16/TF32 mamamm within a stated 1e-2), pads exactly zero."""
     import pygho_b200.ops  # noqa: F401
     gen = torch.Generator().manual_seed(n * 131 + d)
@@ -459,10 +459,42 @@ def test_mamamm_tcgen05_matches_fp32_kernel(n, d, ta, tb):
         got = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, e, 1)
         assert float((got - ref).abs().max()) <= 1e-2 * scale
         assert float(got[~mask].abs().max()) == 0.0
+        # the pipelined kernel issues the same MMAs on the same tiles: identical bits
+        # (n = 48 needs two stages of 144 KB -> it falls back to the algo-1 kernel)
+        pipe = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, e, 2)
+        assert torch.equal(pipe, got)
         # the fp32 kernel with extents is bit-identical to the one without
         assert torch.equal(torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, e, 0), ref)
     from pygho_b200.ops import mask_extents
     assert torch.equal(mask_extents(mask).cpu(), torch.stack((sizes, sizes), 1).to(torch.int32))
+    torch.cuda.synchronize()
+
+
+def test_mamamm_pipeline_many_items():
+    """The persistent pipeline with more work items than CTAs (b * dense / 8 = 800 > 148),
+    graphs of every size incl. empty ones, a mask with holes: bit-identical to the
+    one-CTA-per-item tcgen05 kernel, pads exactly zero, 1e-2 against exact fp32."""
+    import pygho_b200.ops  # noqa: F401
+    gen = torch.Generator().manual_seed(7)
+    b, n, d = 50, 40, 128
+    sizes = torch.randint(0, n + 1, (b,), generator=gen)
+    sizes[0], sizes[1], sizes[2] = n, 0, 1
+    ar = torch.arange(n)
+    mask = (ar[None, :, None] < sizes[:, None, None]) & (ar[None, None, :] < sizes[:, None, None])
+    holes = mask & (torch.rand((b, n, n), generator=gen) < 0.8)
+    mask, holes = mask.to(DEV), holes.to(DEV)
+    A = (torch.randn((b, n, n, d), generator=gen).to(DEV) * mask.unsqueeze(-1)).contiguous()
+    Bm = (torch.randn((b, n, n, d), generator=gen).to(DEV) * mask.unsqueeze(-1)).contiguous()
+    ext = torch.stack((sizes, sizes, sizes), 1).to(torch.int32).to(DEV)
+    ref = torch.ops.pygho_b200.mamamm(A, False, Bm, False, holes, None, 0)
+    for e in (None, ext):
+        one = torch.ops.pygho_b200.mamamm(A, False, Bm, False, holes, e, 1)
+        # poison the output allocation so unwritten positions would be noticed
+        torch.full((b, n, n, d), float("nan"), device=DEV)
+        pipe = torch.ops.pygho_b200.mamamm(A, False, Bm, False, holes, e, 2)
+        assert torch.equal(pipe, one)
+        assert float(pipe[~holes].abs().max()) == 0.0
+        assert float((pipe - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
     torch.cuda.synchronize()
 
 
