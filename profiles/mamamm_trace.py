@@ -1,5 +1,5 @@
-"""Timeline of the pipelined mamamm kernel (algo 2): %globaltimer stamps of the producer,
-MMA and epilogue roles of CTA 0 for its first work items (pgh_debug_trace hook)."""
+"""Timeline of the pipelined mamamm kernel (algo 2): %globaltimer stamps of the copy,
+transposer, MMA and epilogue roles of CTA 0 for its first work items (pgh_debug_trace hook)."""
 import os
 import sys
 
@@ -23,15 +23,14 @@ ext = torch.stack((sizes, sizes, sizes), 1).to(torch.int32).to(dev)
 for _ in range(3):
     torch.ops.pygho_b200.mamamm(A, False, B, False, mask, ext, 2)
 K = 32
-buf = torch.zeros(3 * K * 4, dtype=torch.int64, device=dev)
+buf = torch.zeros(4 * K * 4, dtype=torch.int64, device=dev)
 _lib.call("pgh_debug_trace", buf.data_ptr(), buf.numel())
 torch.ops.pygho_b200.mamamm(A, False, B, False, mask, ext, 2)
 torch.cuda.synchronize()
 _lib.call("pgh_debug_trace", None, 0)
-t = buf.cpu().numpy().reshape(3, K, 4)
+t = buf.cpu().numpy().reshape(4, K, 4)
 t0 = t[t > 0].min()
-names = [("P", ("top", "stage free", "issued", "prev landed")), ("M", ("top", "full", "acc free", "committed")),
-         ("E", ("top", "mask+zero", "acc full", "done"))]
+names = [("C", ()), ("T", ()), ("M", ()), ("E", ())]
 items = [it for it in range(0, b * d // 8, 148)]
 for q in range(16):
     g = items[q] // 16 if q < len(items) else -1
@@ -39,5 +38,7 @@ for q in range(16):
     for r, (nm, evs) in enumerate(names):
         line += f"| {nm} " + " ".join(f"{(t[r, q, e] - t0) / 1e3:6.2f}" if t[r, q, e] else "   -  " for e in range(4)) + " "
     print(line)
-print("columns (us since first stamp): P = top / stage free / issued / prev landed; M = top / operands full / acc free / "
-      "committed; E = top / mask+zeros done / acc full / item done")
+print("us since first stamp.  C(opy warp) = zeros written / ring space granted / copies issued; "
+      "T(ransposers) = mask loads issued / operands landed / tiles free / tiles written; "
+      "M(MA warp) = top / tiles full / accumulator free / all rounds issued; "
+      "E(pilogue) = top / mask row read / accumulator full / item stored")

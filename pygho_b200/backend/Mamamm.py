@@ -20,8 +20,8 @@ from .MaTensor import MaskedTensor
 def default_algo() -> int:
     """0 = exact-fp32 CUDA-core kernel, 1 = tcgen05 TF32 tensor-core kernel with one CTA per
     (graph, channel slab), 2 = the same tiles and MMAs in a persistent warp-specialised
-    pipeline.  Default 1 (the reference runs this contraction in TF32 too, example/zinc.py:30)."""
-    return int(os.environ.get("PYGHO_B200_MAMAMM_ALGO", "1"))
+    pipeline (default; the reference runs this contraction in TF32 too, example/zinc.py:30)."""
+    return int(os.environ.get("PYGHO_B200_MAMAMM_ALGO", "2"))
 
 
 def mamamm(A: MaskedTensor, dim1: int, B: MaskedTensor, dim2: int, mask: BoolTensor,

@@ -19,6 +19,8 @@
 // HBM-bound by design (13 flop/B vs a ridge of ~200 flop/B): what matters is that every
 // byte is read once, in full sectors, and that loads of one CTA overlap the MMA/epilogue of
 // the other CTA on the SM.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pgh {
@@ -61,17 +63,20 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // bounded spin: a lost arrival traps instead of hanging the GPU
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+  // try_wait with a suspend-time hint: the waiting warp is parked by the hardware until the
+  // phase completes (or the hint expires) instead of spinning -- a spinning waiter competes
+  // for issue slots with the working warps of its scheduler, which made every role of the
+  // pipelined kernel several times slower.  Bounded: a lost arrival traps instead of hanging.
+  for (uint32_t spin = 0; spin < (1u << 12); ++spin) {
     uint32_t done;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(1000000u)
         : "memory");
     if (done) return;
   }
@@ -333,29 +338,29 @@ mamamm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B,
 
 
 // ---------------------------------------------------------------------------------------
-// Pipelined variant (algo 2): one persistent CTA per SM, three warp roles, the same tile
-// layout and MMA shape as above.
-//   * producer warps (8 = two groups of 4, group s owns shared-memory stage s and every
-//     second work item): 128-bit loads of the two operand slabs, transposed on the fly into
-//     the per-channel K-major tiles exactly like the kernel above (load_tiles), plus the
-//     item's mask tile; while one group waits for its loads or stores its tiles the other
-//     group's loads are in flight, so the load stream does not drain between items.
-//     (A 4-byte cp.async scatter was measured first: LDGSTS.32 with 32 distinct destination
-//     rows costs ~46 cycles per warp instruction and starves the whole LSU,
-//     profiles/r1_mamamm_pipe.md.)
-//   * MMA warp (one elected thread): waits for a full stage and a free accumulator, issues
-//     the tcgen05.mma K-steps of 4 or 8 channels (one "round") and commits to the
-//     accumulator-full barrier; after the last round of an item the commit also releases
-//     the shared-memory stage.
-//   * epilogue warps (8, two per TMEM lane quarter): zero the pad positions of the item,
-//     pull their mask row out of the stage into a 64-bit register, then per round
-//     tcgen05.ld -> masked 16/32 B stores and hand the accumulator back.
-// Two shared-memory stages and two TMEM accumulators (2 x 256 columns) decouple the roles.
+// Pipelined variant (algo 2): one persistent CTA per SM, four warp roles, the same tile
+// layout and MMA shape as above.  What the one-CTA-per-item kernel cannot do is keep enough
+// bytes in flight: a loaded HBM round trip is ~2 us on B200, so an SM needs >= 64 KB of
+// outstanding loads *all the time* to see its share of the bandwidth, while a register-
+// staged load phase holds ~40 KB for a fraction of the CTA's life (profiles/r1_mamamm_pipe.md).
+//   * copy warps (3): walk the CTA's work items (graph, 8-channel slab) and streams both
+//     operand slabs global -> shared with 16-byte cp.async (LDGSTS.128, one instruction per
+//     16 positions) into a byte ring of ~120 KB: no registers, no waiting, 3-4 typical items
+//     in flight.  Completion is signalled per item by cp.async.mbarrier.arrive.
+//   * transposer warps (8): wait for an item to land, re-lay it from the ring into the 8
+//     per-channel K-major UMMA tiles (LDS.128 + 4 STS.32 in the bank-conflict-free lane
+//     mapping of load_tiles), stage the mask tile, hand the ring bytes back.
+//   * MMA warp: warp-uniform control flow, one elected lane issues the tcgen05.mma K-steps
+//     of 4 or 8 channels (one "round") into one of two TMEM accumulators and commits.
+//   * epilogue warps (8, two per TMEM lane quarter): mask row -> 64-bit register, then per
+//     round tcgen05.ld -> masked 32-byte (256-bit) stores and hand the accumulator back.
+//     The warps whose quarter has no valid row of the item write the zeros of its pad
+//     positions afterwards (whole dense rows, shared among the slab items of a graph).
 constexpr int kTraceItems = 32;
 __device__ unsigned long long* g_trace = nullptr;
 __device__ long long g_trace_words = 0;
 // profiling hook (pgh_debug_trace): 64-bit %globaltimer stamps of CTA 0, laid out as
-// [role 0..2][item slot 0..kTraceItems-1][event 0..3]
+// [role 0..3][item slot 0..kTraceItems-1][event 0..3]
 __device__ __forceinline__ void trace(unsigned long long* t, int role, int q, int ev) {
   if (t && q < kTraceItems) {
     unsigned long long now;
@@ -364,11 +369,19 @@ __device__ __forceinline__ void trace(unsigned long long* t, int role, int q, in
   }
 }
 
-constexpr int kPipeProducers = 8;   // warps 0..7: two groups of kPipeGroup warps
-constexpr int kPipeGroup = 4;
-constexpr int kPipeEpi = 8;         // warps 9..16 (warp 8 issues the MMAs)
-constexpr int kPipeThreads = (kPipeProducers + 1 + kPipeEpi) * 32;
+// Roles are laid out by scheduler (warp & 3 = SM sub-partition): the five roles run five
+// different loops, and a sub-partition whose warps all run the same loop keeps it in its
+// instruction cache.  The epilogue has to sit on all four (a warp can only read the TMEM lanes
+// of its own quarter), but for graphs of <= 32 nodes only quarter 0 has rows.
+//   warps 0..7   epilogue (quarter = warp & 3, two per quarter)
+//   warps 8..19  scheduler 1, 2: transposers; scheduler 3: copy; scheduler 0: MMA + 2 transposers
+constexpr int kPipeCopy = 3;
+constexpr int kPipeXpose = 8;
+constexpr int kPipeEpi = 8;
+constexpr int kPipeThreads = 20 * 32;
+enum PipeRole { kRoleEpi, kRoleXpose, kRoleCopy, kRoleMma };
 constexpr int kPipeAccCols = 256;
+constexpr int kRingSlots = 8;       // items in flight in the staging ring (barrier pairs)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -377,6 +390,27 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(saddr)
+               : "memory");
+  return v;
 }
 
 struct PipeItem {
@@ -399,7 +433,145 @@ __device__ __forceinline__ PipeItem pipe_item(int it, int slabs, const int* __re
   return I;
 }
 
-template <int CH>
+// staging of one item in the ring: operand A rows at [0, ni * pitch), operand B rows after
+// them; a row holds k_pad positions of 32 B (8 channels) plus 16 B of padding, which spreads
+// the 16 B pieces of a column-wise copy over all banks
+struct PipeStage {
+  int pitch, off_b, bytes;
+};
+__device__ __forceinline__ PipeStage pipe_stage(const PipeItem& I) {
+  PipeStage S;
+  S.pitch = ((I.nj + 7) & ~7) * 32 + 16;
+  S.off_b = I.ni * S.pitch;
+  S.bytes = ((I.ni + I.nk) * S.pitch + 127) & ~127;
+  return S;
+}
+// every role replays the same allocation rule, so ring offsets need no communication
+__device__ __forceinline__ int ring_place(int& head, int bytes, int cap) {
+  const int off = (head + bytes > cap) ? 0 : head;
+  head = off + bytes;
+  return off;
+}
+
+// global -> ring: positions are walked along the dimension that is contiguous in global
+// memory (stride one position = dense floats); copy warp cw takes every kPipeCopy-th outer
+// row, lane = (position & 15, 16-byte half).  One warp issues ~0.2 instructions per cycle
+// on dependent address arithmetic, hence several copy warps and a two-add inner loop.
+__device__ __forceinline__ void pipe_copy_operand(const float* __restrict__ src, uint32_t stg,
+                                                  int n_rows, int nj, long long s_row,
+                                                  long long s_k, int dense, int pitch, int cw,
+                                                  int lane) {
+  const int h = lane & 1, p = lane >> 1;
+  const bool k_inner = (s_k == 1);
+  const int n_in = k_inner ? nj : n_rows, n_out = k_inner ? n_rows : nj;
+  const size_t pos_bytes = (size_t)dense * 4;
+  const size_t out_bytes = (size_t)(k_inner ? s_row : s_k) * pos_bytes;
+  const uint32_t in_step = k_inner ? 32u : (uint32_t)pitch, out_step = k_inner ? (uint32_t)pitch : 32u;
+  const char* gp_row = reinterpret_cast<const char*>(src) + h * 16 + (size_t)p * pos_bytes +
+                       (size_t)cw * out_bytes;
+  uint32_t dst_row = stg + (uint32_t)h * 16u + (uint32_t)p * in_step + (uint32_t)cw * out_step;
+  const size_t g16 = 16 * pos_bytes, g_out = kPipeCopy * out_bytes;
+  const uint32_t s16 = 16u * in_step, s_out = kPipeCopy * out_step;
+  const bool p0 = p < n_in, p1 = p + 16 < n_in;
+  for (int o = cw; o < n_out; o += kPipeCopy) {
+    if (p0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_row), "l"(gp_row) : "memory");
+    if (p1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_row + s16), "l"(gp_row + g16) : "memory");
+    if (n_in > 32) {
+      const char* gp = gp_row + 2 * g16;
+      uint32_t dst = dst_row + 2 * s16;
+      for (int t = p + 32; t < n_in; t += 16) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gp) : "memory");
+        gp += g16;
+        dst += s16;
+      }
+    }
+    gp_row += g_out;
+    dst_row += s_out;
+  }
+}
+
+// ring -> the 8 channel tiles of both operands.  A warp takes a patch row (4 tile rows of one
+// operand) and walks its K quads; lane = (r2, kq, h) as in load_tiles, so each LDS.128
+// quarter-warp reads 128 contiguous bytes and every STS.32 hits 32 different banks.
+template <int kWarps>
+__device__ __forceinline__ void pipe_transpose(uint32_t stg_a, uint32_t stg_b, int pitch,
+                                               unsigned char* tiles_a, unsigned char* tiles_b,
+                                               int rows_a, int rows_b, int ts_a, int ts_b, int nj,
+                                               int k_pad, int sbo, int warp, int lane) {
+  const int h = lane & 1, kq = (lane >> 1) & 3, r2 = lane >> 3;
+  const int kquads = k_pad >> 2;
+  const int npa = (rows_a + 3) >> 2, npb = (rows_b + 3) >> 2;
+  for (int pp = warp; pp < npa + npb; pp += kWarps) {
+    const bool is_b = pp >= npa;
+    const int row = (is_b ? pp - npa : pp) * 4 + r2;
+    if (row >= (is_b ? rows_b : rows_a)) continue;
+    const int ts = is_b ? ts_b : ts_a;
+    uint32_t src = (is_b ? stg_b : stg_a) + (uint32_t)(row * pitch + kq * 32 + h * 16);
+    unsigned char* dst = (is_b ? tiles_b : tiles_a) + (4 * h) * ts + (row >> 3) * sbo + (row & 7) * 16 + kq * 4;
+    const int nq_live = (nj - kq + 3) >> 2;            // quads whose kcol = 4 pr + kq < nj
+#pragma unroll 2
+    for (int pr = 0; pr < kquads; ++pr) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pr < nq_live) v = lds128(src);
+      *reinterpret_cast<float*>(dst) = v.x;
+      *reinterpret_cast<float*>(dst + ts) = v.y;
+      *reinterpret_cast<float*>(dst + 2 * ts) = v.z;
+      *reinterpret_cast<float*>(dst + 3 * ts) = v.w;
+      src += 128u;
+      dst += kCoreBytes;
+    }
+  }
+}
+
+// zeros outside the valid rectangle of one item.  The 32-byte pieces of one slab would cost
+// one L2 request each; instead the `slabs` items of a graph share the pad positions among them
+// (position p = i * n_k + k belongs to slab p % slabs) and write whole dense rows, 128 B per
+// request.  The 32 lanes test 32 candidate positions at once (one division per lane, in
+// parallel), then the warp visits them and stores one 512 B row per pad position.
+__device__ __forceinline__ void pipe_zero_item(const PipeItem& I, const TcGeom& g, int slabs,
+                                               int dense, float* __restrict__ out, int zr, int nz,
+                                               int lane) {
+  const int ni = I.empty ? 0 : I.ni, nk = I.nk;
+  const int sidx = I.c0 / kCS;
+  const int total = g.n_i * g.n_k;
+  float* og = out + (size_t)I.b * total * dense + lane * 4;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  // candidate m of this slab is position sidx + m * slabs; warp zr takes m = zr (mod nz)
+  for (int m0 = zr; sidx + m0 * slabs < total; m0 += 32 * nz) {
+    const int p = sidx + (m0 + lane * nz) * slabs;
+    const int i = p / g.n_k, k = p - i * g.n_k;
+    const bool pad = p < total && (i >= ni || k >= nk);
+    unsigned todo = __ballot_sync(0xffffffffu, pad);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      float* o = og + (size_t)(sidx + (m0 + src * nz) * slabs) * dense;
+      for (int c = lane * 4; c < dense; c += 128) *reinterpret_cast<float4*>(o + (c - lane * 4)) = z;
+    }
+  }
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
+__device__ __forceinline__ void st256(float* p, const float4& a, const float4& b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y),
+               "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+
+template <int CH, bool WIDE>
 __device__ __forceinline__ void pipe_epilogue_round(uint32_t tacc, int quarter, int alt, int n_pad,
                                                     int nk, bool row_ok, unsigned long long mbits,
                                                     float* orow, int dense) {
@@ -411,50 +583,74 @@ __device__ __forceinline__ void pipe_epilogue_round(uint32_t tacc, int quarter, 
       tmem_ld8(tacc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * n_pad + kc * 8), v[cc]);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (row_ok) {
+      float* o = orow + (size_t)(kc * 8) * dense;
+      const unsigned have = (unsigned)(mbits >> (kc * 8)) & 0xffu;
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
-        const int k = kc * 8 + kk;
-        if (k < nk) {
-          const bool m = (mbits >> k) & 1ull;
-          float* o = orow + (size_t)k * dense;
+        if (kc * 8 + kk < nk) {
+          const bool m = (have >> kk) & 1u;
+          float4 w[CH / 4];
 #pragma unroll
-          for (int q = 0; q < CH / 4; ++q) {
-            const float4 w = m ? make_float4(v[4 * q][kk], v[4 * q + 1][kk], v[4 * q + 2][kk], v[4 * q + 3][kk])
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(o + 4 * q) = w;
+          for (int q = 0; q < CH / 4; ++q)
+            w[q] = m ? make_float4(v[4 * q][kk], v[4 * q + 1][kk], v[4 * q + 2][kk], v[4 * q + 3][kk])
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (CH == 8 && WIDE) {
+            st256(o, w[0], w[1]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < CH / 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = w[q];
           }
         }
+        o += dense;
       }
     }
   }
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 mamamm_tc_pipe_kernel(const float* __restrict__ A, const float* __restrict__ B,
                       const unsigned char* __restrict__ mask, const int* __restrict__ ext,
-                      int dense, int n_items, int stage_bytes, int mask_off, TcGeom g,
-                      float* __restrict__ out) {
+                      int dense, int n_items, int mask_off, int mask_stride, int ring_off, int ring_bytes,
+                      TcGeom g,
+                      int dbg, float* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // barriers: full[2], empty[2] (smem stages), tfull[2], tempty[2] (TMEM accumulators)
-  __shared__ __align__(8) unsigned long long bars[8];
+  // barriers: [0,8) ring full, [8,16) ring freed, 16 tiles full, 17 tiles empty,
+  //           18,19 accumulator full, 20,21 accumulator empty, 22..24 mask tile full
+  __shared__ __align__(8) unsigned long long bars[2 * kRingSlots + 9];
   __shared__ uint32_t tmem_base_holder;
+  __shared__ int ring_meta[kPipeCopy * 2 * kRingSlots];   // per copy warp: (offset, bytes) of items in flight
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int role = kRoleEpi, ridx = warp;            // ridx: index of the warp inside its role
+  if (warp >= kPipeEpi) {
+    const int sch = warp & 3, j = (warp - kPipeEpi) >> 2;
+    if (sch == 1 || sch == 2) { role = kRoleXpose; ridx = (sch - 1) * 3 + j; }
+    else if (sch == 3) { role = kRoleCopy; ridx = j; }
+    else if (j == 0) { role = kRoleMma; ridx = 0; }
+    else { role = kRoleXpose; ridx = 5 + j; }
+  }
   const int slabs = dense / kCS;
   const uint32_t bar0 = smem_u32(bars);
 #define PGH_BAR(i) (bar0 + 8u * (uint32_t)(i))
+  constexpr int kFull = 0, kFreed = kRingSlots, kTilesFull = 2 * kRingSlots,
+                kTilesEmpty = kTilesFull + 1, kAccFull = kTilesFull + 2, kAccEmpty = kTilesFull + 4,
+                kMaskFull = kTilesFull + 6;
   if (tid == 0) {
-    mbar_init(PGH_BAR(0), kPipeGroup * 32);      // full: the stage's producer group
-    mbar_init(PGH_BAR(1), kPipeGroup * 32);
-    mbar_init(PGH_BAR(2), 1 + kPipeEpi);         // empty: MMA commit + mask read by the epilogue
-    mbar_init(PGH_BAR(3), 1 + kPipeEpi);
-    mbar_init(PGH_BAR(4), 1);                    // tfull: MMA commit
-    mbar_init(PGH_BAR(5), 1);
-    mbar_init(PGH_BAR(6), kPipeEpi);             // tempty: epilogue warps
-    mbar_init(PGH_BAR(7), kPipeEpi);
+    for (int k = 0; k < kRingSlots; ++k) {
+      mbar_init(PGH_BAR(kFull + k), kPipeCopy * 32);   // cp.async completion of every copy lane
+      mbar_init(PGH_BAR(kFreed + k), kPipeXpose);      // transposer warps are done reading
+    }
+    mbar_init(PGH_BAR(kTilesFull), kPipeXpose * 32);
+    mbar_init(PGH_BAR(kTilesEmpty), 1);                // MMA commit
+    mbar_init(PGH_BAR(kAccFull), 1);
+    mbar_init(PGH_BAR(kAccFull + 1), 1);
+    mbar_init(PGH_BAR(kAccEmpty), kPipeEpi);
+    mbar_init(PGH_BAR(kAccEmpty + 1), kPipeEpi);
+    for (int k = 0; k < 3; ++k) mbar_init(PGH_BAR(kMaskFull + k), kPipeXpose * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kPipeProducers) {
+  if (role == kRoleMma) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_holder)),
                  "r"(2 * kPipeAccCols)
@@ -464,79 +660,138 @@ mamamm_tc_pipe_kernel(const float* __restrict__ A, const float* __restrict__ B,
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_base_holder;
   const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring_base = smem_base + (uint32_t)ring_off;
   unsigned long long* tr =
-      (blockIdx.x == 0 && lane == 0 && g_trace_words >= 3 * kTraceItems * 4) ? g_trace : nullptr;
+      (blockIdx.x == 0 && lane == 0 && g_trace_words >= 4 * kTraceItems * 4) ? g_trace : nullptr;
 
-  if (warp < kPipeProducers) {
-    // ------------------------------------------------------------------ producers
-    const int grp = warp / kPipeGroup, gw = warp % kPipeGroup, gtid = gw * 32 + lane;
-    unsigned char* stage = smem + (size_t)grp * stage_bytes;
-    int q = 0;
+  if (role == kRoleCopy) {
+    // ------------------------------------------------------------------ copy warps
+    // every copy warp replays the same ring bookkeeping (private copy of the in-flight list)
+    const int cw = ridx;
+    int* meta = ring_meta + cw * 2 * kRingSlots;
+    int q = 0, oldest = 0, head = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const PipeItem I = pipe_item(it, slabs, ext, g);
       if (I.empty) continue;
-      if ((q & 1) == grp) {
-        if (gw == 0) trace(tr, 0, q, 0);
-        mbar_wait(PGH_BAR(2 + grp), (uint32_t)(((q >> 1) & 1) ^ 1));    // stage free?
-        if (gw == 0) trace(tr, 0, q, 1);
-        const int k_pad = (I.nj + 7) & ~7;
-        const unsigned char* mb = mask + (size_t)I.b * g.n_i * g.n_k;
-        constexpr int kMV = 16;
-        unsigned char mv[kMV];
-        const int total = I.ni * g.n_k;
-#pragma unroll
-        for (int m = 0; m < kMV; ++m) {
-          const int t = gtid + m * kPipeGroup * 32;
-          mv[m] = t < total ? __ldg(mb + t) : 0;
+      if (cw == 0) trace(tr, 0, q, 0);
+      const PipeStage S = pipe_stage(I);
+      const int off = ring_place(head, S.bytes, ring_bytes);
+      // wait until no item still in the ring overlaps [off, off + bytes)
+      for (;;) {
+        bool clash = (q - oldest) >= kRingSlots;
+        for (int j = oldest; j < q && !clash; ++j) {
+          const int o = meta[2 * (j % kRingSlots)], sz = meta[2 * (j % kRingSlots) + 1];
+          clash = !(o + sz <= off || off + S.bytes <= o);
         }
-        OperandView va{A + (size_t)I.b * g.n_i * g.n_j * dense + I.c0, stage, I.ni, g.ts_a, g.sa_i, g.sa_j};
-        OperandView vb{B + (size_t)I.b * g.n_j * g.n_k * dense + I.c0, stage + g.off_b, I.nk, g.ts_b, g.sb_k, g.sb_j};
-        load_tiles<kPipeGroup>(va, vb, I.nj, k_pad, dense, g.sbo, gw, lane);
-        if (gw == 0) trace(tr, 0, q, 2);
-#pragma unroll
-        for (int m = 0; m < kMV; ++m) {
-          const int t = gtid + m * kPipeGroup * 32;
-          if (t < total) stage[mask_off + t] = mv[m];
-        }
-        for (int t = gtid + kMV * kPipeGroup * 32; t < total; t += kPipeGroup * 32)
-          stage[mask_off + t] = __ldg(mb + t);
-        // generic-proxy writes -> visible to the tensor-core (async) proxy, then publish
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(PGH_BAR(grp));
-        if (gw == 0) trace(tr, 0, q, 3);
+        if (!clash) break;
+        mbar_wait(PGH_BAR(kFreed + oldest % kRingSlots), (uint32_t)((oldest / kRingSlots) & 1));
+        ++oldest;
       }
+      if (cw == 0) trace(tr, 0, q, 1);
+      const uint32_t stg = ring_base + (uint32_t)off;
+      if (!(dbg & 4)) {
+      pipe_copy_operand(A + (size_t)I.b * g.n_i * g.n_j * dense + I.c0, stg, I.ni, I.nj, g.sa_i,
+                        g.sa_j, dense, S.pitch, cw, lane);
+      pipe_copy_operand(B + (size_t)I.b * g.n_j * g.n_k * dense + I.c0, stg + (uint32_t)S.off_b,
+                        I.nk, I.nj, g.sb_k, g.sb_j, dense, S.pitch, cw, lane);
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
+                       PGH_BAR(kFull + q % kRingSlots))
+                   : "memory");
+      __syncwarp();
+      meta[2 * (q % kRingSlots)] = off;
+      meta[2 * (q % kRingSlots) + 1] = S.bytes;
+      __syncwarp();
+      if (cw == 0) trace(tr, 0, q, 2);
       ++q;
     }
-  } else if (warp == kPipeProducers) {
+  } else if (role == kRoleXpose) {
+    // ------------------------------------------------------------------ transposers
+    const int tw = ridx, ttid = tw * 32 + lane;
+    int q = 0, head = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const PipeItem I = pipe_item(it, slabs, ext, g);
+      if (I.empty) continue;
+      const PipeStage S = pipe_stage(I);
+      const int off = ring_place(head, S.bytes, ring_bytes);
+      // mask bytes of the item: issued now, consumed after the operands have landed
+      const unsigned char* mb = mask + (size_t)I.b * g.n_i * g.n_k;
+      // warp tw takes rows tw, tw + 8, ...: lane = column k (and k + 32); the bytes are
+      // requested now, balloted into one 64-bit word per row after the operands have landed
+      constexpr int kMR = 4;                    // rows per warp held in registers (n_i <= 32)
+      unsigned char mlo[kMR], mhi[kMR];
+#pragma unroll
+      for (int m = 0; m < kMR; ++m) {
+        const int r = tw + m * kPipeXpose;
+        mlo[m] = (r < I.ni && lane < I.nk) ? __ldg(mb + r * g.n_k + lane) : 0;
+        mhi[m] = (r < I.ni && lane + 32 < I.nk) ? __ldg(mb + r * g.n_k + lane + 32) : 0;
+      }
+      if (tw == 0) trace(tr, 1, q, 0);
+      mbar_wait(PGH_BAR(kFull + q % kRingSlots), (uint32_t)((q / kRingSlots) & 1));   // landed
+      if (tw == 0) trace(tr, 1, q, 1);
+      mbar_wait(PGH_BAR(kTilesEmpty), (uint32_t)((q & 1) ^ 1));                       // tiles free
+      if (tw == 0) trace(tr, 1, q, 2);
+      const uint32_t stg = ring_base + (uint32_t)off;
+      pipe_transpose<kPipeXpose>(stg, stg + (uint32_t)S.off_b, S.pitch, smem, smem + g.off_b, I.ni,
+                                 I.nk, g.ts_a, g.ts_b, I.nj, (I.nj + 7) & ~7, g.sbo, tw, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(PGH_BAR(kFreed + q % kRingSlots));                   // ring bytes back
+      // three mask tiles in rotation: the epilogue reads tile q % 3 at the start of item q,
+      // and the MMAs of item q + 2 cannot be issued before it has drained an accumulator of
+      // item q, so tile q % 3 is free again when item q + 3 is transposed
+      unsigned long long* mtile = reinterpret_cast<unsigned long long*>(smem + mask_off + (q % 3) * mask_stride);
+#pragma unroll
+      for (int m = 0; m < kMR; ++m) {
+        const int r = tw + m * kPipeXpose;
+        const unsigned lo = __ballot_sync(0xffffffffu, mlo[m] != 0), hi = __ballot_sync(0xffffffffu, mhi[m] != 0);
+        if (r < I.ni && lane == 0) mtile[r] = ((unsigned long long)hi << 32) | lo;
+      }
+      for (int r = tw + kMR * kPipeXpose; r < I.ni; r += kPipeXpose) {     // graphs of > 32 nodes
+        const unsigned lo = __ballot_sync(0xffffffffu, lane < I.nk && __ldg(mb + r * g.n_k + lane) != 0);
+        const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < I.nk && __ldg(mb + r * g.n_k + lane + 32) != 0);
+        if (lane == 0) mtile[r] = ((unsigned long long)hi << 32) | lo;
+      }
+      // the epilogue may be two items behind, which a one-bit phase cannot express on the
+      // tiles barrier: each mask tile has its own barrier (one phase per three items)
+      mbar_arrive(PGH_BAR(kMaskFull + q % 3));
+      // generic-proxy writes -> visible to the tensor-core (async) proxy, then publish
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(PGH_BAR(kTilesFull));
+      if (tw == 0) trace(tr, 1, q, 3);
+      ++q;
+    }
+  } else if (role == kRoleMma) {
     // ------------------------------------------------------------------ MMA issue
-    if (lane == 0) {
-      int q = 0, rr = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const PipeItem I = pipe_item(it, slabs, ext, g);
-        if (I.empty) continue;
-        const int s = q & 1;
-        const int ksteps = ((I.nj + 7) & ~7) / 8;
-        const int n_pad = max((I.nk + 15) & ~15, 16);
-        const int ch_round = (kCS * n_pad <= kPipeAccCols) ? 8 : 4;
-        const uint32_t idesc = umma_idesc_tf32(128, n_pad);
-        const uint32_t st = smem_base + (uint32_t)(s * stage_bytes);
-        trace(tr, 1, q, 0);
-        mbar_wait(PGH_BAR(s), (uint32_t)((q >> 1) & 1));              // operands landed
-        trace(tr, 1, q, 1);
+    // the whole warp runs the (warp-uniform) control flow; values that feed the descriptors
+    // are broadcast from lane 0 so that they live in uniform registers
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_holder, 0);
+    int q = 0, rr = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const PipeItem I = pipe_item(it, slabs, ext, g);
+      const int nj = __shfl_sync(0xffffffffu, I.nj, 0), nk = __shfl_sync(0xffffffffu, I.nk, 0);
+      const int ni = __shfl_sync(0xffffffffu, I.ni, 0);
+      if (ni == 0 || nj == 0 || nk == 0) continue;
+      const int ksteps = ((nj + 7) & ~7) / 8;
+      const int n_pad = max((nk + 15) & ~15, 16);
+      const int ch_round = (kCS * n_pad <= kPipeAccCols) ? 8 : 4;
+      const uint32_t idesc = umma_idesc_tf32(128, n_pad);
+      trace(tr, 2, q, 0);
+      mbar_wait(PGH_BAR(kTilesFull), (uint32_t)(q & 1));                // tiles written
+      trace(tr, 2, q, 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int r = 0; r < kCS / ch_round; ++r, ++rr) {
+        const int a = rr & 1;
+        mbar_wait(PGH_BAR(kAccEmpty + a), (uint32_t)(((rr >> 1) & 1) ^ 1));   // accumulator drained
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int r = 0; r < kCS / ch_round; ++r, ++rr) {
-          const int a = rr & 1;
-          mbar_wait(PGH_BAR(6 + a), (uint32_t)(((rr >> 1) & 1) ^ 1)); // accumulator drained
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (r == 0) trace(tr, 1, q, 2);
+        if (r == 0) trace(tr, 2, q, 2);
+        if (elect_one()) {
           for (int cc = 0; cc < ch_round; ++cc) {
             const int ch = r * ch_round + cc;
             // descriptors of K step 0; a K=8 step = 2 core matrices = +256 B = +16 in the
             // (address >> 4) start field, which never carries out of its 14 bits here
-            uint64_t da = umma_desc(st + (uint32_t)(ch * g.ts_a), kCoreBytes, g.sbo);
-            uint64_t db = umma_desc(st + (uint32_t)(g.off_b + ch * g.ts_b), kCoreBytes, g.sbo);
+            uint64_t da = umma_desc(smem_base + (uint32_t)(ch * g.ts_a), kCoreBytes, g.sbo);
+            uint64_t db = umma_desc(smem_base + (uint32_t)(g.off_b + ch * g.ts_b), kCoreBytes, g.sbo);
             const uint32_t td = tmem_base + (uint32_t)(a * kPipeAccCols + cc * n_pad);
             umma_tf32(td, da, db, idesc, 0u);
             for (int ks = 1; ks < ksteps; ++ks) {
@@ -545,72 +800,65 @@ mamamm_tc_pipe_kernel(const float* __restrict__ A, const float* __restrict__ B,
               umma_tf32(td, da, db, idesc, 1u);
             }
           }
-          umma_commit(PGH_BAR(4 + a));                                 // accumulator ready
+          umma_commit(PGH_BAR(kAccFull + a));                             // accumulator ready
+          if (r == kCS / ch_round - 1) umma_commit(PGH_BAR(kTilesEmpty)); // tiles may be rewritten
         }
-        umma_commit(PGH_BAR(2 + s));                                   // stage may be refilled
-        trace(tr, 1, q, 3);
-        ++q;
+        __syncwarp();
       }
+      trace(tr, 2, q, 3);
+      ++q;
     }
   } else {
     // ------------------------------------------------------------------ epilogue
+    const uint32_t tmem_base = tmem_base_holder;
     const int quarter = warp & 3;                     // TMEM lanes this warp may read
-    const int alt = (warp - (kPipeProducers + 1)) >> 2;
-    const int etid = tid - (kPipeProducers + 1) * 32; // 0 .. 255
+    const int alt = warp >> 2;
     const int row = quarter * 32 + lane;              // TMEM lane == output row i
     int rr = 0, q = 0;
     unsigned long long* etr = (quarter == 0 && alt == 0) ? tr : nullptr;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const PipeItem I = pipe_item(it, slabs, ext, g);
-      trace(etr, 2, q, 0);
+      // the zeros of the item's pad positions are written by the epilogue warps whose TMEM
+      // quarter holds no valid row of this item (6 of 8 for graphs of <= 32 nodes; all of
+      // them if every quarter is busy), after their barrier duties for the item: they stay
+      // in step with the pipeline but never hold it up
+      const int busy_q = I.empty ? 0 : (I.ni + 31) >> 5;
+      const int nz = busy_q < 4 ? 2 * (4 - busy_q) : kPipeEpi;
+      const int zr = busy_q >= 4 ? warp : (quarter >= busy_q ? (quarter - busy_q) * 2 + alt : -1);
+      if (I.empty) {
+        if (!(dbg & 1)) pipe_zero_item(I, g, slabs, dense, out, zr, nz, lane);
+        continue;
+      }
+      trace(etr, 3, q, 0);
       float* ob = out + (size_t)I.b * g.n_i * g.n_k * dense + I.c0;
-      // zeros outside the valid rectangle
-      {
-        const int h = etid & 1;
-        const int step = kPipeEpi * 32 / 2, di = step / g.n_k, dk = step - di * g.n_k;
-        int p = etid >> 1;
-        int i = p / g.n_k, k = p - i * g.n_k;
-        for (; p < g.n_i * g.n_k; p += step) {
-          if (I.empty || i >= I.ni || k >= I.nk)
-            *reinterpret_cast<float4*>(ob + (size_t)p * dense + 4 * h) = make_float4(0.f, 0.f, 0.f, 0.f);
-          i += di;
-          k += dk;
-          if (k >= g.n_k) { k -= g.n_k; ++i; }
-        }
-      }
-      if (I.empty) continue;
-      const int s = q & 1;
       const bool row_ok = row < I.ni;
-      // the mask row travels with the operands: read it out of the stage, then let it go
-      mbar_wait(PGH_BAR(s), (uint32_t)((q >> 1) & 1));
+      // the mask tile is written with the operand tiles: take this row's bits
+      mbar_wait(PGH_BAR(kMaskFull + q % 3), (uint32_t)((q / 3) & 1));
       unsigned long long mbits = 0ull;
-      if (row_ok) {
-        const unsigned char* mrow = smem + (size_t)s * stage_bytes + mask_off + row * g.n_k;
-        for (int k = 0; k < I.nk; ++k) mbits |= (unsigned long long)(mrow[k] != 0) << k;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(PGH_BAR(2 + s));
-      trace(etr, 2, q, 1);
+      if (row_ok)
+        mbits = reinterpret_cast<const unsigned long long*>(smem + mask_off + (q % 3) * mask_stride)[row];
+      trace(etr, 3, q, 1);
       const int n_pad = max((I.nk + 15) & ~15, 16);
       const int ch_round = (kCS * n_pad <= kPipeAccCols) ? 8 : 4;
       float* orow = ob + ((size_t)(row_ok ? row : 0) * g.n_k) * dense;
       for (int r = 0; r < kCS / ch_round; ++r, ++rr) {
         const int a = rr & 1;
-        mbar_wait(PGH_BAR(4 + a), (uint32_t)((rr >> 1) & 1));
+        mbar_wait(PGH_BAR(kAccFull + a), (uint32_t)((rr >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (r == 0) trace(etr, 2, q, 2);
+        if (r == 0) trace(etr, 3, q, 2);
         const uint32_t tacc = tmem_base + (uint32_t)(a * kPipeAccCols);
-        if (quarter * 32 < I.ni) {
+        if (quarter * 32 < I.ni && !(dbg & 2)) {
           if (ch_round == 8)
-            pipe_epilogue_round<8>(tacc, quarter, alt, n_pad, I.nk, row_ok, mbits, orow, dense);
+            pipe_epilogue_round<8, WIDE>(tacc, quarter, alt, n_pad, I.nk, row_ok, mbits, orow, dense);
           else
-            pipe_epilogue_round<4>(tacc, quarter, alt, n_pad, I.nk, row_ok, mbits, orow + r * 4, dense);
+            pipe_epilogue_round<4, WIDE>(tacc, quarter, alt, n_pad, I.nk, row_ok, mbits, orow + r * 4, dense);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(PGH_BAR(6 + a));
+        if (lane == 0) mbar_arrive(PGH_BAR(kAccEmpty + a));
       }
-      trace(etr, 2, q, 3);
+      trace(etr, 3, q, 3);
+      if (zr >= 0 && !(dbg & 1)) pipe_zero_item(I, g, slabs, dense, out, zr, nz, lane);
       ++q;
     }
   }
@@ -618,8 +866,8 @@ mamamm_tc_pipe_kernel(const float* __restrict__ A, const float* __restrict__ B,
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (warp == kPipeProducers) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+  if (role == kRoleMma) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_holder),
                  "r"(2 * kPipeAccCols)
                  : "memory");
   }
@@ -661,20 +909,39 @@ int mamamm_tc_launch(const float* A, int trans_a, const float* B, int trans_b,
   if (end_a > total) total = end_a;
   if (end_b > total) total = end_b;
   total = (total + 127) / 128 * 128;
-  // two stages of (operand tiles + mask tile) fit: persistent, warp-specialised pipeline
-  const int stage = total + (int)((n_i * n_k + 127) / 128 * 128);
-  if (pipelined && 2 * stage <= 227 * 1024) {
-    static int configured_pipe = 0;
-    if (configured_pipe < 2 * stage) {
-      PGH_CUDA(cudaFuncSetAttribute(mamamm_tc_pipe_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * stage));
-      configured_pipe = 2 * stage;
+  // persistent pipeline: one set of tiles + mask tile, the rest of shared memory is the
+  // staging ring, which must hold at least the largest possible item
+  {
+    const int mask_off = total;
+    const int mask_stride = (int)((n_i * 8 + 127) / 128 * 128);        // one 64-bit word per row
+    const int ring_off = total + 3 * mask_stride;
+    const int ring_bytes = (227 * 1024 - 1024 - ring_off) & ~127;    // 1 KB: static shared memory
+    const int64_t max_item = ((n_i + n_k) * (int64_t)(k_pad * 32 + 16) + 127) / 128 * 128;
+    if (pipelined && ring_bytes >= max_item) {
+      const int smem_bytes = ring_off + ring_bytes;
+      const bool wide = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
+      static bool configured_pipe = false;
+      if (!configured_pipe) {
+        PGH_CUDA(cudaFuncSetAttribute(mamamm_tc_pipe_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        PGH_CUDA(cudaFuncSetAttribute(mamamm_tc_pipe_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        configured_pipe = true;
+      }
+      const int64_t n_items = b * (dense / kCS);
+      const unsigned grid = (unsigned)(n_items < kSMs ? n_items : kSMs);
+      // timing experiments only (results are wrong): 1 = no zero fill, 2 = no epilogue, 4 = no copies
+      static const int dbg = [] { const char* e = getenv("PYGHO_B200_PIPE_DEBUG"); return e ? atoi(e) : 0; }();
+      if (wide)
+        mamamm_tc_pipe_kernel<true><<<grid, kPipeThreads, smem_bytes, s>>>(
+            A, B, mask, ext, (int)dense, (int)n_items, mask_off, mask_stride, ring_off, ring_bytes, g, dbg,
+            out);
+      else
+        mamamm_tc_pipe_kernel<false><<<grid, kPipeThreads, smem_bytes, s>>>(
+            A, B, mask, ext, (int)dense, (int)n_items, mask_off, mask_stride, ring_off, ring_bytes, g, dbg,
+            out);
+      return check_launch("mamamm_tc_pipe");
     }
-    const int64_t n_items = b * (dense / kCS);
-    const unsigned grid = (unsigned)(n_items < kSMs ? n_items : kSMs);
-    mamamm_tc_pipe_kernel<<<grid, kPipeThreads, 2 * stage, s>>>(A, B, mask, ext, (int)dense,
-                                                                (int)n_items, stage, total, g, out);
-    return check_launch("mamamm_tc_pipe");
   }
   g.off_mask = total;
   total += (int)((n_i * n_k + 127) / 128 * 128);
