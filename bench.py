@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=128, help="graphs per CPU reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch the resident-batch steps eagerly instead of replaying CUDA graphs")
     return ap.parse_args()
 
 
@@ -272,7 +274,8 @@ def run_b200(args):
     broadcast_parameters(model)
     keys = parse_precomputekey(model)
     bucket = FlatGradBucket(model.parameters())
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+    # capturable: the step counter lives on the device, so the optimizer can be graph-captured
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True, capturable=True)
 
     # synthetic data: `num_batches` distinct batches per rank (weak scaling: fixed per-GPU work)
     hbs = [make_batch(args.batch, seed=1000 * rank + i) for i in range(args.num_batches)]
@@ -302,13 +305,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launches()
         e0.record()
         for i in range(steps):
             fn(i)
+        if finish is not None:
+            finish()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
@@ -319,8 +324,31 @@ def run_b200(args):
     warm = max(3, args.warmup)
     for i in range(warm):
         train_step(dds[i % len(dds)])
+    # Resident batches: the whole step (fwd, loss, bwd, all-reduce, AdamW) of each batch is
+    # captured into one CUDA graph and replayed (pygho_b200/graph.py) -- the eager step needs
+    # 14.8 ms of host time for 16.4 ms of device time, i.e. it is nearly launch-bound.  If
+    # capture fails on this rank the eager step is used (it issues the same collectives).
+    graphs, graph_note = None, "eager (--no-graph)"
+    if not args.no_graph:
+        try:
+            from pygho_b200.graph import StepGraph
+            graphs = [StepGraph(lambda dd=dd: train_step(dd), warmup=1) for dd in dds]
+            graph_note = f"cuda graph replay, one graph per resident batch ({len(graphs)})"
+        except Exception as e:  # noqa: BLE001
+            graphs = None
+            graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            print(f"[bench] rank {rank}: {graph_note}", file=sys.stderr, flush=True)
+            torch.cuda.synchronize(device)
+    if graphs is not None:
+        run_step = lambda i: graphs[i % len(graphs)].replay()  # noqa: E731
+    else:
+        run_step = lambda i: train_step(dds[i % len(dds)])  # noqa: E731
+    for i in range(warm):
+        run_step(i)
     with ClockSampler(local) as clocks:
-        ms_total, launches = timed(lambda i: train_step(dds[i % len(dds)]), args.steps)
+        ms_total, launches = timed(run_step, args.steps)
+    if graphs is not None:                                # replays do not pass through Python
+        launches = sum(graphs[i % len(graphs)].launches for i in range(args.steps))
     clock_summary = clocks.summary()
     ms_step = ms_total / args.steps
     value = args.batch * world / (ms_step * 1e-3)
@@ -332,14 +360,39 @@ def run_b200(args):
     from pygho_b200.hodata.device import DevicePrefetcher
     feeder = DevicePrefetcher(hbs, device, keys, pinned)
 
+    # The loss of every step is copied to pinned host memory and read by the host ONE step
+    # late (deferred logging): the host launches step i, then waits for step i-1's loss,
+    # then issues the prefetch of batch i+1 -- the GPU never idles while the host blocks.
+    # That wait is also the synchronisation DevicePrefetcher.advance() asks for (batch i-1
+    # is fully consumed before its buffers are recycled).
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+    losses = []
+    pending = [None]
+
+    def read_pending():
+        if pending[0] is not None:
+            slot = pending[0]
+            loss_evt[slot].synchronize()
+            losses.append(float(loss_host[slot]))            # D2H read of the result
+            pending[0] = None
+
     def e2e_step(i):
         dd = feeder.get()
         loss = train_step(dd)
+        slot = i & 1
+        loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_evt[slot].record()
+        read_pending()                                   # loss of the step before this one
+        pending[0] = slot
         feeder.advance()                                 # next batch's H2D + plans, side stream
-        return float(loss.item())                        # D2H read of the result
 
-    for i in range(max(3, len(hbs))):
-        e2e_step(i)
+    def e2e_steps(n):
+        for i in range(n):
+            e2e_step(i)
+        read_pending()                                   # every timed step's loss is read
+
+    e2e_steps(max(3, len(hbs)))
     if os.environ.get("PYGHO_B200_BENCH_DEBUG"):
         for i in range(12):
             torch.cuda.synchronize(device)
@@ -347,7 +400,10 @@ def run_b200(args):
             e2e_step(i)
             torch.cuda.synchronize(device)
             print(f"[debug] e2e step {i}: {1e3 * (time.perf_counter() - t0):.2f} ms", file=sys.stderr)
-    e2e_ms, _ = timed(e2e_step, args.steps)
+        read_pending()
+    losses.clear()
+    e2e_ms, _ = timed(e2e_step, args.steps, finish=read_pending)
+    assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: every step's loss is read"
     e2e_value = args.batch * world / (e2e_ms / args.steps * 1e-3)
 
     out = None
@@ -368,6 +424,7 @@ def run_b200(args):
                        "triples_per_key": int(dds[0][keys[0] + "___acd"].shape[1]),
                        "matmul": "tf32 (reference sets float32_matmul_precision('high'))",
                        "l2": f"step working set >> L2; {len(dds)} distinct batches rotated",
+                       "launch": graph_note,
                        "parallelism": f"dp{world} (graphs sharded, flat-bucket NCCL all-reduce)"},
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},

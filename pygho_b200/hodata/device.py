@@ -7,6 +7,8 @@ carries it (the reference precomputes plans per graph on the CPU and ships them 
 every batch) or it is built on the device by the fused plan kernels."""
 from __future__ import annotations
 
+import queue
+import threading
 from typing import Dict, Iterable, Optional
 
 import numpy as np
@@ -93,42 +95,88 @@ class DevicePrefetcher:
     The side stream never waits for the compute stream: everything it touches is allocated
     on it (its own allocator pool), and a batch's buffers only go back to that pool in
     ``advance()`` one step after the batch was consumed -- by which time the caller has
-    synchronised with that step (see ``advance``)."""
+    synchronised with that step (see ``advance``).
 
-    def __init__(self, host_batches, device, keys, pinned: Optional[dict] = None):
+    With ``threaded=True`` (default) the enqueueing itself (a few dozen small launches and
+    their Python glue, ~4 ms of host time per batch) runs on a worker thread, like a
+    DataLoader's pin-memory thread: the training step is launch-bound on the host
+    (profiles/r1_graph_probe.json: 14.8 ms of host time per 16.4 ms step), so host work on
+    the main thread would extend every step.  CUDA calls and the C-ABI kernels release the
+    GIL while they run."""
+
+    def __init__(self, host_batches, device, keys, pinned: Optional[dict] = None,
+                 threaded: bool = True):
         self.hbs, self.device, self.keys = list(host_batches), device, list(keys)
         self.pinned = {} if pinned is None else pinned
         self.stream = torch.cuda.Stream(device)
         self.pos = 0
         self._ready = self._inflight = None
-        self._issue()
+        self._error = None
+        self._done = threading.Event()
+        self._jobs: Optional[queue.Queue] = None
+        if threaded:
+            self._jobs = queue.Queue()
+            self._worker = threading.Thread(target=self._run, name="pygho-prefetch", daemon=True)
+            self._worker.start()
+        self._submit()
 
-    def _issue(self):
-        hb = self.hbs[self.pos % len(self.hbs)]
-        self.pos += 1
+    # -- the actual work: runs on the worker thread (or inline when not threaded)
+    def _issue(self, hb):
         with torch.cuda.stream(self.stream):
             dd = sp_datadict(hb, self.device, self.keys, self.pinned)
             prefetch_plans(dd, self.keys)
-        self._ready = dd
+        return dd
+
+    def _run(self):
+        torch.cuda.set_device(self.device)
+        while True:
+            hb = self._jobs.get()
+            if hb is None:
+                return
+            try:
+                self._ready = self._issue(hb)
+            except BaseException as e:  # noqa: BLE001 - re-raised in get()
+                self._error = e
+            self._done.set()
+
+    def _submit(self):
+        hb = self.hbs[self.pos % len(self.hbs)]
+        self.pos += 1
+        self._done.clear()
+        if self._jobs is not None:
+            self._jobs.put(hb)
+        else:
+            self._ready = self._issue(hb)
+            self._done.set()
 
     def get(self) -> dict:
         """Datadict of the current batch (waits, on the device, for its copies)."""
+        self._done.wait()
+        if self._error is not None:
+            err, self._error = self._error, None
+            raise err
         torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return self._ready
 
     def advance(self) -> None:
         """Issue the next batch's copies and plan regrouping on the side stream.  Call it
         right after the training step has been launched: the host work overlaps the step's
-        execution.  The caller must synchronise with that step (e.g. read the loss back)
-        before the following ``advance()``: the buffers of the batch before it are released
-        here and reused."""
+        execution.  The caller must synchronise with the step BEFORE the one just launched
+        (e.g. read its loss back) before calling this: the buffers of that older batch are
+        released here and reused."""
         self._inflight = self._ready
-        self._issue()
+        self._submit()
 
     def next(self) -> dict:
         dd = self.get()
         self.advance()
         return dd
+
+    def close(self) -> None:
+        if self._jobs is not None:
+            self._jobs.put(None)
+            self._worker.join(timeout=5)
+            self._jobs = None
 
 
 def attach_host_plans(hb: HostBatch, datadict: dict, keys: Iterable[str]) -> None:
