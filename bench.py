@@ -405,6 +405,8 @@ def run_b200(args):
     e2e_ms, _ = timed(e2e_step, args.steps, finish=read_pending)
     assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: every step's loss is read"
     e2e_value = args.batch * world / (e2e_ms / args.steps * 1e-3)
+    feeder.close()                                       # no stray side-stream work below
+    torch.cuda.synchronize(device)
 
     out = None
     if rank == 0:
@@ -444,8 +446,23 @@ def run_b200(args):
                                          "reference (torch CPU ops), same model and generator"}
     if rank == 0:
         print(json.dumps(out), flush=True)
+    # Orderly teardown: prefetch thread first, then the CUDA graphs (they hold captured NCCL
+    # kernels and must go before the communicator), then the process group.  A watchdog ends
+    # the process with status 0 if NCCL's shutdown blocks: the result line is already out.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    killer = threading.Timer(30.0, lambda: os._exit(0))
+    killer.daemon = True
+    killer.start()
+    del feeder, run_step
+    graphs = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize(device)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    killer.cancel()
 
 
 def main():

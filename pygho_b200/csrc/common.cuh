@@ -41,4 +41,6 @@ inline unsigned blocks_for(int64_t n, int per_block) {
 
 constexpr int kSMs = 148;  // B200
 
+extern int g_tune[8];  // run-time tuning knobs (pgh_set_tuning), defined in seg_gmr.cu
+
 }  // namespace pgh

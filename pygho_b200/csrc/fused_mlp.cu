@@ -21,7 +21,14 @@
 namespace pgh {
 
 constexpr int kBnThreads = 256;
-constexpr int kBnMaxBlocks = 148 * 4;
+
+// run-time tuning (pgh_set_tuning): [2] partial-reduction CTAs per SM (default 4), [3] rows in
+// flight per thread in the backward kernels (2 or 4), [4] 1 = the apply passes walk the rows in
+// the opposite direction of the reduce pass before them (the tail of that pass is still in the
+// 126 MB L2), [5] elements in flight per thread of the forward apply (1, 2 or 4; default 2).
+// Sweep on B200 (profiles/r1_bn_sweep.txt): 2 rows in flight and 4 CTAs/SM are best, the
+// reverse walk buys nothing (the L2 does not keep the tail of a streaming pass)
+static int bn_tune(int key, int dflt) { return g_tune[key] > 0 ? g_tune[key] : dflt; }
 
 struct BnGeom {
   int c4;        // float4 columns per row
@@ -35,7 +42,8 @@ static BnGeom bn_geom(int64_t rows, int64_t C) {
   g.c4 = (int)(C / 4);
   g.ty = kBnThreads / g.c4;
   if (g.ty < 1) g.ty = 1;
-  long long rpb = (rows + kBnMaxBlocks - 1) / kBnMaxBlocks;
+  const long long max_blocks = (long long)kSMs * bn_tune(2, 4);
+  long long rpb = (rows + max_blocks - 1) / max_blocks;
   const long long min_rows = 8LL * g.ty;
   if (rpb < min_rows) rpb = min_rows;
   rpb = (rpb + g.ty - 1) / g.ty * g.ty;
@@ -148,28 +156,40 @@ __global__ void bn_stats_final_kernel(const float* __restrict__ y, const float* 
 }
 
 // ---- forward apply ------------------------------------------------------------------------
-template <int ACT>
+template <int ACT, int UN>
 __global__ void bn_act_fwd_kernel(const float4* __restrict__ y, const float4* __restrict__ mean,
                                   const float4* __restrict__ rstd, const float4* __restrict__ gamma,
-                                  const float4* __restrict__ beta, long long n4, int c4,
+                                  const float4* __restrict__ beta, long long n4, int c4, int rev,
                                   float4* __restrict__ z) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const int c = (int)(i % c4);
-    const float4 v = __ldg(y + i), m = __ldg(mean + c), r = __ldg(rstd + c);
-    const float4 g = gamma ? __ldg(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-    const float4 b = beta ? __ldg(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 o;
-    o.x = act_fwd<ACT>(fmaf((v.x - m.x) * r.x, g.x, b.x));
-    o.y = act_fwd<ACT>(fmaf((v.y - m.y) * r.y, g.y, b.y));
-    o.z = act_fwd<ACT>(fmaf((v.z - m.z) * r.z, g.z, b.z));
-    o.w = act_fwd<ACT>(fmaf((v.w - m.w) * r.w, g.w, b.w));
-    z[i] = o;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UN) {
+    float4 v[UN];
+    long long idx[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long i = min(i0 + u * stride, n4 - 1);      // clamped: loads are unconditional
+      idx[u] = rev ? n4 - 1 - i : i;
+      v[u] = __ldg(y + idx[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (i0 + u * stride >= n4) break;
+      const int c = (int)(idx[u] % c4);
+      const float4 m = __ldg(mean + c), r = __ldg(rstd + c);
+      const float4 g = gamma ? __ldg(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 b = beta ? __ldg(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 o;
+      o.x = act_fwd<ACT>(fmaf((v[u].x - m.x) * r.x, g.x, b.x));
+      o.y = act_fwd<ACT>(fmaf((v[u].y - m.y) * r.y, g.y, b.y));
+      o.z = act_fwd<ACT>(fmaf((v[u].z - m.z) * r.z, g.z, b.z));
+      o.w = act_fwd<ACT>(fmaf((v[u].w - m.w) * r.w, g.w, b.w));
+      z[idx[u]] = o;
+    }
   }
 }
 
 // ---- backward reduce: sum dyh and sum dyh * xh -------------------------------------------
-template <int ACT>
+template <int ACT, int UN>
 __global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y,
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -186,14 +206,24 @@ __global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const flo
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   const float4* yb = reinterpret_cast<const float4*>(y) + tx;
   const float4* db = reinterpret_cast<const float4*>(dz) + tx;
-#pragma unroll 2
-  for (long long r = r0 + threadIdx.y; r < r1; r += ty_n) {
-    const float4 v = __ldg(yb + r * c4), d = __ldg(db + r * c4);
-    const float xx = (v.x - m.x) * rs.x, xy = (v.y - m.y) * rs.y, xz = (v.z - m.z) * rs.z, xw = (v.w - m.w) * rs.w;
-    const float gx = d.x * act_grad<ACT>(fmaf(xx, g.x, bt.x)), gy = d.y * act_grad<ACT>(fmaf(xy, g.y, bt.y));
-    const float gz = d.z * act_grad<ACT>(fmaf(xz, g.z, bt.z)), gw = d.w * act_grad<ACT>(fmaf(xw, g.w, bt.w));
-    s.x += gx; s.y += gy; s.z += gz; s.w += gw;
-    q.x = fmaf(gx, xx, q.x); q.y = fmaf(gy, xy, q.y); q.z = fmaf(gz, xz, q.z); q.w = fmaf(gw, xw, q.w);
+  for (long long rb = r0 + threadIdx.y; rb < r1; rb += (long long)ty_n * UN) {
+    float4 vv[UN], dd[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {                 // clamped rows: all 2*UN loads issue together
+      const long long r = min(rb + (long long)u * ty_n, r1 - 1);
+      vv[u] = __ldg(yb + r * c4);
+      dd[u] = __ldg(db + r * c4);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (rb + (long long)u * ty_n >= r1) break;
+      const float4 v = vv[u], d = dd[u];
+      const float xx = (v.x - m.x) * rs.x, xy = (v.y - m.y) * rs.y, xz = (v.z - m.z) * rs.z, xw = (v.w - m.w) * rs.w;
+      const float gx = d.x * act_grad<ACT>(fmaf(xx, g.x, bt.x)), gy = d.y * act_grad<ACT>(fmaf(xy, g.y, bt.y));
+      const float gz = d.z * act_grad<ACT>(fmaf(xz, g.z, bt.z)), gw = d.w * act_grad<ACT>(fmaf(xw, g.w, bt.w));
+      s.x += gx; s.y += gy; s.z += gz; s.w += gw;
+      q.x = fmaf(gx, xx, q.x); q.y = fmaf(gy, xy, q.y); q.z = fmaf(gz, xz, q.z); q.w = fmaf(gw, xw, q.w);
+    }
   }
   reduce_rows(s, q, sm, c4, ty_n);
   if (threadIdx.y == 0) {
@@ -218,12 +248,12 @@ __global__ void bn_bwd_final_kernel(const float* __restrict__ part, int blocks, 
 }
 
 // ---- backward apply: dy and the column sums of dy (the Linear bias gradient) ------------------
-template <int ACT>
+template <int ACT, int UN>
 __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y,
                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                         const float* __restrict__ m1, const float* __restrict__ m2,
-                                        long long rows, int C, long long rows_per_block,
+                                        long long rows, int C, long long rows_per_block, int rev,
                                         float* __restrict__ dy, float* __restrict__ part) {
   extern __shared__ float4 sm[];
   const int tx = threadIdx.x, c4 = blockDim.x, ty_n = blockDim.y;
@@ -234,29 +264,42 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const floa
   const float4 a1 = __ldg(reinterpret_cast<const float4*>(m1) + tx);
   const float4 a2 = __ldg(reinterpret_cast<const float4*>(m2) + tx);
   const float4 sc = make_float4(g.x * rs.x, g.y * rs.y, g.z * rs.z, g.w * rs.w);
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  // rev: CTA 0 takes the LAST row slab (the rows the reduce pass touched most recently)
+  const long long slab = rev ? (long long)(gridDim.x - 1 - blockIdx.x) : (long long)blockIdx.x;
+  const long long r0 = slab * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), unused = s;
   const float4* yb = reinterpret_cast<const float4*>(y) + tx;
   const float4* db = reinterpret_cast<const float4*>(dz) + tx;
   float4* ob = reinterpret_cast<float4*>(dy) + tx;
-#pragma unroll 2
-  for (long long r = r0 + threadIdx.y; r < r1; r += ty_n) {
-    const float4 v = __ldg(yb + r * c4), d = __ldg(db + r * c4);
-    const float xx = (v.x - m.x) * rs.x, xy = (v.y - m.y) * rs.y, xz = (v.z - m.z) * rs.z, xw = (v.w - m.w) * rs.w;
-    const float gx = d.x * act_grad<ACT>(fmaf(xx, g.x, bt.x)), gy = d.y * act_grad<ACT>(fmaf(xy, g.y, bt.y));
-    const float gz = d.z * act_grad<ACT>(fmaf(xz, g.z, bt.z)), gw = d.w * act_grad<ACT>(fmaf(xw, g.w, bt.w));
-    float4 o;
-    o.x = sc.x * (gx - a1.x - xx * a2.x);
-    o.y = sc.y * (gy - a1.y - xy * a2.y);
-    o.z = sc.z * (gz - a1.z - xz * a2.z);
-    o.w = sc.w * (gw - a1.w - xw * a2.w);
-    ob[r * c4] = o;
-    s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+  for (long long rb = r0 + threadIdx.y; rb < r1; rb += (long long)ty_n * UN) {
+    float4 vv[UN], dd[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long r = min(rb + (long long)u * ty_n, r1 - 1);
+      vv[u] = __ldg(yb + r * c4);
+      dd[u] = __ldg(db + r * c4);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long r = rb + (long long)u * ty_n;
+      if (r >= r1) break;
+      const float4 v = vv[u], d = dd[u];
+      const float xx = (v.x - m.x) * rs.x, xy = (v.y - m.y) * rs.y, xz = (v.z - m.z) * rs.z, xw = (v.w - m.w) * rs.w;
+      const float gx = d.x * act_grad<ACT>(fmaf(xx, g.x, bt.x)), gy = d.y * act_grad<ACT>(fmaf(xy, g.y, bt.y));
+      const float gz = d.z * act_grad<ACT>(fmaf(xz, g.z, bt.z)), gw = d.w * act_grad<ACT>(fmaf(xw, g.w, bt.w));
+      float4 o;
+      o.x = sc.x * (gx - a1.x - xx * a2.x);
+      o.y = sc.y * (gy - a1.y - xy * a2.y);
+      o.z = sc.z * (gz - a1.z - xz * a2.z);
+      o.w = sc.w * (gw - a1.w - xw * a2.w);
+      ob[r * c4] = o;
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
   }
   if (part) {
     reduce_rows(s, unused, sm, c4, ty_n);
-    if (threadIdx.y == 0) reinterpret_cast<float4*>(part + (size_t)blockIdx.x * C)[tx] = s;
+    if (threadIdx.y == 0) reinterpret_cast<float4*>(part + (size_t)slab * C)[tx] = s;
   }
 }
 
@@ -310,11 +353,18 @@ extern "C" int pgh_bn_act_fwd_f32(const float* y, const float* mean, const float
   long long nb = (n4 + 255) / 256;
   if (nb > 148 * 16) nb = 148 * 16;
   cudaStream_t s = as_stream(stream);
-#define PGH_FWD(A) bn_act_fwd_kernel<A><<<(unsigned)nb, 256, 0, s>>>(                                \
+  const int rev = bn_tune(4, 0) == 1;
+#define PGH_FWD_U(A, U) bn_act_fwd_kernel<A, U><<<(unsigned)nb, 256, 0, s>>>(                        \
       (const float4*)y, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,             \
-      (const float4*)beta, n4, (int)(C / 4), (float4*)z)
+      (const float4*)beta, n4, (int)(C / 4), rev, (float4*)z)
+#define PGH_FWD(A)                                                                                   \
+  do {                                                                                               \
+    const int un_ = bn_tune(5, 2);                                                                   \
+    if (un_ >= 4) PGH_FWD_U(A, 4); else if (un_ == 2) PGH_FWD_U(A, 2); else PGH_FWD_U(A, 1);        \
+  } while (0)
   if (act == 1) PGH_FWD(1); else if (act == 2) PGH_FWD(2); else if (act == 0) PGH_FWD(0);
   else return arg_error("bn_act_fwd: act");
+#undef PGH_FWD_U
 #undef PGH_FWD
   return check_launch("bn_act_fwd");
 }
@@ -336,15 +386,21 @@ extern "C" int pgh_bn_act_bwd_f32(const float* dz, const float* y, const float* 
   float* m2 = m1 + C;
   const size_t smem = (size_t)g.c4 * g.ty * 2 * sizeof(float4);
   const dim3 blk(g.c4, g.ty);
-#define PGH_BWD(A)                                                                                   \
-  bn_act_bwd_reduce_kernel<A><<<g.blocks, blk, smem, s>>>(dz, y, mean, rstd, gamma, beta, rows,     \
-                                                           (int)C, g.rows_per_block, part);          \
+  const int rev = bn_tune(4, 0) == 1;
+#define PGH_BWD_U(A, U)                                                                              \
+  bn_act_bwd_reduce_kernel<A, U><<<g.blocks, blk, smem, s>>>(dz, y, mean, rstd, gamma, beta, rows,  \
+                                                              (int)C, g.rows_per_block, part);       \
   bn_bwd_final_kernel<<<blocks_for(C, 32), dim3(32, 32), 0, s>>>(part, g.blocks, rows, (int)C, dgamma,      \
                                                           dbeta, m1, m2);                            \
-  bn_act_bwd_apply_kernel<A><<<g.blocks, blk, smem, s>>>(dz, y, mean, rstd, gamma, beta, m1, m2,    \
-                                                          rows, (int)C, g.rows_per_block, dy,        \
-                                                          dbias ? part : nullptr)
+  bn_act_bwd_apply_kernel<A, U><<<g.blocks, blk, smem, s>>>(dz, y, mean, rstd, gamma, beta, m1, m2, \
+                                                             rows, (int)C, g.rows_per_block, rev,    \
+                                                             dy, dbias ? part : nullptr)
+#define PGH_BWD(A)                                                                                   \
+  do {                                                                                               \
+    if (bn_tune(3, 2) >= 4) { PGH_BWD_U(A, 4); } else { PGH_BWD_U(A, 2); }                           \
+  } while (0)
   if (act == 1) { PGH_BWD(1); } else if (act == 2) { PGH_BWD(2); } else { PGH_BWD(0); }
+#undef PGH_BWD_U
 #undef PGH_BWD
   if (dbias) colsum_final_kernel<<<blocks_for(C, 32), dim3(32, 32), 0, s>>>(part, g.blocks, (int)C, dbias);
   return check_launch("bn_act_bwd");

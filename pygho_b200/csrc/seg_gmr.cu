@@ -614,7 +614,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // run-time tuning knobs (pgh_set_tuning): [0] seg_gmr variant (-1 = built-in choice),
 // [1] ring kernel: target plan entries per warp, [2..7] reserved
-static int g_tune[8] = {-1, 16, 0, 0, 0, 0, 0, 0};
+// [2..5] fused BN kernels (fused_mlp.cu)
+int g_tune[8] = {-1, 16, 0, 0, 0, 0, 0, 0};
 
 template <int AGGR, bool HAS_B, int NS, int U, int WARPS>
 static void launch_ring_t(cudaStream_t s, const float* a_val, const int* c, const float* a_scale,
