@@ -39,8 +39,10 @@ const char* pgh_last_error(void);
 int pgh_abi_version(void);
 /* fills {device ordinal, SM count, L2 bytes, cc major, cc minor}; host pointer */
 int pgh_device_info(int32_t* out5);
-/* run-time tuning knobs (never change results, only the work split): key 0 = seg_gmr kernel
- * variant (-1 built-in choice), key 1 = ring kernel plan entries per warp; host call */
+/* run-time tuning knobs (only the work split changes; reductions stay deterministic for a
+ * given setting): key 0 = seg_gmr kernel variant (-1 built-in choice), key 1 = ring kernel
+ * plan entries per warp, keys 2..5 = fused BatchNorm kernels (CTAs per SM, rows in flight,
+ * reverse walk, forward elements in flight; 0 = default); host call */
 int pgh_set_tuning(int key, int value);
 /* profiling hook: device buffer of n_words uint64 that the pipelined mamamm kernel fills
  * with %globaltimer stamps of its three warp roles (CTA 0 only); NULL switches it off */
@@ -224,6 +226,51 @@ int pgh_bn_act_bwd_f32(const float* dz, const float* y, const float* mean, const
                        const float* gamma, const float* beta, int64_t rows, int64_t C, int act,
                        float* dy, float* dgamma, float* dbeta, float* dbias, void* ws,
                        size_t ws_bytes, void* stream);
+
+/* ------------------------------------- batch preparation on the device (SURVEY 8f rank 1 + 3) */
+
+/* All-pairs hop distances of every graph of a block-diagonal batch, one CTA per graph:
+ * the adjacency lives in shared memory as bit rows, a warp runs the breadth-first search of
+ * one root node with one 32-bit word of the visited / frontier sets per lane.
+ *   edge_src/edge_dst : (E) int64 GLOBAL node ids, edges of graph g are [edge_ptr[g], edge_ptr[g+1])
+ *   node_ptr, edge_ptr, sq_ptr : (B+1) int64; sq_ptr[g] = sum_{h<g} n_h^2
+ *   D[sq_ptr[g] + i*n_g + j] = dist(i -> j) if <= cutoff else 255   (uint8, cutoff <= 254)
+ *   cnt[node_ptr[g] + i] = #{j : dist <= cutoff}   (int32, may be NULL)
+ * The search follows edges from target to source like the reference's k_hop_subgraph
+ * (hodata/SpTupleSampler.py:12-88, flow='source_to_target'); graphs of up to 1024 nodes.
+ * Replaces the per-node Python loop of KhopSampler (SpTupleSampler.py:91-126) and scipy's
+ * shortest_path in spdsampler (MaTupleSampler.py:11-31).                                     */
+int pgh_graph_dist_u8(const int64_t* edge_src, const int64_t* edge_dst, const int64_t* node_ptr,
+                      const int64_t* edge_ptr, const int64_t* sq_ptr, int64_t n_graphs,
+                      int64_t max_nodes, int cutoff, uint8_t* D, int32_t* cnt, void* stream);
+/* Tuples {(i, j) : dist(i, j) <= cutoff} of the whole batch, sorted by (i, j), with the
+ * distance as feature -- what KhopSampler + the collate offsets of SpHoData.__inc__
+ * (hodata/SpData.py:60-77) produce.  node_graph: (N) int64 graph id of every node;
+ * rowptr: (N+1) int64 exclusive scan of cnt; tupleid: (2, T) int64 row-major; feat: (T) int64. */
+int pgh_khop_emit(const uint8_t* D, const int64_t* node_ptr, const int64_t* sq_ptr,
+                  const int64_t* node_graph, const int64_t* rowptr, int64_t n_nodes,
+                  int64_t n_tuples, int64_t* tupleid, int64_t* feat, void* stream);
+/* Dense shortest-path-distance features padded to (B, nmax, nmax): out = min(dist, clamp)
+ * (unreachable -> clamp), mask = (i < n_g) & (j < n_g), pads hold `fill`.  spdsampler
+ * (MaTupleSampler.py:11-31) + to_dense_tuplefeat (MaData.py:152-212) in one pass.
+ * D must come from pgh_graph_dist_u8 with cutoff >= clamp - 1.                               */
+int pgh_spd_dense_i64(const uint8_t* D, const int64_t* node_ptr, const int64_t* sq_ptr,
+                      int64_t n_graphs, int64_t nmax, int clamp, int64_t fill, int64_t* out,
+                      uint8_t* mask, void* stream);
+/* to_dense_x (MaData.py:109-149): out[g, i, :] = src[ptr[g] + i, :] for i < n_g, `fill`
+ * elsewhere; mask[g, i] = i < n_g.  Elements are copied as raw 4- or 8-byte words
+ * (elem_bytes), fill is the raw bit pattern.                                                  */
+int pgh_pad_rows(const void* src, const int64_t* ptr, int64_t n_graphs, int64_t nmax,
+                 int64_t width, int elem_bytes, uint64_t fill, void* out, uint8_t* mask,
+                 void* stream);
+/* to_dense_adj (MaData.py:26-72): out[g, r, c, :] = edge_attr[e, :] for every edge e=(r, c)
+ * of graph g = edge_graph[e], `fill` elsewhere; mask marks the edges.  node_ptr != NULL means
+ * the indices are global and node_ptr[g] is subtracted.  The call fills the pads itself
+ * (one fill pass + one scatter pass, stream-ordered).                                         */
+int pgh_dense_adj(const int64_t* edge_src, const int64_t* edge_dst, const int64_t* edge_graph,
+                  const int64_t* node_ptr, const void* edge_attr, int64_t n_edges,
+                  int64_t n_graphs, int64_t nmax, int64_t width, int elem_bytes, uint64_t fill,
+                  void* out, uint8_t* mask, void* stream);
 
 #ifdef __cplusplus
 }

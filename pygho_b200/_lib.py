@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpygho_b200.so")
 
 _p, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
+_u64 = C.c_uint64
 
 # name -> (restype, argtypes); mirrors include/pygho_b200.h one to one
 SIGNATURES = {
@@ -60,6 +61,11 @@ SIGNATURES = {
     "pgh_bn_stats_f32": (_i, [_p, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _sz, _p]),
     "pgh_bn_act_fwd_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _p, _p]),
     "pgh_bn_act_bwd_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "pgh_graph_dist_u8": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _p, _p, _p]),
+    "pgh_khop_emit": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p]),
+    "pgh_spd_dense_i64": (_i, [_p, _p, _p, _i64, _i64, _i, _i64, _p, _p, _p]),
+    "pgh_pad_rows": (_i, [_p, _p, _i64, _i64, _i64, _i, _u64, _p, _p, _p]),
+    "pgh_dense_adj": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _u64, _p, _p, _p]),
 }
 
 AGGR_CODE = {"sum": 0, "mean": 1, "max": 2, "min": 3, "amax": 2, "amin": 3}

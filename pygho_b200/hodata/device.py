@@ -186,30 +186,37 @@ def attach_host_plans(hb: HostBatch, datadict: dict, keys: Iterable[str]) -> Non
         hb.plans[key] = datadict[key + KEYSEP + "acd"].cpu().numpy()
 
 
-def ma_datadict(hb: HostBatch, device, max_dist: int = 5) -> dict:
+def ma_datadict(hb: HostBatch, device, max_dist: int = 5, tuples: str = "khop",
+                pinned: Optional[dict] = None) -> dict:
     """Dense-mode ``datadict``: x (b, n, 1), A (b, n, n), X (b, n, n) masked tensors padded
-    to the largest graph (reference hodata/MaData.py:109-255 ``to_dense_*``)."""
+    to the largest graph (reference hodata/MaData.py:109-255 ``to_dense_*`` / ``batch2dense``).
+
+    The host batch is copied in its sparse form and padded ON THE DEVICE (pad / scatter
+    kernels of ``hodata.cu``).  ``tuples="khop"``: X holds ``min(dist, max_dist) + 1`` on the
+    sampled k-hop tuples and 0 elsewhere; ``tuples="spd"``: X is the shortest-path-distance
+    matrix clamped to ``max_dist + 1``, computed on the device (``spdsampler``)."""
+    from .MaData import to_dense_adj, to_dense_x
+    from .MaTupleSampler import spdsampler
     B = hb.num_graphs
-    sizes = np.diff(hb.node_ptr)
-    n = int(sizes.max())
-    x = np.zeros((B, n, 1), dtype=np.int64)
-    A = np.zeros((B, n, n), dtype=np.int64)
-    X = np.zeros((B, n, n), dtype=np.int64)
-    nmask = np.arange(n)[None, :] < sizes[:, None]
-    g_of_node = hb.batch
-    local = np.arange(hb.num_nodes) - hb.node_ptr[g_of_node]
-    x[g_of_node, local, 0] = hb.x
-    ge = g_of_node[hb.edge_index[0]]
-    A[ge, hb.edge_index[0] - hb.node_ptr[ge], hb.edge_index[1] - hb.node_ptr[ge]] = hb.edge_attr
-    gt = g_of_node[hb.tupleid[0]]
-    X[gt, hb.tupleid[0] - hb.node_ptr[gt], hb.tupleid[1] - hb.node_ptr[gt]] = \
-        np.minimum(hb.tuplefeat, max_dist) + 1
-    m2 = nmask[:, :, None] & nmask[:, None, :]
-    to = lambda a: torch.from_numpy(a).to(device)  # noqa: E731
+    n = int(np.diff(hb.node_ptr).max())
+    node_ptr = _h2d(hb.node_ptr, device, pinned)
+    batch = _h2d(hb.batch, device, pinned)
+    ei = _h2d(hb.edge_index, device, pinned)
+    x = to_dense_x(_h2d(hb.x, device, pinned).unsqueeze(-1), node_ptr, n, B)
+    A = to_dense_adj(ei, batch[ei[0]], _h2d(hb.edge_attr, device, pinned), n, B,
+                     node_ptr=node_ptr)
+    m2 = x.mask.unsqueeze(2) & x.mask.unsqueeze(1)
+    if tuples == "spd":
+        X = spdsampler(ei, hb.node_ptr, max_dist, n)
+    else:
+        tid = _h2d(hb.tupleid, device, pinned)
+        feat = torch.clamp(_h2d(hb.tuplefeat, device, pinned), max=max_dist) + 1
+        X = MaskedTensor(to_dense_adj(tid, batch[tid[0]], feat, n, B, node_ptr=node_ptr).data,
+                         m2, 0, True)
     return {
-        "x": MaskedTensor(to(x), to(nmask), 0, True),
-        "A": MaskedTensor(to(A), to(m2), 0, True),
-        "X": MaskedTensor(to(X), to(m2), 0, True),
+        "x": x,
+        "A": MaskedTensor(A.data, m2, 0, True),
+        "X": X,
         "num_graphs": B,
-        "y": to(hb.y),
+        "y": _h2d(hb.y, device, pinned),
     }

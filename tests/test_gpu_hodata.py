@@ -1,0 +1,158 @@
+"""GPU parity of the device-side batch preparation (hodata.cu through the C ABI) against the
+numpy oracle and the reference golden vectors: bit-exact (integer / index work)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hodata_oracle as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.mark.parametrize("hop", [1, 2, 3, 5])
+def test_khop_sampler_matches_oracle(dev, hop):
+    from pygho_b200.hodata.SpTupleSampler import KhopSampler
+    from pygho_b200.hodata.synthetic import make_batch
+    hb = make_batch(48, seed=11, hop=3)
+    X = KhopSampler(_t(hb.edge_index, dev), hb.node_ptr, hop)
+    tid, feat = H.khop_sampler_batch(hb.edge_index, hb.node_ptr, hop)
+    assert np.array_equal(X.indices.cpu().numpy(), tid)
+    assert np.array_equal(X.values.cpu().numpy(), feat)
+    if hop == 3:                                          # the generator's own host sampler
+        assert np.array_equal(tid, hb.tupleid) and np.array_equal(feat, hb.tuplefeat)
+    # device ptr, shuffled (ungrouped) edges
+    perm = np.random.default_rng(0).permutation(hb.edge_index.shape[1])
+    X2 = KhopSampler(_t(hb.edge_index[:, perm], dev), _t(hb.node_ptr, dev), hop, grouped=False)
+    assert torch.equal(X2.indices, X.indices) and torch.equal(X2.values, X.values)
+
+
+def test_khop_reference_golden_and_directed(dev, golden):
+    from pygho_b200.hodata.SpTupleSampler import KhopSampler
+    g = golden("hodata")
+    for hop in (2, 3):
+        for gi in range(6):
+            n = int(g[f"g{gi}_n"])
+            X = KhopSampler(_t(g[f"g{gi}_edge_index"], dev), [0, n], hop)
+            assert np.array_equal(X.indices[1].cpu().numpy(), g[f"khop{hop}_g{gi}_subset"])
+            assert np.array_equal(X.values.cpu().numpy(), g[f"khop{hop}_g{gi}_dist"])
+            assert np.array_equal(X.indices[0].cpu().numpy(),
+                                  np.repeat(np.arange(n), g[f"khop{hop}_g{gi}_len"]))
+    # directed edges: the search runs target -> source like the reference
+    X = KhopSampler(_t(g["dir_edge_index"], dev), [0, 12], 2, grouped=False)
+    assert np.array_equal(X.indices[1].cpu().numpy(), g["dir_subset"])
+    assert np.array_equal(X.values.cpu().numpy(), g["dir_dist"])
+
+
+def test_khop_large_and_degenerate_graphs(dev):
+    from pygho_b200.hodata.SpTupleSampler import KhopSampler
+    rng = np.random.default_rng(1)
+    # one 700-node graph (22 bit words per row), one isolated node, one 33-node path
+    n_big = 700
+    und = np.stack([rng.integers(0, n_big, 1500), rng.integers(0, n_big, 1500)])
+    und = und[:, und[0] != und[1]]
+    ei_big = np.unique(np.concatenate([und, und[::-1]], axis=1), axis=1)
+    path = np.stack([np.arange(32), np.arange(1, 33)])
+    ei_path = np.concatenate([path, path[::-1]], axis=1) + n_big + 1
+    ei = np.concatenate([ei_big, ei_path], axis=1)
+    node_ptr = np.array([0, n_big, n_big + 1, n_big + 34])
+    for hop in (2, 40):
+        X = KhopSampler(_t(ei, dev), node_ptr, hop, grouped=False)
+        tid, feat = H.khop_sampler_batch(ei, node_ptr, hop)
+        assert np.array_equal(X.indices.cpu().numpy(), tid)
+        assert np.array_equal(X.values.cpu().numpy(), feat)
+    # the isolated node is its own (only) tuple
+    iso = (X.indices[0] == n_big).nonzero().flatten()
+    assert iso.numel() == 1 and int(X.indices[1, iso]) == n_big and int(X.values[iso]) == 0
+    # no edges at all
+    X = KhopSampler(torch.zeros((2, 0), dtype=torch.int64, device=dev), [0, 3, 5], 2)
+    assert np.array_equal(X.indices.cpu().numpy(), np.stack([np.arange(5), np.arange(5)]))
+
+
+def test_khop_full_size_properties(dev):
+    """B=1024 (bench size): sortedness, symmetry, diagonal, counts -- size-independent checks."""
+    from pygho_b200.hodata.SpTupleSampler import KhopSampler
+    from pygho_b200.hodata.synthetic import make_batch
+    hb = make_batch(1024, seed=0, hop=3)
+    X = KhopSampler(_t(hb.edge_index, dev), hb.node_ptr, 3)
+    assert np.array_equal(X.indices.cpu().numpy(), hb.tupleid)
+    assert np.array_equal(X.values.cpu().numpy(), hb.tuplefeat)
+    key = X.indices[0] * hb.num_nodes + X.indices[1]
+    assert bool((key[1:] > key[:-1]).all())
+    keyT = torch.sort(X.indices[1] * hb.num_nodes + X.indices[0]).values
+    assert torch.equal(key, keyT)                                   # undirected -> symmetric
+    assert int((X.values == 0).sum()) == hb.num_nodes               # exactly the diagonal
+    assert int((X.values == 1).sum()) == hb.edge_index.shape[1]     # exactly the edges
+
+
+def test_spdsampler_matches_reference_golden(dev, golden):
+    from pygho_b200.hodata.MaTupleSampler import spdsampler
+    g = golden("hodata")
+    eis, ptr = [], [0]
+    for gi in range(4):
+        eis.append(g[f"g{gi}_edge_index"] + ptr[-1])
+        ptr.append(ptr[-1] + int(g[f"g{gi}_n"]))
+    X = spdsampler(_t(np.concatenate(eis, axis=1), dev), ptr, 3)
+    data, mask = X.data.cpu().numpy(), X.mask.cpu().numpy()
+    for gi in range(4):
+        n = int(g[f"g{gi}_n"])
+        assert np.array_equal(data[gi, :n, :n], g[f"spd_g{gi}"])
+        assert mask[gi, :n, :n].all() and mask[gi].sum() == n * n
+        assert (data[gi][~mask[gi]] == 0).all()
+    X = spdsampler(_t(g["spd_disc_edge_index"], dev), [0, 6], 2, max_num_nodes=8)
+    assert X.data.shape == (1, 8, 8)
+    got, ref = X.data[0, :6, :6].cpu().numpy(), g["spd_disc"]
+    reach = ref >= 0               # unreachable: reference INT64_MIN (bug), ours hop + 1 (Q14)
+    assert np.array_equal(got[reach], ref[reach]) and (got[~reach] == 3).all()
+    assert np.array_equal(got, H.spd_matrix(g["spd_disc_edge_index"], 6, 2))
+
+
+def test_dense_layouts_match_reference_golden(dev, golden):
+    from pygho_b200.hodata.MaData import to_dense_adj, to_dense_x
+    g = golden("hodata")
+    mx = to_dense_x(_t(g["dx_x"], dev), _t(g["dx_ptr"], dev))
+    assert np.array_equal(mx.data.cpu().numpy(), g["dx_data"])
+    assert np.array_equal(mx.mask.cpu().numpy(), g["dx_mask"])
+    mx = to_dense_x(_t(g["dx_x"].astype(np.float32), dev), _t(g["dx_ptr"], dev), 7, None, -1.5)
+    want, wmask = H.to_dense_x(g["dx_x"].astype(np.float32), g["dx_ptr"], 7, -1.5)
+    assert np.array_equal(mx.data.cpu().numpy(), want) and np.array_equal(mx.mask.cpu().numpy(), wmask)
+    ma = to_dense_adj(_t(g["da_ei"], dev), _t(g["da_eb"], dev), _t(g["da_ea"], dev), 6, 4)
+    assert np.array_equal(ma.data.cpu().numpy(), g["da_data"])
+    assert np.array_equal(ma.mask.cpu().numpy(), g["da_mask"])
+    ma = to_dense_adj(_t(g["da_ei"], dev), _t(g["da_eb"], dev), _t(g["da_eaf"], dev), 6, 4)
+    assert np.array_equal(ma.data.cpu().numpy(), g["da_dataf"])
+    # global ids + node_ptr == local ids
+    ptr = np.array([0, 6, 12, 18, 24])
+    ma2 = to_dense_adj(_t(g["da_ei"] + ptr[g["da_eb"]], dev), _t(g["da_eb"], dev),
+                       _t(g["da_ea"], dev), 6, 4, node_ptr=_t(ptr, dev))
+    assert np.array_equal(ma2.data.cpu().numpy(), g["da_data"])
+
+
+def test_ma_datadict_device_padding_matches_host(dev):
+    from pygho_b200.hodata.device import ma_datadict
+    from pygho_b200.hodata.synthetic import make_batch
+    hb = make_batch(16, seed=4)
+    dd = ma_datadict(hb, dev)
+    sizes = np.diff(hb.node_ptr)
+    n = int(sizes.max())
+    x, wm = H.to_dense_x(hb.x[:, None], hb.node_ptr, n)
+    assert np.array_equal(dd["x"].data.cpu().numpy(), x) and np.array_equal(dd["x"].mask.cpu().numpy(), wm)
+    local = lambda idx: idx - hb.node_ptr[hb.batch[idx[0]]]  # noqa: E731
+    A, _ = H.to_dense_adj(local(hb.edge_index), hb.batch[hb.edge_index[0]], hb.edge_attr, n, 16)
+    assert np.array_equal(dd["A"].data.cpu().numpy(), A)
+    Xw, _ = H.to_dense_adj(local(hb.tupleid), hb.batch[hb.tupleid[0]],
+                           np.minimum(hb.tuplefeat, 5) + 1, n, 16)
+    assert np.array_equal(dd["X"].data.cpu().numpy(), Xw)
+    m2 = wm[:, :, None] & wm[:, None, :]
+    assert np.array_equal(dd["X"].mask.cpu().numpy(), m2)
+    spd = ma_datadict(hb, dev, max_dist=3, tuples="spd")["X"].data.cpu().numpy()
+    g0 = H.spd_matrix(hb.edge_index[:, hb.batch[hb.edge_index[0]] == 0], int(sizes[0]), 3)
+    assert np.array_equal(spd[0, :sizes[0], :sizes[0]], g0)

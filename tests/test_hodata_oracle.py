@@ -1,0 +1,80 @@
+"""Pin oracle/hodata_oracle.py (batch preparation: k-hop tuples, SPD features, dense padding)
+to the real reference -- golden vectors from tests/golden/make_golden_hodata.py -- and check the
+host-side generator of this repo against it."""
+import numpy as np
+
+from oracle import hodata_oracle as H
+from pygho_b200.hodata.synthetic import collate, khop_tuples, make_graphs
+
+
+def test_k_hop_subgraph_golden(golden):
+    g = golden("hodata")
+    for hop in (2, 3):
+        for gi in range(6):
+            ei, n = g[f"g{gi}_edge_index"], int(g[f"g{gi}_n"])
+            subs, dists, lens = [], [], []
+            for i in range(n):
+                s, d = H.k_hop_subgraph(i, hop, ei, n)
+                subs.append(s); dists.append(d); lens.append(s.shape[0])
+            assert np.array_equal(np.array(lens), g[f"khop{hop}_g{gi}_len"])
+            assert np.array_equal(np.concatenate(subs), g[f"khop{hop}_g{gi}_subset"])
+            assert np.array_equal(np.concatenate(dists), g[f"khop{hop}_g{gi}_dist"])
+            # KhopSampler content = the same lists with the root repeated
+            tid, feat = H.khop_sampler(ei, n, hop)
+            assert np.array_equal(tid[1], g[f"khop{hop}_g{gi}_subset"])
+            assert np.array_equal(tid[0], np.repeat(np.arange(n), g[f"khop{hop}_g{gi}_len"]))
+            assert np.array_equal(feat, g[f"khop{hop}_g{gi}_dist"])
+
+
+def test_k_hop_subgraph_directed_golden(golden):
+    g = golden("hodata")
+    ei = g["dir_edge_index"]
+    subs, dists = [], []
+    for i in range(12):
+        s, d = H.k_hop_subgraph(i, 2, ei, 12)
+        subs.append(s); dists.append(d)
+    assert np.array_equal(np.concatenate(subs), g["dir_subset"])
+    assert np.array_equal(np.concatenate(dists), g["dir_dist"])
+
+
+def test_spd_golden(golden):
+    g = golden("hodata")
+    for gi in range(4):
+        assert np.array_equal(H.spd_matrix(g[f"g{gi}_edge_index"], int(g[f"g{gi}_n"]), 3),
+                              g[f"spd_g{gi}"])
+    # disconnected graph: the reference converts scipy's inf to int64 (INT64_MIN on x86) BEFORE
+    # clamping (MaTupleSampler.py:29-30), so unreachable pairs come out as INT64_MIN and would
+    # crash the embedding lookup; the intended value -- and ours -- is hop + 1
+    got, ref = H.spd_matrix(g["spd_disc_edge_index"], 6, 2), g["spd_disc"]
+    reach = ref >= 0
+    assert np.array_equal(got[reach], ref[reach]) and (got[~reach] == 3).all()
+    assert (~reach).sum() == 6 * 6 - (9 + 4 + 1)
+
+
+def test_dense_layout_golden(golden):
+    g = golden("hodata")
+    data, mask = H.to_dense_x(g["dx_x"], g["dx_ptr"])
+    assert np.array_equal(data, g["dx_data"]) and np.array_equal(mask, g["dx_mask"])
+    data, mask = H.to_dense_adj(g["da_ei"], g["da_eb"], g["da_ea"], 6, 4)
+    assert np.array_equal(data, g["da_data"]) and np.array_equal(mask, g["da_mask"])
+    data, _ = H.to_dense_adj(g["da_ei"], g["da_eb"], g["da_eaf"], 6, 4)
+    assert np.array_equal(data, g["da_dataf"])
+    data, mask = H.to_dense_tuplefeat(g["dt_feat"], g["dt_shape"], g["dt_ptr"])
+    assert np.array_equal(data, g["dt_data"]) and np.array_equal(mask, g["dt_mask"])
+
+
+def test_host_generator_matches_oracle_sampler():
+    graphs = make_graphs(5, seed=3, hop=3)
+    for gr in graphs:
+        tid, feat = H.khop_sampler(gr.edge_index, gr.num_nodes, 3)
+        tid2, feat2 = khop_tuples(gr.num_nodes, gr.edge_index, 3)
+        assert np.array_equal(tid, tid2) and np.array_equal(feat, feat2)
+    hb = collate(graphs)
+    tid, feat = H.khop_sampler_batch(hb.edge_index, hb.node_ptr, 3)
+    assert np.array_equal(tid, hb.tupleid) and np.array_equal(feat, hb.tuplefeat)
+    # spd restricted to <= hop agrees with the k-hop distances
+    gr = graphs[0]
+    spd = H.spd_matrix(gr.edge_index, gr.num_nodes, 3)
+    t, f = H.khop_sampler(gr.edge_index, gr.num_nodes, 3)
+    assert np.array_equal(spd[t[0], t[1]], f)
+    assert (spd <= 3).sum() == t.shape[1]
