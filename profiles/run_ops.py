@@ -251,6 +251,42 @@ for aggr in ("sum", "max"):
     report(f"masked pool {aggr} dim 2 ({b},{n},{n},{d})", t, tr, pool_valid,
            f"{(4 * d * (b * n * n + b * n) + b * n * n) / 1e6:.0f} MB if pads were read")
 
+# ------------------------------------------------------------------ batch preparation (hodata.cu)
+import time  # noqa: E402
+
+from pygho_b200.hodata.MaData import to_dense_adj, to_dense_x  # noqa: E402
+from pygho_b200.hodata.MaTupleSampler import spdsampler  # noqa: E402
+from pygho_b200.hodata.SpTupleSampler import KhopSampler, graph_distances  # noqa: E402
+from pygho_b200.hodata.synthetic import khop_tuples  # noqa: E402
+
+nptr_d = torch.from_numpy(hb.node_ptr).to(dev)
+sq = int((np.diff(hb.node_ptr) ** 2).sum())
+t0 = time.perf_counter()
+for g in range(64):                                   # host sampler of the generator, 64 graphs
+    e0_, e1_ = int(hb.edge_ptr[g]), int(hb.edge_ptr[g + 1])
+    khop_tuples(int(hb.node_ptr[g + 1] - hb.node_ptr[g]), hb.edge_index[:, e0_:e1_] - hb.node_ptr[g], 3)
+cpu_us = (time.perf_counter() - t0) * 1e6 * (B / 64)
+t = timeit(lambda i: graph_distances(ei, hb.node_ptr, 3), 8, graph=False)
+report(f"hop-distance matrices, B={B} (bit-set BFS, 1 launch + torch glue)", t, None,
+       16 * nA + 8 * 3 * (B + 1) + sq + 4 * N, "int64 edges in, u8 distances + counts out")
+t = timeit(lambda i: KhopSampler(ei, hb.node_ptr, 3), 8, graph=False)
+report(f"KhopSampler hop 3, B={B} -> {nX} tuples (2 launches + scan, 1 size read-back)", t, None,
+       16 * nA + 2 * sq + 4 * N + 8 * (N + 1) + 24 * nX,
+       f"host numpy sampler (1 core): {cpu_us / 1e3:.0f} ms per batch = {cpu_us / t:.0f}x")
+t = timeit(lambda i: spdsampler(ei, hb.node_ptr, 5), 8, graph=False)
+nmax_ = int(np.diff(hb.node_ptr).max())
+report(f"spdsampler hop 5 -> ({B},{nmax_},{nmax_}) padded", t, None,
+       16 * nA + 2 * sq + 9 * B * nmax_ * nmax_, "int64 features + mask out")
+xcol = torch.from_numpy(hb.x).to(dev).unsqueeze(-1)
+t = timeit(lambda i: to_dense_x(xcol, nptr_d, nmax_, B), 8, graph=False)
+report(f"to_dense_x ({N},1) -> ({B},{nmax_},1)", t, None, 8 * N + 9 * B * nmax_, "host-overhead bound")
+ea_d = torch.from_numpy(hb.edge_attr).to(dev)
+eb_d = bvec[ei[0]]
+t = timeit(lambda i: to_dense_adj(ei, eb_d, ea_d, nmax_, B, node_ptr=nptr_d), 8, graph=False)
+report(f"to_dense_adj {nA} edges -> ({B},{nmax_},{nmax_})", t, None,
+       32 * nA + 9 * B * nmax_ * nmax_, "fill pass + scatter pass")
+
+
 if args.md:
     with open(args.md, "w") as f:
         f.write(f"# Op-level rooflines (B200, measured HBM peak {PEAK:.0f} GB/s)\n\n"
