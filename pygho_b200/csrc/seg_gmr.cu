@@ -207,12 +207,14 @@ seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c
       const float n_ = (float)len_;                                                     \
       r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);                 \
     }                                                                                   \
-    if (accum) {                                                                        \
+    if (accum == 1) {                                                                   \
       const float4 o_ = *reinterpret_cast<const float4*>(o_col + (size_t)cur * ldo);    \
       r_ = make_float4(__fadd_rn(o_.x, r_.x), __fadd_rn(o_.y, r_.y),                    \
                        __fadd_rn(o_.z, r_.z), __fadd_rn(o_.w, r_.w));                   \
     }                                                                                   \
-    *reinterpret_cast<float4*>(o_col + (size_t)cur * ldo) = r_;                         \
+    /* accum == 2: profiling mode (tuning key 6), the row store is skipped */           \
+    if (accum != 2 || r_.x == 1.2345e-30f)                                              \
+      *reinterpret_cast<float4*>(o_col + (size_t)cur * ldo) = r_;                       \
     acc = make_float4(init, init, init, init);                                          \
     ++cur;                                                                              \
     cur_beg = cur_end;                                                                  \
@@ -271,6 +273,161 @@ seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Lean streaming variant.  ncu on the kernel above (profiles/r1_seg_gmr_v3_issue.md): 32.2 M warp
+// instructions per launch = 69 per plan entry, i.e. 28.6 us of pure issue time on 148 SMs -- the
+// kernel is as much issue-bound as memory-bound (sm__throughput 49 %, DRAM 49 %).  Same work
+// split, same load batching and the same sequential reduction order, but everything the inner
+// loop does not need is compiled out or hoisted:
+//   * a_scale / accumulate / mean are template parameters, not run-time tests per entry;
+//   * full groups of U entries run without index clamps or validity tests, the (single)
+//     partial group of a warp is a separate, guarded copy of the body;
+//   * the row-end test is one compare + one branch per entry; the flush keeps a running output
+//     pointer and only tracks row lengths for mean / max / min (empty rows of a sum are 0 anyway);
+//   * sum / mean accumulate with one FMA per component (a*b is not rounded separately; max /
+//     min keep the separately rounded product because the tie-splitting backward compares it
+//     bit for bit with the stored extremum).
+template <int AGGR, bool HAS_B, bool HAS_SCALE, bool ACCUM, int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+seg_gmr_lean_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
+                    const float* __restrict__ a_scale, const float* __restrict__ b_val,
+                    const int* __restrict__ d, const int* __restrict__ rowptr,
+                    long long n_rows, int dense, int lda, int ldb, int ldo, int rw,
+                    float* __restrict__ out) {
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr bool kLen = (AGGR != PGH_SUM);          // row lengths matter (mean, empty max/min rows)
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const long long r0 = warp * rw;
+  if (r0 >= n_rows) return;
+  const int nr = (int)min((long long)rw, n_rows - r0);
+  int rp = 0;
+  if (lane <= nr) rp = rowptr ? __ldg(rowptr + r0 + lane) : (int)(r0 + lane);
+  const int e_beg = __shfl_sync(kFull, rp, 0);
+  const int e_end = __shfl_sync(kFull, rp, nr);
+  const float init = (AGGR == PGH_MAX) ? -INFINITY : (AGGR == PGH_MIN) ? INFINITY : 0.f;
+  for (int col = lane * 4; col < dense; col += 128) {
+    const float* __restrict__ a_col = a_val + col;
+    const float* __restrict__ b_col = HAS_B ? b_val + col : nullptr;
+    float* __restrict__ o_ptr = out + (size_t)r0 * ldo + col;      // row being reduced
+    float4 acc = make_float4(init, init, init, init);
+    int cur = 0;
+    int cur_beg = e_beg;
+    int cur_end = __shfl_sync(kFull, rp, 1);
+#define PGH_FLUSH()                                                                     \
+  do {                                                                                  \
+    float4 r_ = acc;                                                                    \
+    if (kLen) {                                                                         \
+      const int len_ = cur_end - cur_beg;                                               \
+      cur_beg = cur_end;                                                                \
+      if (len_ == 0) r_ = make_float4(0.f, 0.f, 0.f, 0.f);                              \
+      else if (AGGR == PGH_MEAN) {                                                      \
+        const float n_ = (float)len_;                                                   \
+        r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);               \
+      }                                                                                 \
+    }                                                                                   \
+    if (ACCUM) {                                                                        \
+      const float4 o_ = *reinterpret_cast<const float4*>(o_ptr);                        \
+      r_ = make_float4(__fadd_rn(o_.x, r_.x), __fadd_rn(o_.y, r_.y),                    \
+                       __fadd_rn(o_.z, r_.z), __fadd_rn(o_.w, r_.w));                   \
+    }                                                                                   \
+    *reinterpret_cast<float4*>(o_ptr) = r_;                                             \
+    o_ptr += ldo;                                                                       \
+    acc = make_float4(init, init, init, init);                                          \
+    ++cur;                                                                              \
+    cur_end = __shfl_sync(kFull, rp, cur + 1);      /* source lane wraps mod 32 */      \
+  } while (0)
+#define PGH_REDUCE(AV, BV, SS)                                                          \
+  do {                                                                                  \
+    float4 m_ = AV;                                                                     \
+    if (HAS_SCALE)                                                                      \
+      m_ = make_float4(__fmul_rn(m_.x, SS), __fmul_rn(m_.y, SS), __fmul_rn(m_.z, SS),   \
+                       __fmul_rn(m_.w, SS));                                            \
+    if (AGGR == PGH_MAX || AGGR == PGH_MIN) {                                           \
+      if (HAS_B)                                                                        \
+        m_ = make_float4(__fmul_rn(m_.x, BV.x), __fmul_rn(m_.y, BV.y),                  \
+                         __fmul_rn(m_.z, BV.z), __fmul_rn(m_.w, BV.w));                 \
+      if (AGGR == PGH_MAX)                                                              \
+        acc = make_float4(fmaxf(acc.x, m_.x), fmaxf(acc.y, m_.y), fmaxf(acc.z, m_.z),   \
+                          fmaxf(acc.w, m_.w));                                          \
+      else                                                                              \
+        acc = make_float4(fminf(acc.x, m_.x), fminf(acc.y, m_.y), fminf(acc.z, m_.z),   \
+                          fminf(acc.w, m_.w));                                          \
+    } else if (HAS_B) {                                                                 \
+      acc = make_float4(__fmaf_rn(m_.x, BV.x, acc.x), __fmaf_rn(m_.y, BV.y, acc.y),     \
+                        __fmaf_rn(m_.z, BV.z, acc.z), __fmaf_rn(m_.w, BV.w, acc.w));    \
+    } else {                                                                            \
+      acc = make_float4(__fadd_rn(acc.x, m_.x), __fadd_rn(acc.y, m_.y),                 \
+                        __fadd_rn(acc.z, m_.z), __fadd_rn(acc.w, m_.w));                \
+    }                                                                                   \
+  } while (0)
+    for (int base = e_beg; base < e_end; base += 32) {
+      const int t = base + lane;
+      int ci = 0, di = 0;
+      float sc = 1.f;
+      if (t < e_end) {
+        ci = c ? __ldg(c + t) : t;
+        if (HAS_B) di = d ? __ldg(d + t) : t;
+        if (HAS_SCALE) sc = __ldg(a_scale + ci);
+      }
+      const int chunk = min(32, e_end - base);
+      int k = 0;
+#pragma unroll 1
+      for (; k + U <= chunk; k += U) {              // full groups: no clamps, no validity tests
+        float4 av[U], bv[U];
+        float ss[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int cc = __shfl_sync(kFull, ci, k + u);
+          av[u] = __ldg(reinterpret_cast<const float4*>(a_col + (size_t)cc * lda));
+          if (HAS_B) {
+            const int dd = __shfl_sync(kFull, di, k + u);
+            bv[u] = __ldg(reinterpret_cast<const float4*>(b_col + (size_t)dd * ldb));
+          }
+          if (HAS_SCALE) ss[u] = __shfl_sync(kFull, sc, k + u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int tt = base + k + u;
+          if (tt >= cur_end) {
+            do PGH_FLUSH(); while (tt >= cur_end);
+          }
+          PGH_REDUCE(av[u], bv[u], ss[u]);
+        }
+      }
+      if (k < chunk) {                              // the one partial group of this warp
+        const int rem = chunk - k;
+        float4 av[U], bv[U];
+        float ss[U];
+#pragma unroll
+        for (int u = 0; u < U - 1; ++u) {
+          const int kk = min(k + u, chunk - 1);     // clamped: the loads stay unconditional
+          const int cc = __shfl_sync(kFull, ci, kk);
+          av[u] = __ldg(reinterpret_cast<const float4*>(a_col + (size_t)cc * lda));
+          if (HAS_B) {
+            const int dd = __shfl_sync(kFull, di, kk);
+            bv[u] = __ldg(reinterpret_cast<const float4*>(b_col + (size_t)dd * ldb));
+          }
+          if (HAS_SCALE) ss[u] = __shfl_sync(kFull, sc, kk);
+        }
+#pragma unroll
+        for (int u = 0; u < U - 1; ++u) {
+          if (u < rem) {
+            const int tt = base + k + u;
+            if (tt >= cur_end) {
+              do PGH_FLUSH(); while (tt >= cur_end);
+            }
+            PGH_REDUCE(av[u], bv[u], ss[u]);
+          }
+        }
+      }
+    }
+    while (cur < nr) PGH_FLUSH();
+#undef PGH_REDUCE
+#undef PGH_FLUSH
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // Ring variant (dense % 128 == 0): same work split and the same sequential reduction order
@@ -435,6 +592,204 @@ seg_gmr_ring_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
       }
     }
     cp_async_wait<0>();
+    while (cur < nr) PGH_FLUSH();
+#undef PGH_ISSUE
+#undef PGH_LOAD_PLAN
+#undef PGH_FLUSH
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Bulk-copy variant (dense % 128 == 0): the same work split and the same sequential reduction
+// order again, but every 512 B value row travels global -> shared memory as ONE bulk async
+// copy (cp.async.bulk / UBLKCP, completion counted in bytes on an mbarrier) issued by a single
+// lane, instead of 32 lanes x LDG.128 / LDGSTS.  A warp owns NS stages of G plan entries
+// (G x OPS rows of 512 B each) and one mbarrier per stage; stages are refilled as soon as they
+// have been read, so up to NS*G*OPS rows per warp are in flight with no register cost and two
+// instructions per entry.  Ablation of the register-staged kernel (profiles/r1_gmr_ablate.txt):
+// with perfectly sequential operands and no stores it still needs 48 us for 148 MB -- it is
+// bound by its own load -> wait -> reduce cycle, not by HBM; this variant decouples the two.
+// Per-warp barriers only: no CTA-wide synchronisation, warps retire independently.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// bounded wait: a lost completion traps (reported as a launch error) instead of hanging
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 14); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(100000u)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+template <int AGGR, bool HAS_B, int G, int NS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+seg_gmr_bulk_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
+                    const float* __restrict__ a_scale, const float* __restrict__ b_val,
+                    const int* __restrict__ d, const int* __restrict__ rowptr,
+                    long long n_rows, int dense, int lda, int ldb, int ldo, int rw, int accum,
+                    float* __restrict__ out) {
+  static_assert(32 % G == 0 && NS * G + G <= 32, "stage geometry (plan registers span 64 entries)");
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int OPS = HAS_B ? 2 : 1;
+  constexpr uint32_t kStage = G * OPS * 512;        // bytes per stage
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const uint32_t data0 = smem_addr(bulk_smem) + (uint32_t)wib * NS * kStage;
+  const uint32_t bar0 = smem_addr(bulk_smem) + (uint32_t)WARPS * NS * kStage + (uint32_t)wib * NS * 8u;
+  if (lane < NS) mbar_init(bar0 + lane * 8u, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  const long long warp = (long long)blockIdx.x * WARPS + wib;
+  const long long r0 = warp * rw;
+  if (r0 >= n_rows) return;
+  const int nr = (int)min((long long)rw, n_rows - r0);
+  int rp = 0;
+  if (lane <= nr) rp = rowptr ? __ldg(rowptr + r0 + lane) : (int)(r0 + lane);
+  const int e_beg = __shfl_sync(kFull, rp, 0);
+  const int e_end = __shfl_sync(kFull, rp, nr);
+  const float init = (AGGR == PGH_MAX) ? -INFINITY : (AGGR == PGH_MIN) ? INFINITY : 0.f;
+  uint32_t fill_idx = 0, cons_idx = 0;              // stage groups issued / consumed so far
+  for (int col0 = 0; col0 < dense; col0 += 128) {
+    const float* __restrict__ a_col = a_val + col0;
+    const float* __restrict__ b_col = HAS_B ? b_val + col0 : nullptr;
+    float* __restrict__ o_col = out + (size_t)r0 * ldo + col0 + lane * 4;
+    float4 acc = make_float4(init, init, init, init);
+    int cur = 0;
+    int cur_beg = e_beg;
+    int cur_end = __shfl_sync(kFull, rp, 1);
+#define PGH_FLUSH()                                                                     \
+  do {                                                                                  \
+    const int len_ = cur_end - cur_beg;                                                 \
+    float4 r_ = acc;                                                                    \
+    if (len_ == 0) r_ = make_float4(0.f, 0.f, 0.f, 0.f);                                \
+    else if (AGGR == PGH_MEAN) {                                                        \
+      const float n_ = (float)len_;                                                     \
+      r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);                 \
+    }                                                                                   \
+    if (accum) {                                                                        \
+      const float4 o_ = *reinterpret_cast<const float4*>(o_col + (size_t)cur * ldo);    \
+      r_ = make_float4(__fadd_rn(o_.x, r_.x), __fadd_rn(o_.y, r_.y),                    \
+                       __fadd_rn(o_.z, r_.z), __fadd_rn(o_.w, r_.w));                   \
+    }                                                                                   \
+    *reinterpret_cast<float4*>(o_col + (size_t)cur * ldo) = r_;                         \
+    acc = make_float4(init, init, init, init);                                          \
+    ++cur;                                                                              \
+    cur_beg = cur_end;                                                                  \
+    cur_end = __shfl_sync(kFull, rp, min(cur + 1, 31));                                 \
+  } while (0)
+    int ci0 = 0, di0 = 0, ci1 = 0, di1 = 0;
+    float sc0 = 1.f, sc1 = 1.f;
+#define PGH_LOAD_PLAN(BASE, CI, DI, SC)                                                 \
+  do {                                                                                  \
+    const int t_ = (BASE) + lane;                                                       \
+    CI = 0; DI = 0; SC = 1.f;                                                           \
+    if (t_ < e_end) {                                                                   \
+      CI = c ? __ldg(c + t_) : t_;                                                      \
+      if (HAS_B) DI = d ? __ldg(d + t_) : t_;                                           \
+      if (a_scale) SC = __ldg(a_scale + CI);                                            \
+    }                                                                                   \
+  } while (0)
+    PGH_LOAD_PLAN(e_beg, ci0, di0, sc0);
+    PGH_LOAD_PLAN(e_beg + 32, ci1, di1, sc1);
+    int chunk_base = e_beg;                         // first entry held by ci0 / di0 / sc0
+    int ti = e_beg;                                 // next entry to issue
+// fill the next stage with entries ti .. ti+G-1: lane u issues the row copies of entry ti+u
+#define PGH_ISSUE()                                                                     \
+  do {                                                                                  \
+    if (ti < e_end) {                                                                   \
+      const uint32_t s_ = fill_idx % NS;                                                \
+      const int nvalid_ = min(G, e_end - ti);                                           \
+      const uint32_t bar_ = bar0 + s_ * 8u;                                             \
+      if (lane == 0) mbar_expect_tx(bar_, (uint32_t)nvalid_ * OPS * 512u);              \
+      __syncwarp();                                                                     \
+      const int off_ = ti + lane - chunk_base;      /* < 64 for the issuing lanes */      \
+      const int c_lo_ = __shfl_sync(kFull, ci0, off_ & 31);                             \
+      const int c_hi_ = __shfl_sync(kFull, ci1, off_ & 31);                             \
+      const int d_lo_ = HAS_B ? __shfl_sync(kFull, di0, off_ & 31) : 0;                 \
+      const int d_hi_ = HAS_B ? __shfl_sync(kFull, di1, off_ & 31) : 0;                 \
+      if (lane < nvalid_) {                                                             \
+        const uint32_t dst_ = data0 + s_ * kStage + (uint32_t)(lane * OPS) * 512u;      \
+        const int cc_ = off_ < 32 ? c_lo_ : c_hi_;                                      \
+        bulk_g2s(dst_, a_col + (size_t)cc_ * lda, 512u, bar_);                          \
+        if (HAS_B) {                                                                    \
+          const int dd_ = off_ < 32 ? d_lo_ : d_hi_;                                    \
+          bulk_g2s(dst_ + 512u, b_col + (size_t)dd_ * ldb, 512u, bar_);                 \
+        }                                                                               \
+      }                                                                                 \
+      ++fill_idx;                                                                       \
+      ti += G;                                                                          \
+    }                                                                                   \
+  } while (0)
+#pragma unroll
+    for (int g = 0; g < NS; ++g) PGH_ISSUE();
+    for (int tc = e_beg; tc < e_end; tc += G) {
+      const uint32_t s = cons_idx % NS;
+      mbar_wait(bar0 + s * 8u, (cons_idx / NS) & 1u);
+      const uint32_t base = data0 + s * kStage + (uint32_t)lane * 16u;
+      float4 av[G], bv[G];
+      float ss[G];
+#pragma unroll
+      for (int u = 0; u < G; ++u) {                 // unfilled slots hold stale bytes: unused
+        av[u] = lds128(base + (uint32_t)(u * OPS) * 512u);
+        if (HAS_B) bv[u] = lds128(base + (uint32_t)(u * OPS) * 512u + 512u);
+        ss[u] = a_scale ? __shfl_sync(kFull, sc0, (tc + u - chunk_base) & 31) : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        if (tc + u < e_end) {
+          const int tt = tc + u;
+          while (tt >= cur_end) PGH_FLUSH();
+          float4 m = av[u];
+          if (a_scale)
+            m = make_float4(__fmul_rn(m.x, ss[u]), __fmul_rn(m.y, ss[u]), __fmul_rn(m.z, ss[u]),
+                            __fmul_rn(m.w, ss[u]));
+          if (HAS_B)
+            m = make_float4(__fmul_rn(m.x, bv[u].x), __fmul_rn(m.y, bv[u].y),
+                            __fmul_rn(m.z, bv[u].z), __fmul_rn(m.w, bv[u].w));
+          if (AGGR == PGH_MAX)
+            acc = make_float4(fmaxf(acc.x, m.x), fmaxf(acc.y, m.y), fmaxf(acc.z, m.z), fmaxf(acc.w, m.w));
+          else if (AGGR == PGH_MIN)
+            acc = make_float4(fminf(acc.x, m.x), fminf(acc.y, m.y), fminf(acc.z, m.z), fminf(acc.w, m.w));
+          else
+            acc = make_float4(__fadd_rn(acc.x, m.x), __fadd_rn(acc.y, m.y),
+                              __fadd_rn(acc.z, m.z), __fadd_rn(acc.w, m.w));
+        }
+      }
+      ++cons_idx;
+      // every lane has its values in registers: the stage may be overwritten
+      __syncwarp();
+      PGH_ISSUE();
+      if (tc + G - chunk_base >= 32) {              // consume pointer enters the next chunk
+        chunk_base += 32;
+        ci0 = ci1; di0 = di1; sc0 = sc1;
+        PGH_LOAD_PLAN(chunk_base + 32, ci1, di1, sc1);
+      }
+    }
     while (cur < nr) PGH_FLUSH();
 #undef PGH_ISSUE
 #undef PGH_LOAD_PLAN
@@ -613,7 +968,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 
 // run-time tuning knobs (pgh_set_tuning): [0] seg_gmr variant (-1 = built-in choice),
-// [1] ring kernel: target plan entries per warp, [2..7] reserved
+// [1] ring kernel: target plan entries per warp, [6] profiling: no row stores,
+// [7] bulk kernel: target plan entries per warp (default 32)
 // [2..5] fused BN kernels (fused_mlp.cu)
 int g_tune[8] = {-1, 16, 0, 0, 0, 0, 0, 0};
 
@@ -667,6 +1023,79 @@ static void launch_ring(int variant, cudaStream_t s, const float* a_val, const i
 #undef PGH_RING
 }
 
+
+template <int AGGR, bool HAS_B, int G, int NS, int WARPS>
+static void launch_bulk_t(cudaStream_t s, const float* a_val, const int* c, const float* a_scale,
+                          const float* b_val, const int* d, const int* rowptr, int64_t n_rows,
+                          int dense, int lda, int ldb, int ldo, int rw, int accum, float* out) {
+  constexpr int smem = WARPS * NS * G * (HAS_B ? 2 : 1) * 512 + WARPS * NS * 8;
+  auto kern = seg_gmr_bulk_kernel<AGGR, HAS_B, G, NS, WARPS>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  const unsigned nb = blocks_for(n_rows, WARPS * rw);
+  kern<<<nb, WARPS * 32, smem, s>>>(a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb,
+                                    ldo, rw, accum, out);
+}
+
+// variants 20..: bulk-copy kernel; g_tune[1] = target plan entries per warp (as for the ring)
+template <int AGGR>
+static void launch_bulk(int variant, cudaStream_t s, const float* a_val, const int* c,
+                        const float* a_scale, const float* b_val, const int* d,
+                        const int* rowptr, int64_t n_rows, int64_t n_entries, int dense, int lda,
+                        int ldb, int ldo, int accum, float* out) {
+  int rw = 16;
+  if (n_entries > 0 && n_rows > 0) {
+    const double avg = (double)n_entries / (double)n_rows;
+    rw = (int)((double)(g_tune[7] > 0 ? g_tune[7] : 32) / (avg > 0.5 ? avg : 0.5));
+  }
+  if (rw < 1) rw = 1;
+  if (rw > 31) rw = 31;
+#define PGH_BULK(G, NS, W)                                                                   \
+  do {                                                                                       \
+    if (b_val) launch_bulk_t<AGGR, true, G, NS, W>(s, a_val, c, a_scale, b_val, d, rowptr,   \
+                                                   n_rows, dense, lda, ldb, ldo, rw, accum,  \
+                                                   out);                                     \
+    else launch_bulk_t<AGGR, false, G, NS, W>(s, a_val, c, a_scale, b_val, d, rowptr,        \
+                                              n_rows, dense, lda, ldb, ldo, rw, accum, out); \
+  } while (0)
+  switch (variant) {
+    case 21: PGH_BULK(8, 3, 4); break;    // 96 KB (two operands): 2 CTAs/SM
+    case 22: PGH_BULK(4, 4, 8); break;    // 128 KB: 1 CTA/SM, 8 warps
+    case 23: PGH_BULK(4, 6, 4); break;    // 96 KB: 2 CTAs/SM
+    case 24: PGH_BULK(8, 3, 2); break;    // 48 KB: 4 CTAs/SM
+    case 25: PGH_BULK(4, 2, 4); break;    // 32 KB: 6-7 CTAs/SM
+    default: PGH_BULK(4, 4, 4); break;    // 20: 64 KB: 3 CTAs/SM
+  }
+#undef PGH_BULK
+}
+
+
+// variants 30..: lean streaming kernel (see seg_gmr_lean_kernel)
+template <int AGGR, int U, int MINB>
+static void launch_lean(cudaStream_t s, const float* a_val, const int* c, const float* a_scale,
+                        const float* b_val, const int* d, const int* rowptr, int64_t n_rows,
+                        int dense, int lda, int ldb, int ldo, int rw, int accum, float* out) {
+  const unsigned nb = blocks_for(n_rows, (kThreads / 32) * rw);
+#define PGH_LEAN(B, S, A)                                                                      \
+  seg_gmr_lean_kernel<AGGR, B, S, A, U, MINB><<<nb, kThreads, 0, s>>>(                         \
+      a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, out)
+  const int sel = (b_val ? 4 : 0) | (a_scale ? 2 : 0) | (accum ? 1 : 0);
+  switch (sel) {
+    case 0: PGH_LEAN(false, false, false); break;
+    case 1: PGH_LEAN(false, false, true); break;
+    case 2: PGH_LEAN(false, true, false); break;
+    case 3: PGH_LEAN(false, true, true); break;
+    case 4: PGH_LEAN(true, false, false); break;
+    case 5: PGH_LEAN(true, false, true); break;
+    case 6: PGH_LEAN(true, true, false); break;
+    default: PGH_LEAN(true, true, true); break;
+  }
+#undef PGH_LEAN
+}
+
 template <int AGGR, int VEC>
 static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, const int* c,
                        const float* a_scale, const float* b_val, const int* d,
@@ -685,13 +1114,28 @@ static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, co
       if (rw > kMaxRW) rw = kMaxRW;
     }
     const unsigned nb = blocks_for(n_rows, (kThreads / 32) * rw);
+    if (g_tune[6] == 1) accum = 2;                  // profiling only: no row stores (WRONG results)
     // measured on B200 (profiles/README.md): 4 entries in flight at 64 registers (4 CTAs/SM)
     // is best for the short rows of the SSWL keys, 2 entries at 48 registers (5 CTAs/SM) for
     // long rows (the 2-FWL key, ~8 entries per row); PYGHO_B200_GMR_VARIANT overrides
     static const int forced = [] { const char* e = getenv("PYGHO_B200_GMR_VARIANT"); return e ? atoi(e) : -1; }();
     int variant = g_tune[0] >= 0 ? g_tune[0] : forced;
-    // single operand (pooling, unpooling, coalesce): the cp.async ring wins (bench_gmr.py)
-    if (variant < 0 && !b_val) variant = 13;
+    // single operand (pooling, unpooling, coalesce): the cp.async ring wins (bench_gmr.py);
+    // two operands: the lean kernel (half the instructions of the first streaming kernel,
+    // 54 vs 61 us on the SSWL key, profiles/r1_gmr_ablate.txt)
+    if (variant < 0) variant = b_val ? 30 : 13;
+    if (variant >= 30) {
+      if (g_tune[6] == 1) accum = 0;
+      if (variant == 31) launch_lean<AGGR, 8, 2>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
+      else if (variant == 32) launch_lean<AGGR, 2, 5>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
+      else if (variant == 33) launch_lean<AGGR, 4, 3>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
+      else launch_lean<AGGR, 4, 4>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
+      return;
+    }
+    if (variant >= 20) {
+      launch_bulk<AGGR>(variant, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, n_entries, dense, lda, ldb, ldo, accum, out);
+      return;
+    }
     if (variant >= 10) {
       launch_ring<AGGR>(variant, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, n_entries, dense, lda, ldb, ldo, accum, out);
       return;

@@ -244,15 +244,23 @@ def test_step_graph_replay_matches_eager_training():
         return model, step
 
     m_eager, step_eager = build()
-    eager_losses = [float(step_eager()) for _ in range(4)]
+    eager_losses, eager_state = [], None
+    for i in range(4):
+        eager_losses.append(float(step_eager()))
+        if i == 1:
+            eager_state = {k: v.detach().clone().float() for k, v in m_eager.state_dict().items()}
     m_graph, step_graph = build()
     sg = StepGraph(step_graph, warmup=1)                 # 1 eager step, then capture
     assert sg.launches > 10                              # our kernels are inside the graph
-    graph_losses = [float(sg.replay()) for _ in range(3)]
+    graph_losses = [float(sg.replay())]
+    # after two updates the two models agree to rounding.  (Later states are compared through
+    # the loss only: Linear biases in front of a BatchNorm have a mathematically zero gradient,
+    # Adam normalises the ~1e-9 atomics noise of torch's embedding backward to +-lr steps.)
+    for k, q in m_graph.state_dict().items():
+        close(q.float(), eager_state[k], 1e-6)
+    graph_losses += [float(sg.replay()) for _ in range(2)]
     for a, b in zip(eager_losses[1:], graph_losses):
         assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (eager_losses, graph_losses)
-    for (k, p), (_, q) in zip(m_eager.state_dict().items(), m_graph.state_dict().items()):
-        close(q.float(), p.float(), 1e-4)
 
 
 @pytest.mark.parametrize("threaded", [False, True])
