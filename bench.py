@@ -238,7 +238,7 @@ def roofline_spspmm(dd_list, hidden, device, peaks):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))["traffic"]
     except Exception:
         pass
-    return {"bound": "hbm", "kernel": "seg_gmr_stream_kernel<sum,B> (spspmm fwd, key X___X___1___A___0)",
+    return {"bound": "hbm", "kernel": "seg_gmr_lean_kernel<sum,B> (spspmm fwd, key X___X___1___A___0)",
             "achieved": achieved, "peak": peak if peak else 6650.0, "unit": "GB/s",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peak
             else "fallback 6650 GB/s (B200_PROFILING.md)",
@@ -358,7 +358,9 @@ def run_b200(args):
     # acd plans); the copies + CSR regrouping of batch i+1 are issued on a side stream right
     # after step i has been launched (DevicePrefetcher), the loss is read back every step
     from pygho_b200.hodata.device import DevicePrefetcher
-    feeder = DevicePrefetcher(hbs, device, keys, pinned)
+    tables = {"x": model.x_encoder.num_embeddings, "A": model.ea_encoder.num_embeddings,
+              "X": model.tuplefeat_encoder.num_embeddings}
+    feeder = DevicePrefetcher(hbs, device, keys, pinned, embeddings=tables)
 
     # The loss of every step is copied to pinned host memory and read by the host ONE step
     # late (deferred logging): the host launches step i, then waits for step i-1's loss,

@@ -15,7 +15,7 @@ from pygho_b200.backend.utils import torch_scatter_reduce
 from pygho_b200.honn import Conv
 from pygho_b200.honn.MaOperator import OpPooling
 from pygho_b200.honn.TensorOp import OpPoolingSubg2D, OpPoolingSubg3D
-from pygho_b200.honn.utils import MLP
+from pygho_b200.honn.utils import MLP, Embedding
 
 CONVS = ("NGNN", "SSWL", "DSSGNN", "PPGN", "I2GNN", "GNNAK")
 
@@ -47,11 +47,12 @@ class SpModel(nn.Module):
         base = {"dp": 0.0, "norm": norm, "act": "silu", "normparam": normparam}
         convmlp = dict(base, tailact=True, numlayer=mlplayer)
         self.conv_name, self.residual, self.npool = conv, residual, npool
-        self.x_encoder = nn.Embedding(32, hiddim)
-        self.ea_encoder = nn.Embedding(16, hiddim)
-        self.tuplefeat_encoder = nn.Embedding(16, hiddim)
+        # nn.Embedding subclasses (same state dict): gather kernel + deterministic gradient
+        self.x_encoder = Embedding(32, hiddim)
+        self.ea_encoder = Embedding(16, hiddim)
+        self.tuplefeat_encoder = Embedding(16, hiddim)
         if conv == "I2GNN":
-            self.tuplefeat_encoder2 = nn.Embedding(16, hiddim)
+            self.tuplefeat_encoder2 = Embedding(16, hiddim)
         self.lin_tupleinit0 = nn.Linear(hiddim, hiddim)
         self.lin_tupleinit1 = nn.Linear(hiddim, hiddim)
         self.subggnns = nn.ModuleList(

@@ -74,6 +74,19 @@ int pgh_seg_gmr_ld_f32(const float* a_val, int64_t lda, const int32_t* c, const 
                        int64_t n_rows, int64_t n_entries, int64_t dense, int aggr, int accumulate,
                        float* out, int64_t ldo, void* stream);
 
+/* pgh_seg_gmr_ld_f32 with a fused row epilogue (dense % 128 == 0, 16-byte aligned rows, sum or
+ * mean):  out[r,:] = (add_src ? add_src[r,:] : 0) + reduction(r)   and, if copy_src != NULL,
+ * copy_dst[r,:] = copy_src[r,:].  One SSWL layer uses it twice: the forward writes X next to
+ * X (x) A in the concatenated buffer (reference Conv.py:97-103 `catvalue`) without a separate
+ * copy, the backward starts the accumulation of dX from the gradient slice instead of cloning
+ * it first.                                                                                   */
+int pgh_seg_gmr_fused_f32(const float* a_val, int64_t lda, const int32_t* c, const float* a_scale,
+                          const float* b_val, int64_t ldb, const int32_t* d, const int32_t* rowptr,
+                          int64_t n_rows, int64_t n_entries, int64_t dense, int aggr,
+                          const float* add_src, int64_t ld_add, const float* copy_src,
+                          int64_t ld_copy_src, float* copy_dst, int64_t ld_copy_dst, float* out,
+                          int64_t ldo, void* stream);
+
 /* max/min backward, step 1: gscaled[r,:] = grad[r,:] / (#{t in seg(r): A(t)*B(t) == out[r,:]}
  *                                                       + [out[r,:] == 0])
  * (torch's scatter_reduce amax/amin backward splits the gradient evenly among ties and

@@ -294,7 +294,9 @@ seg_gmr_lean_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
                     const float* __restrict__ a_scale, const float* __restrict__ b_val,
                     const int* __restrict__ d, const int* __restrict__ rowptr,
                     long long n_rows, int dense, int lda, int ldb, int ldo, int rw,
-                    float* __restrict__ out) {
+                    const float* __restrict__ acc_src, int lds,
+                    const float* __restrict__ copy_src, int ldcs, float* __restrict__ copy_dst,
+                    int ldcd, float* __restrict__ out) {
   constexpr unsigned kFull = 0xffffffffu;
   constexpr bool kLen = (AGGR != PGH_SUM);          // row lengths matter (mean, empty max/min rows)
   const int lane = threadIdx.x & 31;
@@ -327,13 +329,17 @@ seg_gmr_lean_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
         r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);               \
       }                                                                                 \
     }                                                                                   \
-    if (ACCUM) {                                                                        \
-      const float4 o_ = *reinterpret_cast<const float4*>(o_ptr);                        \
+    if (ACCUM) {       /* out = acc_src + reduction (acc_src == out: accumulate in place) */ \
+      const float4 o_ = *reinterpret_cast<const float4*>(                               \
+          acc_src + (size_t)(r0 + cur) * lds + col);                                    \
       r_ = make_float4(__fadd_rn(o_.x, r_.x), __fadd_rn(o_.y, r_.y),                    \
                        __fadd_rn(o_.z, r_.z), __fadd_rn(o_.w, r_.w));                   \
     }                                                                                   \
     *reinterpret_cast<float4*>(o_ptr) = r_;                                             \
     o_ptr += ldo;                                                                       \
+    if (copy_src)      /* fused row copy: copy_dst[row] = copy_src[row] (warp-uniform) */  \
+      *reinterpret_cast<float4*>(copy_dst + (size_t)(r0 + cur) * ldcd + col) =          \
+          __ldg(reinterpret_cast<const float4*>(copy_src + (size_t)(r0 + cur) * ldcs + col)); \
     acc = make_float4(init, init, init, init);                                          \
     ++cur;                                                                              \
     cur_end = __shfl_sync(kFull, rp, cur + 1);      /* source lane wraps mod 32 */      \
@@ -1074,15 +1080,29 @@ static void launch_bulk(int variant, cudaStream_t s, const float* a_val, const i
 
 
 // variants 30..: lean streaming kernel (see seg_gmr_lean_kernel)
+struct LeanExtra {                       // optional fused epilogue work, all row-aligned with out
+  const float* add_src = nullptr;        // out = add_src + reduction (NULL + accum: in place)
+  int ld_add = 0;
+  const float* copy_src = nullptr;       // copy_dst[row] = copy_src[row]
+  int ld_copy_src = 0;
+  float* copy_dst = nullptr;
+  int ld_copy_dst = 0;
+};
+
 template <int AGGR, int U, int MINB>
 static void launch_lean(cudaStream_t s, const float* a_val, const int* c, const float* a_scale,
                         const float* b_val, const int* d, const int* rowptr, int64_t n_rows,
-                        int dense, int lda, int ldb, int ldo, int rw, int accum, float* out) {
+                        int dense, int lda, int ldb, int ldo, int rw, int accum, float* out,
+                        const LeanExtra& x) {
   const unsigned nb = blocks_for(n_rows, (kThreads / 32) * rw);
+  const float* acc_src = x.add_src ? x.add_src : out;
+  const int lds = x.add_src ? x.ld_add : ldo;
+  const bool acc = accum || x.add_src;
 #define PGH_LEAN(B, S, A)                                                                      \
   seg_gmr_lean_kernel<AGGR, B, S, A, U, MINB><<<nb, kThreads, 0, s>>>(                         \
-      a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, out)
-  const int sel = (b_val ? 4 : 0) | (a_scale ? 2 : 0) | (accum ? 1 : 0);
+      a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, acc_src, lds,     \
+      x.copy_src, x.ld_copy_src, x.copy_dst, x.ld_copy_dst, out)
+  const int sel = (b_val ? 4 : 0) | (a_scale ? 2 : 0) | (acc ? 1 : 0);
   switch (sel) {
     case 0: PGH_LEAN(false, false, false); break;
     case 1: PGH_LEAN(false, false, true); break;
@@ -1097,10 +1117,10 @@ static void launch_lean(cudaStream_t s, const float* a_val, const int* c, const 
 }
 
 template <int AGGR, int VEC>
-static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, const int* c,
-                       const float* a_scale, const float* b_val, const int* d,
-                       const int* rowptr, int64_t n_rows, int64_t n_entries, int dense, int lda,
-                       int ldb, int ldo, int accum, float* out) {
+static int launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, const int* c,
+                      const float* a_scale, const float* b_val, const int* d,
+                      const int* rowptr, int64_t n_rows, int64_t n_entries, int dense, int lda,
+                      int ldb, int ldo, int accum, float* out, const LeanExtra* extra = nullptr) {
   if (VEC == 4 && dense % 128 == 0 && !g_force_rowwise) {
     // rows per warp: aim at ~32 plan entries per warp, at least 4 warps' worth of blocks per SM
     int rw = kMaxRW;
@@ -1124,21 +1144,24 @@ static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, co
     // two operands: the lean kernel (half the instructions of the first streaming kernel,
     // 54 vs 61 us on the SSWL key, profiles/r1_gmr_ablate.txt)
     if (variant < 0) variant = b_val ? 30 : 13;
+    if (extra) variant = 30;                        // the fused epilogue lives in the lean kernel
     if (variant >= 30) {
       if (g_tune[6] == 1) accum = 0;
-      if (variant == 31) launch_lean<AGGR, 8, 2>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
-      else if (variant == 32) launch_lean<AGGR, 2, 5>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
-      else if (variant == 33) launch_lean<AGGR, 4, 3>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
-      else launch_lean<AGGR, 4, 4>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
-      return;
+      const LeanExtra none;
+      const LeanExtra& x = extra ? *extra : none;
+      if (variant == 31) launch_lean<AGGR, 8, 2>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
+      else if (variant == 32) launch_lean<AGGR, 2, 5>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
+      else if (variant == 33) launch_lean<AGGR, 4, 3>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
+      else launch_lean<AGGR, 4, 4>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
+      return 0;
     }
     if (variant >= 20) {
       launch_bulk<AGGR>(variant, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, n_entries, dense, lda, ldb, ldo, accum, out);
-      return;
+      return 0;
     }
     if (variant >= 10) {
       launch_ring<AGGR>(variant, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, n_entries, dense, lda, ldb, ldo, accum, out);
-      return;
+      return 0;
     }
     if (variant < 0) variant = (n_entries > 6 * n_rows) ? 3 : 2;
     if (b_val) {
@@ -1158,14 +1181,16 @@ static void launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, co
       seg_gmr_stream_kernel<AGGR, false, 8, 1><<<nb, kThreads, 0, s>>>(
           a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
     }
-    return;
+    return 0;
   }
+  if (extra) return arg_error("seg_gmr_fused: needs dense % 128 == 0 and 16-byte aligned rows");
   if (b_val)
     seg_gmr_kernel<AGGR, VEC, true><<<g.blocks, kThreads, 0, s>>>(
         a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, g.lpr, accum, out);
   else
     seg_gmr_kernel<AGGR, VEC, false><<<g.blocks, kThreads, 0, s>>>(
         a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, g.lpr, accum, out);
+  return 0;
 }
 
 }  // namespace pgh
@@ -1226,6 +1251,48 @@ extern "C" int pgh_seg_gmr_ld_f32(const float* a_val, int64_t lda, const int32_t
   }
 #undef PGH_GMR
   return check_launch("seg_gmr");
+}
+
+extern "C" int pgh_seg_gmr_fused_f32(const float* a_val, int64_t lda, const int32_t* c,
+                                     const float* a_scale, const float* b_val, int64_t ldb,
+                                     const int32_t* d, const int32_t* rowptr, int64_t n_rows,
+                                     int64_t n_entries, int64_t dense, int aggr,
+                                     const float* add_src, int64_t ld_add, const float* copy_src,
+                                     int64_t ld_copy_src, float* copy_dst, int64_t ld_copy_dst,
+                                     float* out, int64_t ldo, void* stream) {
+  if (!a_val || !out) return arg_error("seg_gmr_fused: a_val and out are required");
+  if (n_rows < 0 || dense <= 0 || dense % 128 != 0) return arg_error("seg_gmr_fused: dense % 128");
+  if (aggr < 0 || aggr > 1) return arg_error("seg_gmr_fused: sum or mean only");
+  if ((copy_src == nullptr) != (copy_dst == nullptr)) return arg_error("seg_gmr_fused: copy pair");
+  const int64_t lim = 0x7fffffff;
+  if (lda < dense || ldo < dense || (b_val && ldb < dense) || lda > lim || ldb > lim || ldo > lim ||
+      (add_src && (ld_add < dense || ld_add > lim)) ||
+      (copy_src && (ld_copy_src < dense || ld_copy_dst < dense || ld_copy_src > lim ||
+                    ld_copy_dst > lim)))
+    return arg_error("seg_gmr_fused: leading dimensions");
+  if (n_rows == 0) return 0;
+  const bool al = aligned16(a_val) && aligned16(out) && (!b_val || aligned16(b_val)) &&
+                  lda % 4 == 0 && ldo % 4 == 0 && (!b_val || ldb % 4 == 0) &&
+                  (!add_src || (aligned16(add_src) && ld_add % 4 == 0)) &&
+                  (!copy_src || (aligned16(copy_src) && aligned16(copy_dst) &&
+                                 ld_copy_src % 4 == 0 && ld_copy_dst % 4 == 0));
+  if (!al) return arg_error("seg_gmr_fused: rows must be 16-byte aligned");
+  const Geometry g = geometry(n_rows, dense, true);
+  if (!rowptr) n_entries = n_rows;
+  LeanExtra x;
+  x.add_src = add_src; x.ld_add = (int)ld_add;
+  x.copy_src = copy_src; x.ld_copy_src = (int)ld_copy_src;
+  x.copy_dst = copy_dst; x.ld_copy_dst = (int)ld_copy_dst;
+  const int la = (int)lda, lb = (int)(b_val ? ldb : dense), lo = (int)ldo;
+  int rc;
+  if (aggr == PGH_SUM)
+    rc = launch_gmr<PGH_SUM, 4>(g, as_stream(stream), a_val, c, a_scale, b_val, d, rowptr, n_rows,
+                                n_entries, (int)dense, la, lb, lo, 0, out, &x);
+  else
+    rc = launch_gmr<PGH_MEAN, 4>(g, as_stream(stream), a_val, c, a_scale, b_val, d, rowptr, n_rows,
+                                 n_entries, (int)dense, la, lb, lo, 0, out, &x);
+  if (rc) return rc;
+  return check_launch("seg_gmr_fused");
 }
 
 extern "C" int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float* a_scale,

@@ -73,9 +73,17 @@ def sp_datadict(hb: HostBatch, device, keys: Iterable[str] = (),
     return dd
 
 
-def prefetch_plans(datadict: dict, keys: Iterable[str], backward: bool = True) -> None:
+def prefetch_plans(datadict: dict, keys: Iterable[str], backward: bool = True,
+                   embeddings: Optional[Dict[str, int]] = None) -> None:
     """Build (and cache on the ``acd`` tensors) the CSR groupings the kernels will ask for,
-    so that the first layer of the model does not pay for them."""
+    so that the first layer of the model does not pay for them.  ``embeddings`` maps datadict
+    entries holding integer labels ("x", "A", "X") to the size of the embedding table that
+    encodes them: their :class:`pygho_b200.plans.EmbeddingPlan` is built here too."""
+    for name, num in (embeddings or {}).items():
+        t = datadict[name]
+        t = t.values if isinstance(t, SparseTensor) else t
+        if t is not None and t.is_cuda and t.dtype in (torch.int64, torch.int32) and t.numel():
+            P.embedding_plan(t, int(num))
     nX, nA = datadict["X"].nnz, datadict["A"].nnz
     for key in keys:
         _op0, op1, _d1, op2, _d2 = parse_key(key)
@@ -105,8 +113,9 @@ class DevicePrefetcher:
     GIL while they run."""
 
     def __init__(self, host_batches, device, keys, pinned: Optional[dict] = None,
-                 threaded: bool = True):
+                 threaded: bool = True, embeddings: Optional[Dict[str, int]] = None):
         self.hbs, self.device, self.keys = list(host_batches), device, list(keys)
+        self.embeddings = dict(embeddings or {})
         self.pinned = {} if pinned is None else pinned
         self.stream = torch.cuda.Stream(device)
         self.pos = 0
@@ -124,7 +133,7 @@ class DevicePrefetcher:
     def _issue(self, hb):
         with torch.cuda.stream(self.stream):
             dd = sp_datadict(hb, self.device, self.keys, self.pinned)
-            prefetch_plans(dd, self.keys)
+            prefetch_plans(dd, self.keys, embeddings=self.embeddings)
         return dd
 
     def _run(self):

@@ -64,6 +64,25 @@ class LayerNorm(nn.Module):
         return self.norm(x)
 
 
+class Embedding(nn.Embedding):
+    """``nn.Embedding`` whose CUDA path gathers with the seg_gmr kernel and computes the weight
+    gradient deterministically from a per-batch plan cached on the index tensor (the integer
+    node / edge / tuple labels of a batch never change).  Same parameters and state dict;
+    ``padding_idx`` / ``max_norm`` / ``sparse`` tables and non-fp32 weights use torch's path."""
+
+    def forward(self, input: Tensor) -> Tensor:
+        import torch
+        if (input.is_cuda and self.weight.dtype == torch.float32 and self.padding_idx is None
+                and self.max_norm is None and not self.sparse and not self.scale_grad_by_freq
+                and input.dtype in (torch.int64, torch.int32) and input.numel() > 0
+                and self.embedding_dim % 4 == 0):
+            from .. import plans as P
+            from ..ops import EmbeddingGather
+            return EmbeddingGather.apply(self.weight, input,
+                                         P.embedding_plan(input, self.num_embeddings))
+        return super().forward(input)
+
+
 normdict = {"bn": BatchNorm, "ln": LayerNorm, "none": NoneNorm}
 act_dict = {"relu": nn.ReLU(inplace=True), "ELU": nn.ELU(inplace=True),
             "silu": nn.SiLU(inplace=True)}

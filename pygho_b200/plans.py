@@ -466,3 +466,52 @@ def filtered_plan(tar_ind: Tensor, ind1: Tensor, dim1: int, ind2: Tensor, dim2: 
         torch.zeros((3, 0), dtype=torch.int64, device=dev)
     _cache(acd)[("acd", n_out, ind1.shape[1], ind2.shape[1])] = plan
     return acd, plan
+
+
+# ------------------------------------------------------------------------- embedding tables
+class EmbeddingPlan(NamedTuple):
+    """Index structures of one ``nn.Embedding`` lookup (``idx`` -> rows of the table), built
+    once per index tensor and cached on it:
+
+    * ``idx32``: the indices as int32 (forward gather);
+    * ``perm``: stable sort of the positions by index value;
+    * ``levels``: row pointers of a reduction tree.  Level 0 cuts the sorted positions into
+      chunks of at most ``chunk`` entries that never straddle two index values, every further
+      level does the same with the partial sums of the level before, the last one has exactly
+      ``num_embeddings`` rows.  All sizes are static (V + ceil(n / chunk) per level), so
+      building the plan needs no host synchronisation.  The weight gradient is then a chain of
+      segmented sums in a fixed order: deterministic, no atomics, no per-step sort."""
+    idx32: Tensor
+    perm: Tensor
+    levels: Tuple[Tensor, ...]
+    num_embeddings: int
+
+
+def embedding_plan(idx: Tensor, num_embeddings: int, chunk: int = 64) -> EmbeddingPlan:
+    cache = _cache(idx)
+    ck = ("embedding", int(num_embeddings), int(chunk))
+    hit = cache.get(ck)
+    if hit is not None:
+        return hit
+    dev = _lib.require_cuda(idx)
+    flat = idx.reshape(-1)
+    n, V = flat.numel(), int(num_embeddings)
+    idx32 = to_i32(flat)
+    rowptr_id, perm = csr_of(idx32, V)                 # positions grouped by index value
+    if perm is None:
+        perm = torch.arange(n, dtype=torch.int32, device=dev)
+    levels = []
+    bounds, size = rowptr_id, n                        # id boundaries in units of the current level
+    while size > max(2 * V, 4 * chunk):
+        cuts = torch.arange(0, size, chunk, dtype=torch.int32, device=dev)
+        starts = torch.sort(torch.cat([bounds[:V], cuts])).values
+        rows = starts.numel()
+        levels.append(torch.cat([starts, bounds[V:V + 1]]).contiguous())
+        # chunk k belongs to the index value whose range contains its start
+        bounds = torch.searchsorted(starts, bounds[:V], right=False).to(torch.int32)
+        bounds = torch.cat([bounds, torch.full((1,), rows, dtype=torch.int32, device=dev)])
+        size = rows
+    levels.append(bounds.contiguous())
+    plan = EmbeddingPlan(idx32, perm, tuple(levels), V)
+    cache[ck] = plan
+    return plan

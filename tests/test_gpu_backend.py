@@ -625,3 +625,61 @@ def test_single_graph_batch(B):
     acd = dd["X___X___1___A___0___acd"]
     want = O.filterind(hb.tupleid, *O.spspmm_ind(hb.tupleid, 1, hb.edge_index, 0))
     assert np.array_equal(canon(acd), want)
+
+
+@pytest.mark.parametrize("mean", [False, True])
+def test_seg_gmr_fused_epilogue_matches_separate_launches(mean):
+    """out = add_src + reduction and the fused row copy (pgh_seg_gmr_fused_f32) against the plain
+    launch + torch arithmetic; strided column slices like the SSWL concatenated buffer."""
+    ops = torch.ops.pygho_b200
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    n_rows, nA, nB, d = 777, 500, 300, 128
+    lens = torch.randint(0, 5, (n_rows,), generator=gen, device=DEV)
+    rowptr = torch.zeros(n_rows + 1, dtype=torch.int32, device=DEV)
+    rowptr[1:] = lens.cumsum(0)
+    Tn = int(rowptr[-1])
+    c = torch.randint(0, nA, (Tn,), generator=gen, device=DEV, dtype=torch.int32)
+    dd = torch.randint(0, nB, (Tn,), generator=gen, device=DEV, dtype=torch.int32)
+    A = torch.randn(nA, d, generator=gen, device=DEV)
+    Bv = torch.randn(nB, d, generator=gen, device=DEV)
+    scale = torch.rand(nA, generator=gen, device=DEV) if mean else None
+    aggr = 1 if mean else 0
+    want = ops.seg_gmr(A, c, scale, Bv, dd, rowptr, n_rows, aggr)
+    wide = torch.randn(n_rows, 3 * d, generator=gen, device=DEV)        # add_src / copy_src slices
+    buf = torch.zeros(n_rows, 3 * d, device=DEV)
+    ops.seg_gmr_fused(A, c, scale, Bv, dd, rowptr, n_rows, aggr, wide[:, :d], wide[:, d:2 * d],
+                      buf[:, 2 * d:], buf[:, d:2 * d])
+    close(buf[:, d:2 * d], want + wide[:, :d], 1e-6)
+    assert torch.equal(buf[:, 2 * d:], wide[:, d:2 * d])
+    assert float(buf[:, :d].abs().max()) == 0.0                          # untouched third
+    out = torch.empty(n_rows, d, device=DEV)
+    ops.seg_gmr_fused(A, c, scale, Bv, dd, rowptr, n_rows, aggr, None, None, None, out)
+    assert torch.equal(out, want)
+    with pytest.raises(Exception):
+        ops.seg_gmr_fused(A[:, :64].contiguous(), c, None, None, None, rowptr, n_rows, 0, None,
+                          None, None, torch.empty(n_rows, 64, device=DEV))
+
+
+@pytest.mark.parametrize("n,V,D", [(5, 16, 8), (300, 16, 128), (70001, 28, 128), (4097, 3, 32)])
+def test_embedding_matches_torch(n, V, D):
+    """pygho_b200.honn.utils.Embedding: forward bit-exact, deterministic weight gradient within
+    fp32 summation error of torch's (which uses atomics), absent ids get a zero gradient."""
+    from pygho_b200.honn.utils import Embedding
+    torch.manual_seed(0)
+    emb = Embedding(V, D).to(DEV)
+    ref = torch.nn.Embedding(V, D).to(DEV)
+    ref.load_state_dict(emb.state_dict())
+    idx = torch.randint(0, max(1, V - 2), (n,), device=DEV)              # last two ids never occur
+    w = torch.randn(n, D, device=DEV)
+    out, out_ref = emb(idx), ref(idx)
+    assert torch.equal(out, out_ref)
+    (out * w).sum().backward()
+    (out_ref * w).sum().backward()
+    close(emb.weight.grad, ref.weight.grad.double(), 2e-6 * max(1.0, n / V) ** 0.5)
+    assert float(emb.weight.grad[V - 2:].abs().max()) == 0.0
+    g1 = emb.weight.grad.clone()
+    emb.weight.grad = None
+    (emb(idx) * w).sum().backward()
+    assert torch.equal(emb.weight.grad, g1)                               # deterministic
+    idx2 = idx.reshape(-1, 1)[: n - n % 1].reshape(n)                     # other tensor object
+    assert torch.equal(emb(idx2.reshape(n, 1)).squeeze(1), out_ref)
