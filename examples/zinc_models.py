@@ -82,6 +82,9 @@ class SpModel(nn.Module):
         x, A, X = self.encode(datadict)
         X = self.tupleinit(X, x)
         for conv in self.subggnns:
+            if self.residual and isinstance(conv, Conv.SSWLConv):
+                X = conv.forward(A, X, datadict, residual=X)     # X + conv(X), add fused
+                continue
             tX = conv.forward(A, X, datadict)
             X = X.add(tX, True) if self.residual else tX
         x = self.poolmlp(self.lpool(X))

@@ -235,6 +235,11 @@ int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, float eps, float m
                      size_t ws_bytes, void* stream);
 int pgh_bn_act_fwd_f32(const float* y, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, int64_t rows, int64_t C, int act, float* z, void* stream);
+/* fwd with a residual input: z = act(...) + residual (the `X + conv(X)` of example/zinc.py:286
+ * folded into the last block of the layer's MLP); residual may be NULL */
+int pgh_bn_act_res_fwd_f32(const float* y, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, int64_t rows, int64_t C, int act,
+                           const float* residual, float* z, void* stream);
 int pgh_bn_act_bwd_f32(const float* dz, const float* y, const float* mean, const float* rstd,
                        const float* gamma, const float* beta, int64_t rows, int64_t C, int act,
                        float* dy, float* dgamma, float* dbeta, float* dbias, void* ws,

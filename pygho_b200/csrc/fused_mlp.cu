@@ -160,16 +160,17 @@ template <int ACT, int UN>
 __global__ void bn_act_fwd_kernel(const float4* __restrict__ y, const float4* __restrict__ mean,
                                   const float4* __restrict__ rstd, const float4* __restrict__ gamma,
                                   const float4* __restrict__ beta, long long n4, int c4, int rev,
-                                  float4* __restrict__ z) {
+                                  const float4* __restrict__ residual, float4* __restrict__ z) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UN) {
-    float4 v[UN];
+    float4 v[UN], res[UN];
     long long idx[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const long long i = min(i0 + u * stride, n4 - 1);      // clamped: loads are unconditional
       idx[u] = rev ? n4 - 1 - i : i;
       v[u] = __ldg(y + idx[u]);
+      if (residual) res[u] = __ldg(residual + idx[u]);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -183,6 +184,7 @@ __global__ void bn_act_fwd_kernel(const float4* __restrict__ y, const float4* __
       o.y = act_fwd<ACT>(fmaf((v[u].y - m.y) * r.y, g.y, b.y));
       o.z = act_fwd<ACT>(fmaf((v[u].z - m.z) * r.z, g.z, b.z));
       o.w = act_fwd<ACT>(fmaf((v[u].w - m.w) * r.w, g.w, b.w));
+      if (residual) { o.x += res[u].x; o.y += res[u].y; o.z += res[u].z; o.w += res[u].w; }
       z[idx[u]] = o;
     }
   }
@@ -342,12 +344,14 @@ extern "C" int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, float e
   return check_launch("bn_stats");
 }
 
-extern "C" int pgh_bn_act_fwd_f32(const float* y, const float* mean, const float* rstd,
-                                  const float* gamma, const float* beta, int64_t rows, int64_t C,
-                                  int act, float* z, void* stream) {
+extern "C" int pgh_bn_act_res_fwd_f32(const float* y, const float* mean, const float* rstd,
+                                      const float* gamma, const float* beta, int64_t rows,
+                                      int64_t C, int act, const float* residual, float* z,
+                                      void* stream) {
   if (!y || !mean || !rstd || !z) return arg_error("bn_act_fwd: null pointer");
   if (!bn_ok(rows, C)) return arg_error("bn_act_fwd: need rows > 0, C % 4 == 0, C <= 1024");
-  if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z)) & 15)
+  if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z) |
+       reinterpret_cast<uintptr_t>(residual)) & 15)
     return arg_error("bn_act_fwd: tensors must be 16-byte aligned");
   const long long n4 = rows * (C / 4);
   long long nb = (n4 + 255) / 256;
@@ -356,7 +360,7 @@ extern "C" int pgh_bn_act_fwd_f32(const float* y, const float* mean, const float
   const int rev = bn_tune(4, 0) == 1;
 #define PGH_FWD_U(A, U) bn_act_fwd_kernel<A, U><<<(unsigned)nb, 256, 0, s>>>(                        \
       (const float4*)y, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,             \
-      (const float4*)beta, n4, (int)(C / 4), rev, (float4*)z)
+      (const float4*)beta, n4, (int)(C / 4), rev, (const float4*)residual, (float4*)z)
 #define PGH_FWD(A)                                                                                   \
   do {                                                                                               \
     const int un_ = bn_tune(5, 2);                                                                   \
@@ -367,6 +371,12 @@ extern "C" int pgh_bn_act_fwd_f32(const float* y, const float* mean, const float
 #undef PGH_FWD_U
 #undef PGH_FWD
   return check_launch("bn_act_fwd");
+}
+
+extern "C" int pgh_bn_act_fwd_f32(const float* y, const float* mean, const float* rstd,
+                                  const float* gamma, const float* beta, int64_t rows, int64_t C,
+                                  int act, float* z, void* stream) {
+  return pgh_bn_act_res_fwd_f32(y, mean, rstd, gamma, beta, rows, C, act, nullptr, z, stream);
 }
 
 extern "C" int pgh_bn_act_bwd_f32(const float* dz, const float* y, const float* mean, const float* rstd,

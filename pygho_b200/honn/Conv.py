@@ -41,13 +41,20 @@ class SSWLConv(Module):
         self.aggr2 = TensorOp.OpMessagePassingCrossSubg2D(mode, aggr, optuplefeat, opadj)
         self.lin = MLP(3 * indim, outdim, **mlp)
 
-    def forward(self, A: AnyTensor, X: AnyTensor, datadict: dict) -> AnyTensor:
+    def forward(self, A: AnyTensor, X: AnyTensor, datadict: dict,
+                residual: Optional[AnyTensor] = None) -> AnyTensor:
+        """``residual`` (not in the reference signature; same sparsity / mask as X) is added to
+        the layer output inside the last kernel of the MLP: ``X + conv(X)`` of the reference
+        training scripts (example/zinc.py:286) without a separate pass over the tuples."""
+        res = None if residual is None else (
+            residual.values if isinstance(residual, SparseTensor) else residual.data)
+        lin = self.lin if res is None else (lambda v: self.lin(v, res))
         fused = self._fused_cat(A, X, datadict)
         if fused is not None:
-            return X.tuplewiseapply(lambda _v: self.lin(fused))
+            return X.tuplewiseapply(lambda _v: lin(fused))
         inside = self.aggr1.forward(A, X, datadict, X)
         across = self.aggr2.forward(A, X, datadict, X)
-        return X.catvalue([inside, across], True).tuplewiseapply(self.lin)
+        return X.catvalue([inside, across], True).tuplewiseapply(lin)
 
     def _fused_cat(self, A, X, datadict):
         """[X, X(x)A, A(x)X] written into one buffer by the two spspmm launches (sparse mode,

@@ -116,9 +116,13 @@ class MLP(nn.Module):
             layers += tail(outdim)
         self.lins = nn.Sequential(*layers)
 
-    def forward(self, x: Tensor):
+    def forward(self, x: Tensor, residual: Tensor = None):
+        """``residual`` (same shape as the output) is added to the result; when the MLP ends
+        with a fused Linear-BatchNorm-activation block the addition happens inside that
+        block's kernel instead of a separate pass."""
         if not _fusable(self.lins, x):
-            return self.lins(x)
+            out = self.lins(x)
+            return out if residual is None else out + residual
         # Linear -> BatchNorm(train) -> SiLU/ReLU blocks go through the fused kernels
         # (pygho_b200/csrc/fused_mlp.cu); anything else runs module by module.
         from ..ops import ACT_CODE, LinearBNAct
@@ -133,13 +137,17 @@ class MLP(nn.Module):
                 bn, act = blk
                 if bn.track_running_stats:
                     bn.num_batches_tracked.add_(1)
+                res = None
+                if residual is not None and i + 3 == len(mods):
+                    res, residual = residual.reshape(-1, residual.shape[-1]), None
                 h = LinearBNAct.apply(h, m.weight, m.bias, bn.weight, bn.bias, bn.running_mean,
-                                      bn.running_var, bn.momentum, bn.eps, ACT_CODE[act])
+                                      bn.running_var, bn.momentum, bn.eps, ACT_CODE[act], res)
                 i += 3
             else:
                 h = m(h)
                 i += 1
-        return h.reshape(shape[:-1] + (h.shape[-1],))
+        h = h.reshape(shape[:-1] + (h.shape[-1],))
+        return h if residual is None else h + residual
 
 
 def _match_block(mods, i):

@@ -401,15 +401,18 @@ def _bn_stats_fake(y, eps, momentum, running_mean, running_var):
     return y.new_empty((y.shape[1],)), y.new_empty((y.shape[1],))
 
 
-_LIB.define("bn_act_fwd(Tensor y, Tensor mean, Tensor rstd, Tensor? gamma, Tensor? beta, int act) -> Tensor")
+_LIB.define("bn_act_fwd(Tensor y, Tensor mean, Tensor rstd, Tensor? gamma, Tensor? beta, int act, "
+            "Tensor? residual=None) -> Tensor")
 
 
-def _bn_act_fwd_cuda(y, mean, rstd, gamma, beta, act):
-    y = _f32c(y)
+def _bn_act_fwd_cuda(y, mean, rstd, gamma, beta, act, residual=None):
+    y, residual = _f32c(y), _f32c(residual)
     rows, C = y.shape
+    if residual is not None and residual.shape != y.shape:
+        raise ValueError("bn_act_fwd: residual must have the shape of y")
     z = torch.empty_like(y)
-    call("pgh_bn_act_fwd_f32", ptr(y), ptr(mean), ptr(rstd), ptr(_f32c(gamma)), ptr(_f32c(beta)),
-         rows, C, act, ptr(z), stream_ptr(y.device))
+    call("pgh_bn_act_res_fwd_f32", ptr(y), ptr(mean), ptr(rstd), ptr(_f32c(gamma)),
+         ptr(_f32c(beta)), rows, C, act, ptr(residual), ptr(z), stream_ptr(y.device))
     _lib.count_launch()
     return z
 
@@ -418,7 +421,7 @@ _LIB.impl("bn_act_fwd", _bn_act_fwd_cuda, "CUDA")
 
 
 @torch.library.register_fake("pygho_b200::bn_act_fwd")
-def _bn_act_fwd_fake(y, mean, rstd, gamma, beta, act):
+def _bn_act_fwd_fake(y, mean, rstd, gamma, beta, act, residual=None):
     return torch.empty_like(y)
 
 
@@ -756,10 +759,11 @@ class LinearBNAct(torch.autograd.Function):
     Saves x and the Linear output y; the normalised tensor is recomputed in the backward."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, momentum, eps, act):
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, momentum, eps, act,
+                residual=None):
         y = torch.nn.functional.linear(x, weight, bias)
         mean, rstd = _ops.bn_stats(y, eps, momentum, running_mean, running_var)
-        z = _ops.bn_act_fwd(y, mean, rstd, gamma, beta, act)
+        z = _ops.bn_act_fwd(y, mean, rstd, gamma, beta, act, residual)   # + residual if given
         ctx.save_for_backward(x, weight, y, mean, rstd, gamma, beta)
         ctx.act = act
         ctx.has_bias = bias is not None
@@ -776,4 +780,5 @@ class LinearBNAct(torch.autograd.Function):
         dw = _tall_skinny_tn(dy, x) if need[1] else None
         return (dx, dw, dbias if (ctx.has_bias and need[2]) else None,
                 dgamma if (gamma is not None and need[3]) else None,
-                dbeta if (beta is not None and need[4]) else None, None, None, None, None, None)
+                dbeta if (beta is not None and need[4]) else None, None, None, None, None, None,
+                dz if (len(need) > 10 and need[10]) else None)   # residual: gradient passes through
