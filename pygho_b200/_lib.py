@@ -116,7 +116,14 @@ def ptr(t: Optional[torch.Tensor]):
 
 
 def stream_ptr(device: torch.device):
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw cudaStream_t of torch's current stream on ``device`` (thread-local, follows
+    ``torch.cuda.stream(...)`` contexts and graph capture).  The raw getter is ~10x cheaper
+    than building a ``torch.cuda.Stream`` object (0.9 ms per training step, profiles/
+    host_profile.py)."""
+    idx = device.index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
 
 
 def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
