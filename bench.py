@@ -224,13 +224,38 @@ def roofline_spspmm(dd_list, hidden, device, peaks):
     iters = 5 * nsets
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        xv, av = sets[i % nsets]
-        ops.seg_gmr(xv, g.first, None, av, g.second, g.rowptr, nX, 0)
-    e1.record()
-    torch.cuda.synchronize(device)
-    us = e0.elapsed_time(e1) * 1e3 / iters
+
+    def launches():
+        for i in range(iters):
+            xv, av = sets[i % nsets]
+            ops.seg_gmr(xv, g.first, None, av, g.second, g.rowptr, nX, 0)
+
+    # the `iters` launches are captured into one CUDA graph and replayed, so the events bracket
+    # back-to-back kernel executions without Python / launch gaps (eager fallback if capture fails)
+    timing = "cuda graph replay of the launches"
+    try:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            launches()
+        graph.replay()
+        torch.cuda.synchronize(device)
+        best = float("inf")
+        for _ in range(3):
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize(device)
+            best = min(best, e0.elapsed_time(e1))
+        us = best * 1e3 / iters
+        del graph
+    except Exception:  # noqa: BLE001
+        torch.cuda.synchronize(device)
+        timing = "eager launches"
+        e0.record()
+        launches()
+        e1.record()
+        torch.cuda.synchronize(device)
+        us = e0.elapsed_time(e1) * 1e3 / iters
     achieved = alg_bytes / (us * 1e-6) / 1e9
     peak = peaks.get("hbm_gbs")
     traffic = None
@@ -244,7 +269,7 @@ def roofline_spspmm(dd_list, hidden, device, peaks):
             else "fallback 6650 GB/s (B200_PROFILING.md)",
             "frac": achieved / (peak if peak else 6650.0), "traffic": traffic,
             "us_per_launch": us, "algorithmic_bytes": alg_bytes,
-            "rows": nX, "triples": T, "operand_sets": nsets, "l2_bytes": l2}
+            "rows": nX, "triples": T, "operand_sets": nsets, "l2_bytes": l2, "timing": timing}
 
 
 def run_b200(args):

@@ -268,6 +268,17 @@ int pgh_graph_dist_u8(const int64_t* edge_src, const int64_t* edge_dst, const in
 int pgh_khop_emit(const uint8_t* D, const int64_t* node_ptr, const int64_t* sq_ptr,
                   const int64_t* node_graph, const int64_t* rowptr, int64_t n_nodes,
                   int64_t n_tuples, int64_t* tupleid, int64_t* feat, void* stream);
+/* I2Sampler (hodata/SpTupleSampler.py:129-174) for a whole batch: for every directed edge
+ * e = (i, j) the nodes k within `hop` of i or of j; tupleid (3, T) = (i, j, k) in edge order then
+ * k order, feat (T, 2) = (min(dist(i,k), hop+1), min(dist(j,k), hop+1)).  D from
+ * pgh_graph_dist_u8 with cutoff >= hop + 1.  count -> scan (caller) -> emit.                  */
+int pgh_i2_count(const uint8_t* D, const int64_t* edge_src, const int64_t* edge_dst,
+                 const int64_t* node_ptr, const int64_t* sq_ptr, const int64_t* node_graph,
+                 int64_t n_edges, int hop, int32_t* cnt, void* stream);
+int pgh_i2_emit(const uint8_t* D, const int64_t* edge_src, const int64_t* edge_dst,
+                const int64_t* node_ptr, const int64_t* sq_ptr, const int64_t* node_graph,
+                const int64_t* rowptr, int64_t n_edges, int64_t n_tuples, int hop,
+                int64_t* tupleid, int64_t* feat, void* stream);
 /* Dense shortest-path-distance features padded to (B, nmax, nmax): out = min(dist, clamp)
  * (unreachable -> clamp), mask = (i < n_g) & (j < n_g), pads hold `fill`.  spdsampler
  * (MaTupleSampler.py:11-31) + to_dense_tuplefeat (MaData.py:152-212) in one pass.

@@ -70,6 +70,25 @@ def khop_sampler_batch(edge_index: np.ndarray, node_ptr: np.ndarray,
     return np.concatenate(tids, axis=1), np.concatenate(feats)
 
 
+def i2_sampler(edge_index: np.ndarray, num_nodes: int, hop: int) -> Tuple[np.ndarray, np.ndarray]:
+    """I2Sampler (SpTupleSampler.py:129-174) of ONE graph: for every directed edge (i, j), in
+    edge order, the sorted union of the ``hop``-neighbourhoods of i and j (``k_hop_subgraph``
+    with the node pair as roots, :153-157) and the two shortest-path distances of every member
+    (:164-167, undirected ``shortest_path``).  tupleid (3, T), tuplefeat (T, 2)."""
+    full = spd_matrix(edge_index, num_nodes, num_nodes + 1)
+    ids, feats = [], []
+    for e in range(edge_index.shape[1]):
+        i, j = int(edge_index[0, e]), int(edge_index[1, e])
+        si, _ = k_hop_subgraph(i, hop, edge_index, num_nodes)
+        sj, _ = k_hop_subgraph(j, hop, edge_index, num_nodes)
+        subset = np.union1d(si, sj)
+        ids.append(np.stack([np.full_like(subset, i), np.full_like(subset, j), subset]))
+        feats.append(np.stack([full[i, subset], full[j, subset]], axis=1))
+    if not ids:
+        return np.zeros((3, 0), dtype=np.int64), np.zeros((0, 2), dtype=np.int64)
+    return np.concatenate(ids, axis=1), np.concatenate(feats)
+
+
 def spd_matrix(edge_index: np.ndarray, num_nodes: int, hop: int) -> np.ndarray:
     """spdsampler (MaTupleSampler.py:11-31): all-pairs unweighted shortest paths of the
     UNDIRECTED graph (``directed=False``), clamped to ``hop + 1``; (n, n).  Unreachable pairs

@@ -66,6 +66,8 @@ SIGNATURES = {
     "pgh_bn_act_bwd_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "pgh_graph_dist_u8": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _p, _p, _p]),
     "pgh_khop_emit": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p]),
+    "pgh_i2_count": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _p, _p]),
+    "pgh_i2_emit": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _p, _p, _p]),
     "pgh_spd_dense_i64": (_i, [_p, _p, _p, _i64, _i64, _i, _i64, _p, _p, _p]),
     "pgh_pad_rows": (_i, [_p, _p, _i64, _i64, _i64, _i, _u64, _p, _p, _p]),
     "pgh_dense_adj": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _u64, _p, _p, _p]),

@@ -127,6 +127,53 @@ spd_dense_kernel(const unsigned char* __restrict__ D, const long long* __restric
   mask[idx] = ok ? 1 : 0;
 }
 
+
+// I2Sampler (hodata/SpTupleSampler.py:129-174): for every directed edge (i, j) the nodes within
+// `hop` of i or of j, with both distances as feature.  One warp per edge; count pass and emit
+// pass share the row walk.  D must hold distances up to hop + 1 (255 beyond).
+template <bool EMIT>
+__global__ void __launch_bounds__(256)
+i2_edge_kernel(const unsigned char* __restrict__ D, const long long* __restrict__ edge_src,
+               const long long* __restrict__ edge_dst, const long long* __restrict__ node_ptr,
+               const long long* __restrict__ sq_ptr, const long long* __restrict__ node_graph,
+               long long n_edges, int hop, int* __restrict__ cnt,
+               const long long* __restrict__ rowptr, long long n_tuples,
+               long long* __restrict__ tupleid, long long* __restrict__ feat) {
+  const int lane = threadIdx.x & 31;
+  const long long e = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= n_edges) return;
+  const long long i = edge_src[e], j = edge_dst[e];
+  const long long g = node_graph[i];
+  const long long n0 = node_ptr[g];
+  const int n = (int)(node_ptr[g + 1] - n0);
+  const unsigned char* __restrict__ ri = D + sq_ptr[g] + (size_t)(i - n0) * n;
+  const unsigned char* __restrict__ rj = D + sq_ptr[g] + (size_t)(j - n0) * n;
+  long long pos = EMIT ? rowptr[e] : 0;
+  int total = 0;
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int k = k0 + lane;
+    const int di = k < n ? (int)ri[k] : 255, dj = k < n ? (int)rj[k] : 255;
+    const bool keep = di <= hop || dj <= hop;
+    const unsigned int bal = __ballot_sync(kFullMask, keep);
+    if (EMIT) {
+      if (keep) {
+        const long long p = pos + __popc(bal & ((1u << lane) - 1u));
+        if (p < n_tuples) {
+          tupleid[p] = i;
+          tupleid[n_tuples + p] = j;
+          tupleid[2 * n_tuples + p] = n0 + k;
+          feat[2 * p] = di < hop + 1 ? di : hop + 1;
+          feat[2 * p + 1] = dj < hop + 1 ? dj : hop + 1;
+        }
+      }
+      pos += __popc(bal);
+    } else {
+      total += __popc(bal);
+    }
+  }
+  if (!EMIT && lane == 0) cnt[e] = total;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 pad_rows_kernel(const T* __restrict__ src, const long long* __restrict__ ptr, long long total,
@@ -207,6 +254,39 @@ extern "C" int pgh_khop_emit(const uint8_t* D, const int64_t* node_ptr, const in
       D, (const long long*)node_ptr, (const long long*)sq_ptr, (const long long*)node_graph,
       (const long long*)rowptr, n_nodes, n_tuples, (long long*)tupleid, (long long*)feat);
   return check_launch("khop_emit");
+}
+
+
+extern "C" int pgh_i2_count(const uint8_t* D, const int64_t* edge_src, const int64_t* edge_dst,
+                            const int64_t* node_ptr, const int64_t* sq_ptr,
+                            const int64_t* node_graph, int64_t n_edges, int hop, int32_t* cnt,
+                            void* stream) {
+  if (n_edges == 0) return 0;
+  if (!D || !edge_src || !edge_dst || !node_ptr || !sq_ptr || !node_graph || !cnt)
+    return arg_error("i2_count: null pointer");
+  if (hop < 0 || hop > 253) return arg_error("i2_count: hop must be in [0, 253]");
+  i2_edge_kernel<false><<<blocks_for(n_edges, 8), 256, 0, as_stream(stream)>>>(
+      D, (const long long*)edge_src, (const long long*)edge_dst, (const long long*)node_ptr,
+      (const long long*)sq_ptr, (const long long*)node_graph, n_edges, hop, cnt, nullptr, 0,
+      nullptr, nullptr);
+  return check_launch("i2_count");
+}
+
+extern "C" int pgh_i2_emit(const uint8_t* D, const int64_t* edge_src, const int64_t* edge_dst,
+                           const int64_t* node_ptr, const int64_t* sq_ptr,
+                           const int64_t* node_graph, const int64_t* rowptr, int64_t n_edges,
+                           int64_t n_tuples, int hop, int64_t* tupleid, int64_t* feat,
+                           void* stream) {
+  if (n_edges == 0 || n_tuples == 0) return 0;
+  if (!D || !edge_src || !edge_dst || !node_ptr || !sq_ptr || !node_graph || !rowptr || !tupleid ||
+      !feat)
+    return arg_error("i2_emit: null pointer");
+  if (hop < 0 || hop > 253) return arg_error("i2_emit: hop must be in [0, 253]");
+  i2_edge_kernel<true><<<blocks_for(n_edges, 8), 256, 0, as_stream(stream)>>>(
+      D, (const long long*)edge_src, (const long long*)edge_dst, (const long long*)node_ptr,
+      (const long long*)sq_ptr, (const long long*)node_graph, n_edges, hop, nullptr,
+      (const long long*)rowptr, n_tuples, (long long*)tupleid, (long long*)feat);
+  return check_launch("i2_emit");
 }
 
 extern "C" int pgh_spd_dense_i64(const uint8_t* D, const int64_t* node_ptr, const int64_t* sq_ptr,

@@ -94,3 +94,32 @@ def KhopSampler(edge_index: LongTensor, node_ptr: PtrLike, hop: int = 2,
              T, ptr(tupleid), ptr(feat), stream_ptr(dev))
         _lib.count_launch()
     return SparseTensor(tupleid, feat, (N, N), is_coalesced=True)
+
+
+def I2Sampler(edge_index: LongTensor, node_ptr: PtrLike, hop: int = 3,
+              grouped: bool = True) -> SparseTensor:
+    """I2-GNN tuples of a batch: for every directed edge ``(i, j)`` the nodes ``k`` within
+    ``hop`` of ``i`` or of ``j``; ``X[i, j, k] = (dist(i, k), dist(j, k))`` clamped to
+    ``hop + 1``.  Tuples follow the edge order, then ``k``: coalesced when ``edge_index`` is
+    sorted by (row, col) (any coalesced batch).  Batch-level counterpart of the reference
+    ``I2Sampler(data, hop)`` (SpTupleSampler.py:129-174) for undirected graphs."""
+    dev = _lib.require_cuda(edge_index)
+    D, sq_ptr, _cnt, node_ptr, node_graph, _nmax = graph_distances(edge_index, node_ptr, hop + 1,
+                                                                   grouped)
+    N, E = node_graph.numel(), edge_index.shape[1]
+    src, dst = edge_index[0].contiguous(), edge_index[1].contiguous()
+    cnt = torch.zeros((E,), dtype=torch.int32, device=dev)
+    if E:
+        call("pgh_i2_count", ptr(D), ptr(src), ptr(dst), ptr(node_ptr), ptr(sq_ptr),
+             ptr(node_graph), E, int(hop), ptr(cnt), stream_ptr(dev))
+        _lib.count_launch()
+    rowptr = torch.zeros((E + 1,), dtype=torch.int64, device=dev)
+    torch.cumsum(cnt, 0, out=rowptr[1:])
+    T = int(rowptr[-1]) if E else 0
+    tupleid = torch.empty((3, T), dtype=torch.int64, device=dev)
+    feat = torch.empty((T, 2), dtype=torch.int64, device=dev)
+    if T:
+        call("pgh_i2_emit", ptr(D), ptr(src), ptr(dst), ptr(node_ptr), ptr(sq_ptr),
+             ptr(node_graph), ptr(rowptr), E, T, int(hop), ptr(tupleid), ptr(feat), stream_ptr(dev))
+        _lib.count_launch()
+    return SparseTensor(tupleid, feat, (N, N, N, 2), is_coalesced=True)

@@ -108,6 +108,24 @@ two = np.array([[0, 1, 1, 2, 3, 4], [1, 0, 2, 1, 4, 3]])          # components {
 feat, shape = RMaSamp.spdsampler(_Data(edge_index=torch.from_numpy(two), num_nodes=6), hop=2)
 out["spd_disc_edge_index"], out["spd_disc"] = two, feat.numpy().reshape(shape)
 
+# ---- I2Sampler content (SpTupleSampler.py:129-174): the reference's own k_hop_subgraph on every
+# node PAIR of an edge + the same scipy shortest_path call it makes; the PyG collate is left out
+for gi, g in enumerate(graphs[:3]):
+    ei = torch.from_numpy(g.edge_index)
+    dist_matrix = torch.from_numpy(ssp.csgraph.shortest_path(
+        _to_scipy(ei, g.num_nodes), directed=False, unweighted=True,
+        return_predecessors=False)).to(torch.long)
+    subs, feats, lens = [], [], []
+    for e in range(ei.shape[1]):
+        pair = ei[:, e]
+        subset, _, _, _, _ = RSamp.k_hop_subgraph(pair, 3, ei, relabel_nodes=True,
+                                                  num_nodes=g.num_nodes)
+        subs.append(subset.numpy()); lens.append(subset.shape[0])
+        feats.append(torch.stack((dist_matrix[pair[0].item()][subset],
+                                  dist_matrix[pair[1].item()][subset]), dim=-1).numpy())
+    out[f"i2_g{gi}_subset"], out[f"i2_g{gi}_len"] = np.concatenate(subs), np.array(lens)
+    out[f"i2_g{gi}_feat"] = np.concatenate(feats)
+
 # ---- to_dense_x / to_dense_adj / to_dense_tuplefeat
 gen = torch.Generator().manual_seed(3)
 sizes = torch.tensor([4, 1, 6, 3])

@@ -93,6 +93,24 @@ def test_khop_full_size_properties(dev):
     assert int((X.values == 1).sum()) == hb.edge_index.shape[1]     # exactly the edges
 
 
+def test_i2_sampler_matches_oracle_and_golden(dev, golden):
+    from pygho_b200.hodata.SpTupleSampler import I2Sampler
+    from pygho_b200.hodata.synthetic import make_batch
+    g = golden("hodata")
+    for gi in range(3):
+        n = int(g[f"g{gi}_n"])
+        X = I2Sampler(_t(g[f"g{gi}_edge_index"], dev), [0, n], 3)
+        assert np.array_equal(X.indices[2].cpu().numpy(), g[f"i2_g{gi}_subset"])
+        assert np.array_equal(X.values.cpu().numpy(), g[f"i2_g{gi}_feat"])
+    hb = make_batch(12, seed=8, hop=2, tuples="i2")
+    X = I2Sampler(_t(hb.edge_index, dev), hb.node_ptr, 2)
+    assert np.array_equal(X.indices.cpu().numpy(), hb.tupleid)
+    assert np.array_equal(X.values.cpu().numpy(), hb.tuplefeat)
+    assert X.shape[:3] == (hb.num_nodes,) * 3 and X.sparse_dim == 3
+    key = (X.indices[0] * hb.num_nodes + X.indices[1]) * hb.num_nodes + X.indices[2]
+    assert bool((key[1:] > key[:-1]).all())             # coalesced: strictly increasing
+
+
 def test_spdsampler_matches_reference_golden(dev, golden):
     from pygho_b200.hodata.MaTupleSampler import spdsampler
     g = golden("hodata")

@@ -51,6 +51,21 @@ def test_spd_golden(golden):
     assert (~reach).sum() == 6 * 6 - (9 + 4 + 1)
 
 
+def test_i2_sampler_golden(golden):
+    g = golden("hodata")
+    for gi in range(3):
+        ei, n = g[f"g{gi}_edge_index"], int(g[f"g{gi}_n"])
+        tid, feat = H.i2_sampler(ei, n, 3)
+        assert np.array_equal(tid[2], g[f"i2_g{gi}_subset"])
+        assert np.array_equal(feat, g[f"i2_g{gi}_feat"])
+        assert np.array_equal(tid[0], np.repeat(ei[0], g[f"i2_g{gi}_len"]))
+        assert np.array_equal(tid[1], np.repeat(ei[1], g[f"i2_g{gi}_len"]))
+        assert feat.max() <= 4                          # connected pairs: never beyond hop + 1
+        from pygho_b200.hodata.synthetic import i2_tuples
+        tid2, feat2 = i2_tuples(n, ei, 3)               # the generator's host sampler
+        assert np.array_equal(tid, tid2) and np.array_equal(feat, feat2)
+
+
 def test_dense_layout_golden(golden):
     g = golden("hodata")
     data, mask = H.to_dense_x(g["dx_x"], g["dx_ptr"])
