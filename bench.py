@@ -38,6 +38,10 @@ import time
 os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF",
                       "expandable_segments:True,roundup_power2_divisions:8")
 
+# NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO) to stdout by default: keep stdout
+# for the one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -419,7 +423,9 @@ def run_b200(args):
             e2e_step(i)
         read_pending()                                   # every timed step's loss is read
 
-    e2e_steps(max(3, len(hbs)))
+    # two full cycles over the host batches: every allocation size of both streams has been
+    # seen (a growth of an expandable segment inside the timed region costs 10-100 ms)
+    e2e_steps(max(args.warmup, 2 * len(hbs) + 1))
     if os.environ.get("PYGHO_B200_BENCH_DEBUG"):
         for i in range(12):
             torch.cuda.synchronize(device)
@@ -429,6 +435,9 @@ def run_b200(args):
             print(f"[debug] e2e step {i}: {1e3 * (time.perf_counter() - t0):.2f} ms", file=sys.stderr)
         read_pending()
     losses.clear()
+    import gc
+    gc.collect()
+    gc.freeze()        # long-lived objects out of the collector's way: no multi-ms gen-2 pauses
     e2e_ms, _ = timed(e2e_step, args.steps, finish=read_pending)
     assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: every step's loss is read"
     e2e_value = args.batch * world / (e2e_ms / args.steps * 1e-3)
