@@ -396,26 +396,21 @@ def run_b200(args):
     # then issues the prefetch of batch i+1 -- the GPU never idles while the host blocks.
     # That wait is also the synchronisation DevicePrefetcher.advance() asks for (batch i-1
     # is fully consumed before its buffers are recycled).
-    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-    loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+    from pygho_b200.hodata.device import DeferredScalar
+    reader = DeferredScalar()
     losses = []
-    pending = [None]
 
     def read_pending():
-        if pending[0] is not None:
-            slot = pending[0]
-            loss_evt[slot].synchronize()
-            losses.append(float(loss_host[slot]))            # D2H read of the result
-            pending[0] = None
+        v = reader.flush()
+        if v is not None:
+            losses.append(v)                             # D2H read of the result
 
     def e2e_step(i):
         dd = feeder.get()
         loss = train_step(dd)
-        slot = i & 1
-        loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
-        loss_evt[slot].record()
-        read_pending()                                   # loss of the step before this one
-        pending[0] = slot
+        prev = reader.push(loss)                         # loss of the step before this one
+        if prev is not None:
+            losses.append(prev)
         feeder.advance()                                 # next batch's H2D + plans, side stream
 
     def e2e_steps(n):
@@ -438,7 +433,19 @@ def run_b200(args):
     import gc
     gc.collect()
     gc.freeze()        # long-lived objects out of the collector's way: no multi-ms gen-2 pauses
-    e2e_ms, _ = timed(e2e_step, args.steps, finish=read_pending)
+    trace = [] if os.environ.get("PYGHO_B200_BENCH_TRACE") else None
+    timed_step = e2e_step
+    if trace is not None:
+        def timed_step(i):
+            e2e_step(i)
+            trace.append(time.perf_counter())
+    mem0 = torch.cuda.memory_stats(device)
+    e2e_ms, _ = timed(timed_step, args.steps, finish=read_pending)
+    if trace is not None:
+        mem1 = torch.cuda.memory_stats(device)
+        gaps = [round(1e3 * (b - a), 2) for a, b in zip(trace[:-1], trace[1:])]
+        grew = {k: mem1[k] - mem0[k] for k in ("num_alloc_retries", "num_device_alloc", "num_device_free")}
+        print(f"[trace] e2e host ms between steps: {gaps}; allocator: {grew}", file=sys.stderr)
     assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: every step's loss is read"
     e2e_value = args.batch * world / (e2e_ms / args.steps * 1e-3)
     feeder.close()                                       # no stray side-stream work below

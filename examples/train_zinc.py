@@ -17,7 +17,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from examples.zinc_models import SpModel  # noqa: E402
 from pygho_b200.dist import FlatGradBucket  # noqa: E402
 from pygho_b200.graph import StepGraph  # noqa: E402
-from pygho_b200.hodata.device import DevicePrefetcher, attach_host_plans, prefetch_plans, sp_datadict  # noqa: E402
+from pygho_b200.hodata.device import (DeferredScalar, DevicePrefetcher, attach_host_plans,  # noqa: E402
+                                      prefetch_plans, sp_datadict)
 from pygho_b200.hodata.synthetic import make_batch  # noqa: E402
 from pygho_b200.honn.SpOperator import parse_precomputekey  # noqa: E402
 
@@ -72,16 +73,15 @@ def main():
                 print(f"step {i:4d} loss {float(loss):.4f}")
     else:
         feeder = DevicePrefetcher(hbs, dev, keys, embeddings=tables)
-        prev = None
+        reader = DeferredScalar()
         for i in range(args.steps):
             dd = feeder.get()
             loss = train_step(dd)
+            prev = reader.push(loss)            # loss of step i-1; waits for that step only
             if prev is not None and (i - 1) % 10 == 0:
-                print(f"step {i - 1:4d} loss {float(prev):.4f}")     # read one step late
-            elif prev is not None:
-                prev.cpu()                                           # fence for the prefetcher
-            prev = loss
-            feeder.advance()
+                print(f"step {i - 1:4d} loss {prev:.4f}")
+            feeder.advance()                    # H2D + plans of the next batch, side stream
+        print(f"step {args.steps - 1:4d} loss {reader.flush():.4f}")
         feeder.close()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0

@@ -8,6 +8,7 @@ every batch) or it is built on the device by the fused plan kernels."""
 from __future__ import annotations
 
 import queue
+import sys
 import threading
 from typing import Dict, Iterable, Optional
 
@@ -124,6 +125,12 @@ class DevicePrefetcher:
         self._done = threading.Event()
         self._jobs: Optional[queue.Queue] = None
         if threaded:
+            # The main thread releases the GIL around every kernel launch (ctypes, torch ops);
+            # with CPython's default 5 ms switch interval each of those hand-overs can park it
+            # behind the worker's Python code for milliseconds (convoy effect: e2e steps of
+            # 26 ms instead of 14 ms were measured).  A 50 us interval keeps hand-overs short.
+            if sys.getswitchinterval() > 1e-4:
+                sys.setswitchinterval(5e-5)
             self._jobs = queue.Queue()
             self._worker = threading.Thread(target=self._run, name="pygho-prefetch", daemon=True)
             self._worker.start()
@@ -186,6 +193,38 @@ class DevicePrefetcher:
             self._jobs.put(None)
             self._worker.join(timeout=5)
             self._jobs = None
+
+
+class DeferredScalar:
+    """Read a device scalar (the loss) ONE step late: ``push(t)`` copies ``t`` to pinned host
+    memory behind an event and returns the value pushed the call before, waiting only for
+    that older event -- the host never blocks on the step it has just launched.  The wait is
+    also the fence :meth:`DevicePrefetcher.advance` asks for."""
+
+    def __init__(self):
+        self._buf = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._evt = [torch.cuda.Event(), torch.cuda.Event()]
+        self._n = 0
+        self._unread: Optional[int] = None
+
+    def _read(self, slot: Optional[int]) -> Optional[float]:
+        if slot is None:
+            return None
+        self._evt[slot].synchronize()
+        return float(self._buf[slot])
+
+    def push(self, value: torch.Tensor) -> Optional[float]:
+        slot = self._n & 1
+        self._n += 1
+        self._buf[slot:slot + 1].copy_(value.detach().reshape(1).float(), non_blocking=True)
+        self._evt[slot].record()
+        prev, self._unread = self._unread, slot
+        return self._read(prev)
+
+    def flush(self) -> Optional[float]:
+        """Value of the last ``push`` (None if it has been returned already)."""
+        prev, self._unread = self._unread, None
+        return self._read(prev)
 
 
 def attach_host_plans(hb: HostBatch, datadict: dict, keys: Iterable[str]) -> None:
