@@ -1,0 +1,46 @@
+"""bench.py contract checks that need no GPU: the reference arm (CPU oracle port) prints ONE
+JSON line with the agreed keys, non-zero ranks stay silent, and the own arm refuses to run
+without a CUDA device instead of falling back to anything."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SMALL = ["--steps", "2", "--warmup", "1", "--ref-batch", "8", "--layers", "1", "--hidden", "16"]
+
+
+def run(args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, cwd=ROOT,
+                          env=e, capture_output=True, text=True, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = run(["--impl", "reference", "--gpus", "1"] + SMALL)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "graphs/s" and d["higher_is_better"] is True
+    assert d["metric"] == "sswl_plus_zinc_shape_train_graphs_per_s" and d["value"] > 0
+    assert d["vs_baseline"] is None and d["scaling"] == "weak" and d["data"] == "synthetic"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    r = run(["--impl", "reference", "--gpus", "2"] + SMALL, {"RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_own_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return
+    r = run(["--gpus", "1", "--steps", "1", "--warmup", "1"])
+    assert r.returncode != 0
+    assert "no CPU path" in (r.stderr + r.stdout)
