@@ -379,3 +379,39 @@ def ma_diag(data: np.ndarray, mask: np.ndarray, dims: Sequence[int]):
     dd = np.moveaxis(np.diagonal(data, axis1=d0, axis2=d1), -1, d0)
     mm = np.moveaxis(np.diagonal(mask, axis1=d0, axis2=d1), -1, d0)
     return dd, mm
+
+
+def spmamm(a_ind: np.ndarray, a_val: Optional[np.ndarray], a_shape: Sequence[int], dim1: int,
+           b_data: np.ndarray, b_mask: np.ndarray, dim2: int, out_mask: Optional[np.ndarray],
+           aggr: str = "sum"):
+    """backend/Spmamm.py:12-67 with its intended semantics: ``dim1`` of the sparse (b, n, m)
+    operand is contracted with masked dim ``dim2`` of B; masked-out positions of B do not
+    contribute (the fill of :60 applied), A's values broadcast over B's other masked dims,
+    empty reductions are 0 (filterinf, :65-66), the result is zero outside ``out_mask``
+    (default B's mask).  Returns (data, mask)."""
+    md = b_mask.ndim
+    if dim1 == 1:
+        n, cidx, tidx = a_shape[2], a_ind[1], a_ind[2]          # :44-47
+    elif dim1 == 2:
+        n, cidx, tidx = a_shape[1], a_ind[2], a_ind[1]          # :48-51
+    else:
+        raise NotImplementedError
+    b = a_shape[0]
+    tb = np.moveaxis(b_data, dim2, 1)                           # :55
+    tm = np.moveaxis(b_mask, dim2, 1)                           # :56
+    others, dense = tb.shape[2:md], tb.shape[md:]
+    fill = {"sum": 0.0, "max": -np.inf, "min": np.inf}[aggr]    # :8
+    rows = tb[a_ind[0], cidx].astype(np.float64)                # (nnz, *others, *dense)
+    if a_val is not None:
+        rows = a_val.reshape((a_val.shape[0],) + (1,) * len(others) + dense) * rows   # :57-58
+    valid = tm[a_ind[0], cidx]
+    rows = np.where(valid.reshape(valid.shape + (1,) * len(dense)), rows, fill)       # :60-61
+    out = np.full((b * n,) + others + dense, fill, dtype=np.float64)
+    tar = n * a_ind[0] + tidx
+    red = {"sum": np.add, "max": np.maximum, "min": np.minimum}[aggr]
+    red.at(out, tar, rows)                                      # :62
+    out = np.where(np.isinf(out), 0.0, out)                     # :65-66
+    out = np.moveaxis(out.reshape((b, n) + others + dense), 1, dim2)
+    mask = b_mask if out_mask is None else out_mask
+    out = np.where(mask.reshape(mask.shape + (1,) * (out.ndim - mask.ndim)), out, 0.0)
+    return out.astype(np.float32), mask

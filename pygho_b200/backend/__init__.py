@@ -6,4 +6,5 @@ from .Spspmm import (spspmm, spspmpnn, spspmm_ind, filterind, spsphadamard, spsp
                      ptr2batch, deg2batch)
 from .Spmm import spmm
 from .Mamamm import mamamm
+from .Spmamm import spmamm
 from .utils import torch_scatter_reduce

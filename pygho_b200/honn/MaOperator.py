@@ -15,10 +15,7 @@ from ..backend.MaTensor import MaskedTensor
 from ..backend.SpTensor import SparseTensor
 
 
-def _sd_unavailable(*_a, **_k):
-    raise NotImplementedError(
-        "spmamm (sparse adjacency x dense tuples, mode 'SD') is outside the hot path built "
-        "here (SURVEY.md section 8f rank 4; the reference's SD SSWL path is itself broken)")
+from ..backend.Spmamm import spmamm
 
 
 class OpNodeMessagePassing(Module):
@@ -33,11 +30,15 @@ class OpNodeMessagePassing(Module):
 
 
 class OpSpNodeMessagePassing(Module):
+    """``X' = A X`` with a sparse batched adjacency A (b, n, n) and X (b, n, d) masked."""
+
     def __init__(self, aggr: str = "sum") -> None:
         super().__init__()
         self.aggr = aggr
 
-    forward = _sd_unavailable
+    def forward(self, A: SparseTensor, X: MaskedTensor, tarX: MaskedTensor) -> MaskedTensor:
+        assert A.sparse_dim == 3, "A should be bxnxn adjacency matrix "
+        return spmamm(A, 2, X, 1, tarX.mask, self.aggr)
 
 
 class OpMessagePassing(Module):
@@ -91,20 +92,33 @@ class OpSpMessagePassing(Module):
         super().__init__()
         self.dim1, self.dim2, self.aggr = dim1, dim2, aggr
 
-    forward = _sd_unavailable
+    def forward(self, A: SparseTensor, X: MaskedTensor, tarX: MaskedTensor) -> MaskedTensor:
+        assert A.sparse_dim == 3, "A should be bxnxn adjacency matrix "
+        return spmamm(A, self.dim1, X, self.dim2, tarX.mask, self.aggr)
 
 
-class OpSpMessagePassingOnSubg2D(OpSpMessagePassing):
+class _SpVariant(OpSpMessagePassing):
+    _NDIM, _MSG = 3, "X should be bxnxn 2D representation "
+
+    def forward(self, A: SparseTensor, X: MaskedTensor, datadict: Dict,
+                tarX: MaskedTensor) -> MaskedTensor:
+        assert X.masked_dim == self._NDIM, self._MSG
+        return OpSpMessagePassing.forward(self, A, X, tarX)
+
+
+class OpSpMessagePassingOnSubg2D(_SpVariant):
     def __init__(self, aggr: str = "sum") -> None:
         super().__init__(1, 2, aggr)
 
 
-class OpSpMessagePassingOnSubg3D(OpSpMessagePassing):
+class OpSpMessagePassingOnSubg3D(_SpVariant):
+    _NDIM, _MSG = 4, "X should be bxnxnxn 3D representation "
+
     def __init__(self, aggr: str = "sum") -> None:
         super().__init__(1, 3, aggr)
 
 
-class OpSpMessagePassingCrossSubg2D(OpSpMessagePassing):
+class OpSpMessagePassingCrossSubg2D(_SpVariant):
     def __init__(self, aggr: str = "sum") -> None:
         super().__init__(1, 1, aggr)
 

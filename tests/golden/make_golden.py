@@ -302,6 +302,42 @@ def g_conv():
     save("conv", **out)
 
 
+def golden_spmamm():
+    """Reference spmamm (backend/Spmamm.py) on the inputs it can run: its masked_fill call (:60)
+    only broadcasts when there are NO dense dims (mask (nnz, k) against mult (nnz, k)), and its
+    result is dropped, which is invisible when B's pads already hold the neutral value of the
+    aggregation.  Scalar features, one 'other' masked dim."""
+    from pygho.backend.Spmamm import spmamm as rspmamm
+    gen = torch.Generator().manual_seed(11)
+    b, n, k = 3, 7, 5
+    sizes = torch.tensor([7, 4, 6])
+    adj = (torch.rand((b, n, n), generator=gen) < 0.35)
+    valid = torch.arange(n)[None, :] < sizes[:, None]
+    adj &= valid[:, :, None] & valid[:, None, :]
+    ind = adj.nonzero().t().contiguous()
+    aval = torch.rand((ind.shape[1],), generator=gen) + 0.5            # positive: -inf stays -inf
+    out = {"ind": ind, "aval": aval, "shape": torch.tensor([b, n, n])}
+    for dim2, tag in ((1, "d1"), (2, "d2")):
+        bmask = (valid[:, :, None] & (torch.arange(k)[None, None, :] < 4)) if dim2 == 1 else \
+            ((torch.arange(k)[None, :, None] < 4) & valid[:, None, :]).expand(b, k, n)
+        bmask = bmask.contiguous()
+        data = torch.randn(tuple(bmask.shape), generator=gen)
+        out[f"{tag}_data"], out[f"{tag}_mask"] = data * bmask, bmask
+        for aggr, pad in (("sum", 0.0), ("max", float("-inf"))):
+            filled = torch.where(bmask, data, torch.full_like(data, pad))
+            for dim1 in (1, 2):
+                B = MaskedTensor(filled, bmask, pad, True)
+                r = rspmamm(SparseTensor(ind, aval, (b, n, n), True), dim1, B, dim2, None, aggr)
+                rd = torch.where(r.mask, r.data, torch.zeros_like(r.data))
+                out[f"{tag}_{aggr}_dim{dim1}"] = rd
+    save("spmamm", **out)
+
+
+if __name__ == "__main__" and "spmamm" in sys.argv[1:]:
+    golden_spmamm()
+    sys.exit(0)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     g_hash()

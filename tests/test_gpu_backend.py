@@ -683,3 +683,58 @@ def test_embedding_matches_torch(n, V, D):
     assert torch.equal(emb.weight.grad, g1)                               # deterministic
     idx2 = idx.reshape(-1, 1)[: n - n % 1].reshape(n)                     # other tensor object
     assert torch.equal(emb(idx2.reshape(n, 1)).squeeze(1), out_ref)
+
+
+def test_spmamm_matches_reference_golden_and_oracle(B, golden):
+    """SD mode: sparse batched adjacency x masked dense tuples (backend/Spmamm.py)."""
+    g = golden("spmamm")
+    ind, shape = T(g["ind"]), tuple(int(x) for x in g["shape"])
+    for tag, dim2 in (("d1", 1), ("d2", 2)):
+        Bm = B.MaskedTensor(T(g[f"{tag}_data"]), T(g[f"{tag}_mask"]), 0.0, True)
+        for aggr in ("sum", "max"):
+            for dim1 in (1, 2):
+                A = B.SparseTensor(ind, T(g["aval"]), shape, True)
+                out = B.spmamm(A, dim1, Bm, dim2, None, aggr)
+                close(out.data, g[f"{tag}_{aggr}_dim{dim1}"], 1e-6)
+                assert torch.equal(out.mask, Bm.mask)
+    # dense features (the reference cannot run these, Q7): oracle, values None, custom mask, min
+    rng = np.random.default_rng(2)
+    b, n, k, d = 3, 7, 5, 8
+    aval = rng.standard_normal((g["ind"].shape[1], d)).astype(np.float32)
+    bmask = g["d1_mask"]
+    data = rng.standard_normal(bmask.shape + (d,)).astype(np.float32) * bmask[..., None]
+    omask = bmask & (rng.random(bmask.shape) < 0.8)
+    for aggr in ("sum", "max", "min"):
+        for av in (aval, None):
+            A = B.SparseTensor(ind, None if av is None else T(av), shape + ((d,) if av is not None else ()), True)
+            out = B.spmamm(A, 2, B.MaskedTensor(T(data), T(bmask), 0.0, True), 1, T(omask), aggr)
+            want, _ = O.spmamm(g["ind"], av, shape, 2, data, bmask, 1, omask, aggr)
+            close(out.data, want, 2e-6)
+    # gradients of the sum against torch autograd on the same arithmetic
+    ar = torch.from_numpy(aval).requires_grad_(True)
+    br = torch.from_numpy(data).requires_grad_(True)
+    it = torch.from_numpy(g["ind"])
+    rows = ar.unsqueeze(1) * br[it[0], it[2]]
+    ref = torch.zeros((b * n, k, d)).index_add_(0, n * it[0] + it[1], rows).reshape(b, n, k, d)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)) * torch.from_numpy(bmask).unsqueeze(-1)
+    (ref * w).sum().backward()
+    ag, bg = torch.from_numpy(aval).to(DEV).requires_grad_(True), torch.from_numpy(data).to(DEV).requires_grad_(True)
+    out = B.spmamm(B.SparseTensor(ind, ag, shape + (d,), True), 2,
+                   B.MaskedTensor(bg, T(bmask), 0.0, True), 1, None, "sum")
+    (out.data * w.to(DEV)).sum().backward()
+    close(ag.grad, ar.grad, 2e-5)
+    close(bg.grad * T(bmask).unsqueeze(-1), br.grad * torch.from_numpy(bmask).unsqueeze(-1), 2e-5)
+    # operator level (honn/MaOperator.py:45-80, 281-372)
+    from pygho_b200.honn.MaOperator import OpSpMessagePassingOnSubg2D, OpSpNodeMessagePassing
+    X2 = B.MaskedTensor(T(data), T(bmask), 0.0, True)
+    A = B.SparseTensor(ind, T(aval), shape + (d,), True)
+    o = OpSpMessagePassingOnSubg2D("sum")(A, B.MaskedTensor(T(np.swapaxes(data, 1, 2).copy()), T(np.swapaxes(bmask, 1, 2).copy()), 0.0, True), None,
+                                          B.MaskedTensor(T(np.swapaxes(data, 1, 2).copy()), T(np.swapaxes(bmask, 1, 2).copy()), 0.0, True))
+    want, _ = O.spmamm(g["ind"], aval, shape, 1, np.swapaxes(data, 1, 2), np.swapaxes(bmask, 1, 2), 2, None, "sum")
+    close(o.data, want, 2e-6)
+    xn = data[:, :, 0]
+    mn = bmask[:, :, 0]
+    o = OpSpNodeMessagePassing("sum")(A, B.MaskedTensor(T(xn), T(mn), 0.0, True), B.MaskedTensor(T(xn), T(mn), 0.0, True))
+    want, _ = O.spmamm(g["ind"], aval, shape, 2, xn, mn, 1, None, "sum")
+    close(o.data, want, 2e-6)
+    assert X2.masked_dim == 3

@@ -262,3 +262,16 @@ def test_oracle_convs_match_reference(golden):
         close(Xv.grad.numpy(), g[f"{name}.gradX"], 2e-5)
         for k, p in conv.named_parameters():
             close(p.grad.numpy(), g[f"{name}.grad.{k}"], 5e-5)
+
+
+def test_spmamm_golden(golden):
+    """oracle spmamm against the reference's spmamm on the inputs the reference can run
+    (scalar features; see tests/golden/make_golden.py::golden_spmamm)."""
+    g = golden("spmamm")
+    for tag, dim2 in (("d1", 1), ("d2", 2)):
+        for aggr in ("sum", "max"):
+            for dim1 in (1, 2):
+                got, mask = O.spmamm(g["ind"], g["aval"], tuple(g["shape"]), dim1, g[f"{tag}_data"],
+                                     g[f"{tag}_mask"], dim2, None, aggr)
+                close(got, g[f"{tag}_{aggr}_dim{dim1}"])
+                assert np.array_equal(mask, g[f"{tag}_mask"])
