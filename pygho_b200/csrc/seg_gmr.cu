@@ -436,6 +436,150 @@ seg_gmr_lean_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
 }
 
 // ---------------------------------------------------------------------------------------
+// Software-pipelined lean variant (variants 34 / 35, opt-in; measured SLOWER: 61.2 us vs 52.2 us
+// for the default lean kernel on the SSWL key, profiles/gmr_variants.py): same split, order and
+// epilogue as seg_gmr_lean_kernel, but groups of 2 entries are double-buffered in registers
+// (the same 32 value registers as 4 entries single-buffered): the loads of group g+1 are in
+// flight while group g is reduced.  Motivation: 52 % of the lean kernel's stall samples sit on
+// the first FMA after a load group.
+template <int AGGR, bool HAS_B, bool HAS_SCALE, bool ACCUM, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+seg_gmr_lean_pipe_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
+                    const float* __restrict__ a_scale, const float* __restrict__ b_val,
+                    const int* __restrict__ d, const int* __restrict__ rowptr,
+                    long long n_rows, int dense, int lda, int ldb, int ldo, int rw,
+                    const float* __restrict__ acc_src, int lds,
+                    const float* __restrict__ copy_src, int ldcs, float* __restrict__ copy_dst,
+                    int ldcd, float* __restrict__ out) {
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr bool kLen = (AGGR != PGH_SUM);          // row lengths matter (mean, empty max/min rows)
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const long long r0 = warp * rw;
+  if (r0 >= n_rows) return;
+  const int nr = (int)min((long long)rw, n_rows - r0);
+  int rp = 0;
+  if (lane <= nr) rp = rowptr ? __ldg(rowptr + r0 + lane) : (int)(r0 + lane);
+  const int e_beg = __shfl_sync(kFull, rp, 0);
+  const int e_end = __shfl_sync(kFull, rp, nr);
+  const float init = (AGGR == PGH_MAX) ? -INFINITY : (AGGR == PGH_MIN) ? INFINITY : 0.f;
+  for (int col = lane * 4; col < dense; col += 128) {
+    const float* __restrict__ a_col = a_val + col;
+    const float* __restrict__ b_col = HAS_B ? b_val + col : nullptr;
+    float* __restrict__ o_ptr = out + (size_t)r0 * ldo + col;      // row being reduced
+    float4 acc = make_float4(init, init, init, init);
+    int cur = 0;
+    int cur_beg = e_beg;
+    int cur_end = __shfl_sync(kFull, rp, 1);
+#define PGH_FLUSH()                                                                     \
+  do {                                                                                  \
+    float4 r_ = acc;                                                                    \
+    if (kLen) {                                                                         \
+      const int len_ = cur_end - cur_beg;                                               \
+      cur_beg = cur_end;                                                                \
+      if (len_ == 0) r_ = make_float4(0.f, 0.f, 0.f, 0.f);                              \
+      else if (AGGR == PGH_MEAN) {                                                      \
+        const float n_ = (float)len_;                                                   \
+        r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);               \
+      }                                                                                 \
+    }                                                                                   \
+    if (ACCUM) {       /* out = acc_src + reduction (acc_src == out: accumulate in place) */ \
+      const float4 o_ = *reinterpret_cast<const float4*>(                               \
+          acc_src + (size_t)(r0 + cur) * lds + col);                                    \
+      r_ = make_float4(__fadd_rn(o_.x, r_.x), __fadd_rn(o_.y, r_.y),                    \
+                       __fadd_rn(o_.z, r_.z), __fadd_rn(o_.w, r_.w));                   \
+    }                                                                                   \
+    *reinterpret_cast<float4*>(o_ptr) = r_;                                             \
+    o_ptr += ldo;                                                                       \
+    if (copy_src)      /* fused row copy: copy_dst[row] = copy_src[row] (warp-uniform) */  \
+      *reinterpret_cast<float4*>(copy_dst + (size_t)(r0 + cur) * ldcd + col) =          \
+          __ldg(reinterpret_cast<const float4*>(copy_src + (size_t)(r0 + cur) * ldcs + col)); \
+    acc = make_float4(init, init, init, init);                                          \
+    ++cur;                                                                              \
+    cur_end = __shfl_sync(kFull, rp, cur + 1);      /* source lane wraps mod 32 */      \
+  } while (0)
+#define PGH_REDUCE(AV, BV, SS)                                                          \
+  do {                                                                                  \
+    float4 m_ = AV;                                                                     \
+    if (HAS_SCALE)                                                                      \
+      m_ = make_float4(__fmul_rn(m_.x, SS), __fmul_rn(m_.y, SS), __fmul_rn(m_.z, SS),   \
+                       __fmul_rn(m_.w, SS));                                            \
+    if (AGGR == PGH_MAX || AGGR == PGH_MIN) {                                           \
+      if (HAS_B)                                                                        \
+        m_ = make_float4(__fmul_rn(m_.x, BV.x), __fmul_rn(m_.y, BV.y),                  \
+                         __fmul_rn(m_.z, BV.z), __fmul_rn(m_.w, BV.w));                 \
+      if (AGGR == PGH_MAX)                                                              \
+        acc = make_float4(fmaxf(acc.x, m_.x), fmaxf(acc.y, m_.y), fmaxf(acc.z, m_.z),   \
+                          fmaxf(acc.w, m_.w));                                          \
+      else                                                                              \
+        acc = make_float4(fminf(acc.x, m_.x), fminf(acc.y, m_.y), fminf(acc.z, m_.z),   \
+                          fminf(acc.w, m_.w));                                          \
+    } else if (HAS_B) {                                                                 \
+      acc = make_float4(__fmaf_rn(m_.x, BV.x, acc.x), __fmaf_rn(m_.y, BV.y, acc.y),     \
+                        __fmaf_rn(m_.z, BV.z, acc.z), __fmaf_rn(m_.w, BV.w, acc.w));    \
+    } else {                                                                            \
+      acc = make_float4(__fadd_rn(acc.x, m_.x), __fadd_rn(acc.y, m_.y),                 \
+                        __fadd_rn(acc.z, m_.z), __fadd_rn(acc.w, m_.w));                \
+    }                                                                                   \
+  } while (0)
+    for (int base = e_beg; base < e_end; base += 32) {
+      const int t = base + lane;
+      int ci = 0, di = 0;
+      float sc = 1.f;
+      if (t < e_end) {
+        ci = c ? __ldg(c + t) : t;
+        if (HAS_B) di = d ? __ldg(d + t) : t;
+        if (HAS_SCALE) sc = __ldg(a_scale + ci);
+      }
+      const int chunk = min(32, e_end - base);
+      // software pipeline over groups of 2 entries with two register buffers: the loads of
+      // group g+1 are issued BEFORE group g is reduced, so a warp always has loads in flight
+      float4 a0[2], b0[2], a1[2], b1[2];
+      float s0[2], s1[2];
+#define PGH_LOAD2(K, AV, BV, SS)                                                        \
+  do {                                                                                  \
+    _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                     \
+      const int kk_ = min((K) + u, chunk - 1);       /* clamped: loads unconditional */   \
+      const int cc_ = __shfl_sync(kFull, ci, kk_);                                      \
+      AV[u] = __ldg(reinterpret_cast<const float4*>(a_col + (size_t)cc_ * lda));        \
+      if (HAS_B) {                                                                      \
+        const int dd_ = __shfl_sync(kFull, di, kk_);                                    \
+        BV[u] = __ldg(reinterpret_cast<const float4*>(b_col + (size_t)dd_ * ldb));      \
+      }                                                                                 \
+      if (HAS_SCALE) SS[u] = __shfl_sync(kFull, sc, kk_);                               \
+    }                                                                                   \
+  } while (0)
+#define PGH_REDUCE2(K, AV, BV, SS)                                                      \
+  do {                                                                                  \
+    _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                     \
+      if ((K) + u < chunk) {                                                            \
+        const int tt = base + (K) + u;                                                  \
+        if (tt >= cur_end) {                                                            \
+          do PGH_FLUSH(); while (tt >= cur_end);                                        \
+        }                                                                               \
+        PGH_REDUCE(AV[u], BV[u], SS[u]);                                                \
+      }                                                                                 \
+    }                                                                                   \
+  } while (0)
+      PGH_LOAD2(0, a0, b0, s0);
+#pragma unroll 1
+      for (int k = 0; k < chunk; k += 4) {
+        if (k + 2 < chunk) PGH_LOAD2(k + 2, a1, b1, s1);
+        PGH_REDUCE2(k, a0, b0, s0);
+        if (k + 2 >= chunk) break;
+        if (k + 4 < chunk) PGH_LOAD2(k + 4, a0, b0, s0);
+        PGH_REDUCE2(k + 2, a1, b1, s1);
+      }
+#undef PGH_REDUCE2
+#undef PGH_LOAD2
+    }
+    while (cur < nr) PGH_FLUSH();
+#undef PGH_REDUCE
+#undef PGH_FLUSH
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Ring variant (dense % 128 == 0): same work split and the same sequential reduction order
 // as the streaming kernel, but the value rows travel global -> shared memory with cp.async
 // (LDGSTS, 16 B per lane = one 512 B row per warp instruction) into a per-lane FIFO of NS
@@ -1103,15 +1247,33 @@ static void launch_lean(cudaStream_t s, const float* a_val, const int* c, const 
       a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, acc_src, lds,     \
       x.copy_src, x.ld_copy_src, x.copy_dst, x.ld_copy_dst, out)
   const int sel = (b_val ? 4 : 0) | (a_scale ? 2 : 0) | (acc ? 1 : 0);
-  switch (sel) {
-    case 0: PGH_LEAN(false, false, false); break;
-    case 1: PGH_LEAN(false, false, true); break;
-    case 2: PGH_LEAN(false, true, false); break;
-    case 3: PGH_LEAN(false, true, true); break;
-    case 4: PGH_LEAN(true, false, false); break;
-    case 5: PGH_LEAN(true, false, true); break;
-    case 6: PGH_LEAN(true, true, false); break;
-    default: PGH_LEAN(true, true, true); break;
+  if constexpr (U == 0) {                             // U == 0 selects the pipelined kernel
+#define PGH_LEANP(B, S, A)                                                                     \
+  seg_gmr_lean_pipe_kernel<AGGR, B, S, A, MINB><<<nb, kThreads, 0, s>>>(                       \
+      a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, acc_src, lds,     \
+      x.copy_src, x.ld_copy_src, x.copy_dst, x.ld_copy_dst, out)
+    switch (sel) {
+      case 0: PGH_LEANP(false, false, false); break;
+      case 1: PGH_LEANP(false, false, true); break;
+      case 2: PGH_LEANP(false, true, false); break;
+      case 3: PGH_LEANP(false, true, true); break;
+      case 4: PGH_LEANP(true, false, false); break;
+      case 5: PGH_LEANP(true, false, true); break;
+      case 6: PGH_LEANP(true, true, false); break;
+      default: PGH_LEANP(true, true, true); break;
+    }
+#undef PGH_LEANP
+  } else {
+    switch (sel) {
+      case 0: PGH_LEAN(false, false, false); break;
+      case 1: PGH_LEAN(false, false, true); break;
+      case 2: PGH_LEAN(false, true, false); break;
+      case 3: PGH_LEAN(false, true, true); break;
+      case 4: PGH_LEAN(true, false, false); break;
+      case 5: PGH_LEAN(true, false, true); break;
+      case 6: PGH_LEAN(true, true, false); break;
+      default: PGH_LEAN(true, true, true); break;
+    }
   }
 #undef PGH_LEAN
 }
@@ -1144,13 +1306,15 @@ static int launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, con
     // two operands: the lean kernel (half the instructions of the first streaming kernel,
     // 54 vs 61 us on the SSWL key, profiles/r1_gmr_ablate.txt)
     if (variant < 0) variant = b_val ? 30 : 13;
-    if (extra) variant = 30;                        // the fused epilogue lives in the lean kernel
+    if (extra && variant < 30) variant = 30;        // the fused epilogue lives in the lean kernels
     if (variant >= 30) {
       if (g_tune[6] == 1) accum = 0;
       const LeanExtra none;
       const LeanExtra& x = extra ? *extra : none;
       if (variant == 31) launch_lean<AGGR, 8, 2>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
       else if (variant == 32) launch_lean<AGGR, 2, 5>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
+      else if (variant == 34) launch_lean<AGGR, 0, 4>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
+      else if (variant == 35) launch_lean<AGGR, 0, 5>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
       else if (variant == 33) launch_lean<AGGR, 4, 3>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
       else launch_lean<AGGR, 4, 4>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
       return 0;
