@@ -64,3 +64,49 @@ def test_gloo_world2_allreduce_mean():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pygho_b200.dist import shard_contiguous
+    torch.manual_seed(100 + rank)                                # replicas start different ...
+    m = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    broadcast_parameters(m)                                      # ... and are made identical
+    b = FlatGradBucket(m.parameters())
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(7)
+    X, y = torch.randn(16, 6, generator=g), torch.randn(16, 1, generator=g)
+    mine = list(shard_contiguous(16, rank, world))               # whole "graphs" per rank
+    for _ in range(3):
+        b.zero()
+        torch.nn.functional.mse_loss(m(X[mine]), y[mine]).backward()
+        b.allreduce_mean()
+        opt.step()
+    out[rank] = torch.cat([p.detach().flatten() for p in m.parameters()]).tolist()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_data_parallel_equals_single_process():
+    """Sharding the batch over two ranks + FlatGradBucket.allreduce_mean reproduces
+    single-process training on the whole batch (equal shard sizes: mean of means)."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    torch.manual_seed(100)                                       # rank 0's initial weights
+    m = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(7)
+    X, y = torch.randn(16, 6, generator=g), torch.randn(16, 1, generator=g)
+    for _ in range(3):
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(m(X), y).backward()
+        opt.step()
+    want = torch.cat([p.detach().flatten() for p in m.parameters()])
+    assert torch.allclose(torch.tensor(out[0]), want, atol=1e-6)
+    assert out[0] == out[1]                                      # replicas stay bit-identical
