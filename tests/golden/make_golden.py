@@ -48,7 +48,7 @@ def npy(x):
 
 
 def save(name, **arrs):
-    path = os.path.join(HERE, name + ".npz")
+    path = os.path.join(os.environ.get("PYGHO_GOLDEN_OUT", HERE), name + ".npz")
     np.savez_compressed(path, **{k: npy(v) for k, v in arrs.items()})
     print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
 

@@ -152,6 +152,6 @@ out["dt_feat"], out["dt_shape"], out["dt_ptr"] = tfeat.numpy(), tshape.numpy(), 
 out["dt_data"] = torch.where(mt.mask, mt.data, torch.zeros_like(mt.data)).numpy()
 out["dt_mask"] = mt.mask.numpy()
 
-path = os.path.join(HERE, "hodata.npz")
+path = os.path.join(os.environ.get("PYGHO_GOLDEN_OUT", HERE), "hodata.npz")
 np.savez_compressed(path, **out)
 print(f"hodata: {os.path.getsize(path) / 1024:.1f} KiB, {len(out)} arrays")
