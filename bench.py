@@ -1,24 +1,32 @@
 #!/usr/bin/env python
-"""Benchmark: SSWL+ training throughput (graphs/s) on synthetic ZINC-shaped batches.
+"""Benchmark: training throughput (graphs/s) of the pygho.backend hot path on synthetic batches.
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA kernels)
     python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port)
 
-One "step" is one full optimisation step (forward, L1 loss, backward, gradient
-all-reduce when N > 1, AdamW) of the 6-layer SSWL+ sparse model of the reference's
-``example/zinc.py`` (hidden 128, mlplayer 2, outlayer 4, bn/silu, npool sum, lpool mean)
-on one batch of ``--batch`` graphs per GPU.  Prints ONE JSON line (rank 0).
+Workloads (``--workload``; BASELINE.json ``configs``):
+
+* ``sswl`` (default, configs[1] / [4]): 6-layer SSWL+ sparse model of the reference's
+  ``example/zinc.py`` (hidden 128, mlplayer 2, outlayer 4, bn/silu, npool sum, lpool mean) on
+  synthetic ZINC-shaped k-hop(3) batches, GLOBAL batch 1024 graphs.  With N GPUs the global
+  batch is sharded 1024/N graphs per rank (``"scaling": "strong"``);
+  ``--scaling weak`` keeps 1024 graphs per GPU instead.
+* ``ppgn_dd`` (configs[2]): dense PPGN / 2-FWL MaskedTensor model (mamamm), 128 graphs.
+* ``dssgnn_sr25`` / ``i2_sr25`` (configs[3]): DSSGNN (2-D tuples) / I2-GNN (3-D tuples) on
+  sr25-shaped strongly regular graphs, 64 graphs.
+
+One "step" is one full optimisation step (forward, L1 loss, backward, gradient all-reduce when
+N > 1, AdamW).  Prints ONE JSON line (rank 0).
 
 * ``value``: graphs/s with batches and plans resident in HBM (device-timed, max over ranks).
-* ``e2e``: the same step driven from pinned HOST buffers in the reference's datadict
-  format (x, edge_index, edge_attr, tupleid, tuplefeat, batch, y and the precomputed
-  ``acd`` plans): host->device copies, SparseTensor wrapping, CSR regrouping of the plans
-  and a device->host read of the loss are inside the timed region.
-* ``roofline``: the dominant kernel of this path, the fused spspmm forward
-  (``pgh_seg_gmr_f32``), timed alone with CUDA events on rotating operand sets larger
-  than L2; achieved = algorithmic bytes / mean launch duration.
-* ``cpu_baseline``: the oracle port of the reference (torch CPU ops) on the host cores,
-  on a bounded sample of the same workload.
+* ``e2e``: the same step driven from pinned HOST buffers in the reference's datadict format:
+  host->device copies, SparseTensor wrapping, CSR regrouping of the plans and a device->host
+  read of the loss are inside the timed region.
+* ``roofline``: the dominant kernel of the workload's hot path timed alone with CUDA events on
+  rotating operand sets larger than L2; achieved = algorithmic bytes / duration.
+* ``cpu_baseline``: the oracle port of the reference (torch CPU ops) on the host cores, on a
+  bounded sample of the same workload; ``stock_gpu_baseline``: the same ATen op chain the
+  reference would run, moved to this GPU (the "kernel to beat" of BASELINE.md).
 """
 from __future__ import annotations
 
@@ -33,8 +41,7 @@ import time
 # batches differ in size from step to step: growable segments keep the caching allocator from
 # falling back to cudaMalloc/cudaFree (device-synchronising) when a block does not fit, and
 # size classes of 1/8 power of two let batches of slightly different sizes reuse each other's
-# blocks instead of fragmenting the pool (every growth is a cuMemMap stall of 10-100 ms,
-# profiles/e2e_trace.py)
+# blocks instead of fragmenting the pool
 os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF",
                       "expandable_segments:True,roundup_power2_divisions:8")
 
@@ -48,7 +55,16 @@ import torch  # noqa: E402
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "sswl_plus_zinc_shape_train_graphs_per_s"
+WORKLOADS = {
+    # name: (metric, default global batch, conv, mode, graph shape, tuple sampler)
+    "sswl": ("sswl_plus_zinc_shape_train_graphs_per_s", 1024, "SSWL", "sparse", "zinc", "khop"),
+    "ppgn_dd": ("ppgn_dense_zinc_shape_train_graphs_per_s", 128, "PPGN", "dense", "zinc", "khop"),
+    "dssgnn_sr25": ("dssgnn_sr25_shape_train_graphs_per_s", 64, "DSSGNN", "sparse", "sr25", "khop"),
+    "i2_sr25": ("i2gnn_sr25_shape_train_graphs_per_s", 64, "I2GNN", "sparse", "sr25", "i2"),
+}
+ORACLE_KEYS = {"SSWL": ["X___X___1___A___0", "X___A___1___X___0"], "NGNN": ["X___X___1___A___0"],
+               "DSSGNN": ["X___X___1___A___0"], "PPGN": ["X___X___1___X___0"],
+               "I2GNN": ["X___X___2___A___0"]}
 
 
 def parse():
@@ -57,22 +73,63 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="graphs per GPU per step")
-    ap.add_argument("--conv", default="SSWL")
+    ap.add_argument("--workload", default="sswl", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0,
+                    help="GLOBAL batch in graphs (default: the workload's; 1024 for sswl)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --batch is sharded over the GPUs; weak: --batch graphs per GPU")
+    ap.add_argument("--conv", default="", help="override the workload's conv layer (sparse mode)")
     ap.add_argument("--hidden", type=int, default=128)
     ap.add_argument("--layers", type=int, default=6)
     ap.add_argument("--num-batches", type=int, default=3, help="distinct batches rotated")
-    ap.add_argument("--ref-batch", type=int, default=128, help="graphs per CPU reference step")
+    ap.add_argument("--ref-batch", type=int, default=0,
+                    help="graphs per CPU reference step (default: the global batch)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0,
+                    help="the reference arm trims its step count to finish within this time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stock-gpu", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch the resident-batch steps eagerly instead of replaying CUDA graphs")
-    return ap.parse_args()
+    ap.add_argument("--syncbn", action="store_true",
+                    help="BatchNorm statistics all-reduced over the ranks (equals single-process "
+                         "training on the global batch)")
+    args = ap.parse_args()
+    metric, batch, conv, mode, shape, tuples = WORKLOADS[args.workload]
+    args.metric, args.mode, args.shape, args.tuples = metric, mode, shape, tuples
+    args.batch = args.batch or batch
+    args.conv = args.conv or conv
+    args.ref_batch = args.ref_batch or args.batch
+    return args
 
 
-def workload_name(args, world):
-    return (f"{args.conv}+ SpModel {args.layers}x{args.hidden} (zinc.py work.sh flags), synthetic "
-            f"ZINC-shape k-hop(3) batches, {args.batch} graphs/GPU x {world} GPU")
+def split(args, world):
+    """(graphs per GPU, global batch)."""
+    if args.scaling == "weak":
+        return args.batch, args.batch * world
+    if args.batch % world:
+        raise SystemExit(f"--batch {args.batch} is not divisible by {world} GPUs")
+    return args.batch // world, args.batch
+
+
+def config_of(args, world, stats):
+    """The `config` object: identical for the own arm and the reference arm of one workload
+    at one N (so the driver can match them); arm-specific notes live in other keys."""
+    per_gpu, glob = split(args, world)
+    model = {"sparse": "SpModel", "dense": "MaModel"}[args.mode]
+    cfg = {
+        "workload": (f"{args.conv}{'+' if args.conv == 'SSWL' else ''} {model} {args.layers}x{args.hidden} "
+                     f"(example/zinc.py, work.sh flags) on synthetic {args.shape}-shape "
+                     f"{args.tuples} batches, global batch {glob} graphs"),
+        "global_batch": glob, "per_gpu_batch": per_gpu, "n_gpus": world,
+        "matmul": "tf32 on the GPU (reference: set_float32_matmul_precision('high')), fp32 on the CPU",
+        "l2": "step working set >> L2 at 1024 graphs/GPU; distinct batches rotated",
+        "parallelism": f"dp{world}: graphs sharded {per_gpu}/GPU, flat-bucket NCCL all-reduce"
+                       + (", SyncBN" if getattr(args, "syncbn", False) else ""),
+    }
+    cfg.update(stats)
+    return cfg
 
 
 # ------------------------------------------------------------------------ clocks
@@ -131,29 +188,61 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------- reference arm
-def oracle_train_throughput(args, steps, warmup, batch_graphs, seed=12345):
-    """graphs/s of the CPU restatement of the reference (oracle/model_oracle.py)."""
-    from oracle import model_oracle as MO
-    from oracle import pygho_oracle as O
+# ------------------------------------------------------------------- host batches
+def host_batches(args, per_gpu, rank, count):
+    """`count` distinct host batches of `per_gpu` graphs for this rank.  Rank r's batch i is
+    graphs [r * per_gpu, (r + 1) * per_gpu) of global batch i (every graph of global batch i
+    comes from one seed stream, so the N-GPU job sees the same kind of data as the 1-GPU job)."""
     from pygho_b200.hodata.synthetic import make_batch
-    # all host threads the process may use (torchrun pins OMP_NUM_THREADS=1 by default)
-    try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except Exception:
-        pass
-    torch.manual_seed(0)
-    hb = make_batch(batch_graphs, seed=seed)
-    keys = {"SSWL": ["X___X___1___A___0", "X___A___1___X___0"], "NGNN": ["X___X___1___A___0"],
-            "DSSGNN": ["X___X___1___A___0"], "PPGN": ["X___X___1___X___0"]}[args.conv]
+    return [make_batch(per_gpu, seed=1000 * rank + i, tuples=args.tuples, shape=args.shape)
+            for i in range(count)]
+
+
+def batch_stats(args, hb, keys):
+    st = {"nodes": int(hb.num_nodes), "edges": int(hb.edge_index.shape[1]),
+          "tuples": int(hb.tupleid.shape[1])}
+    if args.mode == "dense":
+        n = int(np.diff(hb.node_ptr).max())
+        st.update(padded_n=n, dense_positions=int(hb.num_graphs * n * n))
+    elif keys and keys[0] in hb.plans:
+        st["triples_per_key"] = int(hb.plans[keys[0]].shape[1])
+    return st
+
+
+def host_plans(hb, conv):
+    """The reference precomputes the ``acd`` plans per graph on the CPU (hodata/SpData.py:115-172);
+    here with the numpy oracle (reference arm / CPU baseline only)."""
+    from oracle import pygho_oracle as O
     plans = {}
-    for key in keys:
+    for key in ORACLE_KEYS[conv]:
         _o0, o1, d1, o2, d2 = key.split("___")
         pick = lambda op: hb.edge_index if op == "A" else hb.tupleid  # noqa: E731
         plans[key + "___acd"] = torch.from_numpy(
             O.filterind(hb.tupleid, *O.spspmm_ind(pick(o1), int(d1), pick(o2), int(d2))))
-    g = MO.host_graph_dict(hb, plans)
-    model = MO.OSpModel(conv=args.conv, num_layer=args.layers, hiddim=args.hidden)
+    return plans
+
+
+# ----------------------------------------------------------------- reference arm
+def oracle_step_fn(args, batch_graphs, device="cpu", seed=1000):
+    """(step(), stats) of the CPU restatement of the reference (oracle/model_oracle.py) on one
+    batch of `batch_graphs` graphs made by the same generator as the GPU arm's."""
+    from oracle import model_oracle as MO
+    from pygho_b200.hodata.synthetic import make_batch
+    torch.manual_seed(0)
+    hb = make_batch(batch_graphs, seed=seed, tuples=args.tuples, shape=args.shape)
+    if args.mode == "dense":
+        g = MO.host_dense_dict(hb)
+        model = MO.OMaModel(num_layer=args.layers, hiddim=args.hidden)
+        stats = batch_stats(args, hb, [])
+    else:
+        plans = host_plans(hb, args.conv)
+        g = MO.host_graph_dict(hb, plans)
+        model = MO.OSpModel(conv=args.conv, num_layer=args.layers, hiddim=args.hidden)
+        stats = batch_stats(args, hb, [])
+        stats["triples_per_key"] = int(next(iter(plans.values())).shape[1])
+    if device != "cpu":
+        g = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in g.items()}
+        model = model.to(device)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
 
     def step():
@@ -161,34 +250,55 @@ def oracle_train_throughput(args, steps, warmup, batch_graphs, seed=12345):
         loss = torch.nn.functional.l1_loss(g["y"].unsqueeze(-1), model(g))
         loss.backward()
         opt.step()
-        return float(loss.detach())
+        return loss
 
+    return step, stats
+
+
+def oracle_cpu_throughput(args, steps, warmup, batch_graphs, budget_s=None):
+    """graphs/s of the oracle port on all host threads; trims `steps` to `budget_s`."""
+    try:   # all host threads the process may use (torchrun pins OMP_NUM_THREADS=1 by default)
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
+    step, stats = oracle_step_fn(args, batch_graphs)
+    t_w = time.perf_counter()
     for _ in range(warmup):
-        step()
+        float(step())
+    per = (time.perf_counter() - t_w) / max(warmup, 1)
+    if budget_s is not None and warmup and per * (steps + warmup) > budget_s:
+        steps = max(2, int(budget_s / per) - warmup)
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
+        float(step())
     dt = time.perf_counter() - t0
-    return batch_graphs * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+    return batch_graphs * steps / dt, dt / steps * 1e3, torch.get_num_threads(), steps, stats
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port, all host
+    threads) on the own arm's workload: the GLOBAL batch per step, same steps and warm-up
+    (trimmed only if the run would exceed --ref-budget-s).  Rank 0 alone runs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(1, args.warmup)
-    # bound the whole run to a few minutes: the CPU path does ~100-400 graphs/s
-    budget_steps = max(2, min(steps, 24))
-    val, ms, cores = oracle_train_throughput(args, budget_steps, min(warmup, 3), args.ref_batch)
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
-    sample = (f"{budget_steps} steps of {args.ref_batch} graphs (same generator and model as "
-              f"the GPU arm, which runs {args.batch} graphs/GPU)")
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    val, ms, cores, ran, stats = oracle_cpu_throughput(args, steps, warmup, args.ref_batch,
+                                                      args.ref_budget_s)
+    _per_gpu, glob = split(args, world)
+    sample = (f"{ran} steps (+{warmup} warm-up) of {args.ref_batch} graphs = "
+              f"{'the global batch' if args.ref_batch == glob else 'a sample of the global batch'}"
+              f" of the GPU arm, same generator and model, {cores} host threads")
+    cfg = config_of(args, world, stats if args.ref_batch == glob else {})
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "graphs/s",
-        "n_gpus": args.gpus, "steps": budget_steps, "warmup": min(warmup, 3), "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": workload_name(args, world), "l2": "cpu run"},
+        "impl": "reference", "metric": args.metric, "value": val, "unit": "graphs/s",
+        "n_gpus": args.gpus, "steps": ran, "warmup": warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": cfg,
+        "reference_kind": "oracle_port_cpu (oracle/model_oracle.py: the reference's own torch "
+                          "CPU op chain, pinned to the real reference's layer outputs/gradients; "
+                          "/root/reference needs torch_geometric and cannot travel)",
         "cpu_baseline": {"value": val, "unit": "graphs/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": "graphs/s", "h2d_bytes_per_step": 0,
@@ -196,51 +306,49 @@ def run_reference(args):
     }), flush=True)
 
 
-# ------------------------------------------------------------------------ own arm
-def roofline_spspmm(dd_list, hidden, device, peaks):
-    """Time the fused spspmm forward (the SSWL `X x A` key) alone: CUDA events around
-    `iters` back-to-back launches cycling over operand sets whose total size exceeds L2."""
-    from pygho_b200 import plans as P
-    ops = torch.ops.pygho_b200
-    dd = dd_list[0]
-    acd = dd["X___X___1___A___0___acd"]
-    nX, nA = dd["X"].nnz, dd["A"].nnz
-    plan = P.plan_from_acd(acd, nX, nX, nA)
-    g = plan.group("a")
-    T = plan.T
-    alg_bytes = 4 * hidden * (nX + nA + nX) + 4 * (2 * T + nX + 1)
-    l2 = 128 << 20
+def stock_gpu_throughput(args, device, batch_graphs, steps=8, warmup=3):
+    """The reference's ATen op chain (index_select / mul / scatter_reduce_ / cuBLAS / cuDNN BN)
+    run on THIS GPU: the oracle model moved to `device`.  This is what a PygHO user gets on a
+    B200 today (BASELINE.md "kernel to beat"); none of this repo's kernels are on that path."""
+    step, _ = oracle_step_fn(args, batch_graphs, device=device)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": batch_graphs / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms,
+            "steps": steps, "warmup": warmup, "graphs_per_step": batch_graphs,
+            "what": "oracle/model_oracle.py on cuda: stock torch ops (index_select, mul, "
+                    "scatter_reduce_, addmm, batch_norm), eager, TF32 matmuls"}
+
+
+# ---------------------------------------------------------------------- rooflines
+def _l2_bytes():
     try:
         from pygho_b200 import _lib
         import ctypes
         info = (ctypes.c_int32 * 5)()
         _lib.call("pgh_device_info", info)
-        l2 = int(info[2]) << 10
+        return int(info[2]) << 10
     except Exception:
-        pass
-    per_set = 4 * hidden * (2 * nX + nA)
-    nsets = max(4, int(np.ceil(2.5 * l2 / per_set)))
-    gen = torch.Generator(device=device).manual_seed(0)
-    sets = [(torch.randn((nX, hidden), device=device, generator=gen),
-             torch.randn((nA, hidden), device=device, generator=gen)) for _ in range(nsets)]
-    for xv, av in sets[:3]:
-        ops.seg_gmr(xv, g.first, None, av, g.second, g.rowptr, nX, 0)
-    iters = 5 * nsets
+        return 128 << 20
+
+
+def _time_launches(launch, iters, device):
+    """Mean device time (us) of `iters` back-to-back launches: captured into one CUDA graph and
+    replayed (no Python / launch gaps); eager fallback if capture fails."""
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def launches():
-        for i in range(iters):
-            xv, av = sets[i % nsets]
-            ops.seg_gmr(xv, g.first, None, av, g.second, g.rowptr, nX, 0)
-
-    # the `iters` launches are captured into one CUDA graph and replayed, so the events bracket
-    # back-to-back kernel executions without Python / launch gaps (eager fallback if capture fails)
-    timing = "cuda graph replay of the launches"
     try:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            launches()
+            for i in range(iters):
+                launch(i)
         graph.replay()
         torch.cuda.synchronize(device)
         best = float("inf")
@@ -250,39 +358,136 @@ def roofline_spspmm(dd_list, hidden, device, peaks):
             e1.record()
             torch.cuda.synchronize(device)
             best = min(best, e0.elapsed_time(e1))
-        us = best * 1e3 / iters
         del graph
+        return best * 1e3 / iters, "cuda graph replay of the launches"
     except Exception:  # noqa: BLE001
         torch.cuda.synchronize(device)
-        timing = "eager launches"
         e0.record()
-        launches()
+        for i in range(iters):
+            launch(i)
         e1.record()
         torch.cuda.synchronize(device)
-        us = e0.elapsed_time(e1) * 1e3 / iters
-    achieved = alg_bytes / (us * 1e-6) / 1e9
+        return e0.elapsed_time(e1) * 1e3 / iters, "eager launches"
+
+
+def _roofline_obj(kernel, alg_bytes, us, timing, peaks, traffic_key, extra):
     peak = peaks.get("hbm_gbs")
+    achieved = alg_bytes / (us * 1e-6) / 1e9
     traffic = None
     try:  # dram bytes of this launch from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))["traffic"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[traffic_key]
     except Exception:
         pass
-    return {"bound": "hbm", "kernel": "seg_gmr_lean_kernel<sum,B> (spspmm fwd, key X___X___1___A___0)",
-            "achieved": achieved, "peak": peak if peak else 6650.0, "unit": "GB/s",
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peak
-            else "fallback 6650 GB/s (B200_PROFILING.md)",
-            "frac": achieved / (peak if peak else 6650.0), "traffic": traffic,
-            "us_per_launch": us, "algorithmic_bytes": alg_bytes,
-            "rows": nX, "triples": T, "operand_sets": nsets, "l2_bytes": l2, "timing": timing}
+    out = {"bound": "hbm", "kernel": kernel, "achieved": achieved,
+           "peak": peak if peak else 6650.0, "unit": "GB/s",
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peak
+           else "fallback 6650 GB/s (B200_PROFILING.md)",
+           "frac": achieved / (peak if peak else 6650.0), "traffic": traffic,
+           "us_per_launch": us, "algorithmic_bytes": alg_bytes, "timing": timing}
+    out.update(extra)
+    return out
 
 
+def roofline_spspmm(dd, hidden, device, peaks, key="X___X___1___A___0"):
+    """The fused spspmm forward (SSWL / DSSGNN / NGNN key ``X x A``) alone."""
+    from pygho_b200 import plans as P
+    ops = torch.ops.pygho_b200
+    nX, nA = dd["X"].nnz, dd["A"].nnz
+    plan = P.plan_from_acd(dd[key + "___acd"], nX, nX, nA)
+    g = plan.group("a")
+    T = plan.T
+    alg_bytes = 4 * hidden * (nX + nA + nX) + 4 * (2 * T + nX + 1)
+    l2 = _l2_bytes()
+    per_set = 4 * hidden * (2 * nX + nA)
+    nsets = max(4, int(np.ceil(2.5 * l2 / per_set)))
+    gen = torch.Generator(device=device).manual_seed(0)
+    sets = [(torch.randn((nX, hidden), device=device, generator=gen),
+             torch.randn((nA, hidden), device=device, generator=gen)) for _ in range(nsets)]
+
+    def launch(i):
+        xv, av = sets[i % nsets]
+        ops.seg_gmr(xv, g.first, None, av, g.second, g.rowptr, nX, 0)
+
+    for i in range(3):
+        launch(i)
+    us, timing = _time_launches(launch, 5 * nsets, device)
+    return _roofline_obj(f"seg_gmr_lean_kernel<sum,B> (spspmm fwd, key {key})", alg_bytes, us,
+                         timing, peaks, "spspmm_fwd",
+                         {"rows": nX, "triples": T, "operand_sets": nsets, "l2_bytes": l2})
+
+
+def roofline_mamamm(dd, hidden, device, peaks):
+    """The dense 2-FWL contraction (PPGNConv DD) alone: tcgen05 TF32 pipeline kernel."""
+    from pygho_b200.backend.Mamamm import default_algo, mamamm
+    from pygho_b200 import MaskedTensor
+    X = dd["X"]
+    mask = X.mask
+    b, n = mask.shape[0], mask.shape[1]
+    l2 = _l2_bytes()
+    per_set = 4 * hidden * b * n * n * 3
+    nsets = max(3, int(np.ceil(2.5 * l2 / per_set)))
+    gen = torch.Generator(device=device).manual_seed(0)
+    m = mask.unsqueeze(-1)
+    sets = [(MaskedTensor(torch.randn((b, n, n, hidden), device=device, generator=gen) * m, mask, 0.0, True),
+             MaskedTensor(torch.randn((b, n, n, hidden), device=device, generator=gen) * m, mask, 0.0, True))
+            for _ in range(nsets)]
+
+    def launch(i):
+        a, c = sets[i % nsets]
+        mamamm(a, 2, c, 1, mask)
+
+    for i in range(3):
+        launch(i)
+    us, timing = _time_launches(launch, 5 * nsets, device)
+    sizes = mask[:, :, 0].sum(1).double()
+    alg_bytes = 4 * hidden * b * 3 * n * n + b * n * n            # SURVEY 8d (padded tensors)
+    moved = int(4 * hidden * float((2 * sizes * sizes).sum() + b * n * n) + b * n * n)
+    useful = 2.0 * hidden * float((sizes ** 3).sum())
+    return _roofline_obj(f"mamamm_tc_pipe_kernel (algo {default_algo()}; tcgen05 kind::tf32, TMEM accumulators)",
+                         alg_bytes, us, timing, peaks, "mamamm",
+                         {"graphs": b, "padded_n": n, "operand_sets": nsets, "l2_bytes": l2,
+                          "moved_bytes_valid_extents": moved,
+                          "moved_frac_of_peak": moved / (us * 1e-6) / 1e9 / (peaks.get("hbm_gbs") or 6650.0),
+                          "useful_tflops": useful / (us * 1e-6) / 1e12,
+                          "tensor_pipe_util_vs_tf32_dense_1100": useful / (us * 1e-6) / 1e12 / 1100.0})
+
+
+def roofline_pool(dd, hidden, device, peaks, three_d):
+    """Pooling kernels of cfg4: 2-D tuples pooled over dim 0 (key = indices[1], unsorted: needs
+    the CSC permutation) or 3-D tuples pooled over dim 2 into the sparse (i, j) pattern."""
+    X = dd["X"]
+    nX = X.nnz
+    l2 = _l2_bytes()
+    nsets = max(4, int(np.ceil(2.5 * l2 / (4 * hidden * nX))))
+    gen = torch.Generator(device=device).manual_seed(0)
+    from pygho_b200 import SparseTensor
+    sets = [SparseTensor(X.indices, torch.randn((nX, hidden), device=device, generator=gen),
+                         tuple(X.shape[:X.sparse_dim]) + (hidden,), True) for _ in range(nsets)]
+    if three_d:
+        n_out = sets[0].mean([2], return_sparse=True).nnz
+        launch = lambda i: sets[i % nsets].mean([2], return_sparse=True)  # noqa: E731
+        name = "seg_gmr ring kernel (3-D tuples -> sparse (i,j) pattern, mean)"
+        alg = 4 * hidden * (nX + n_out) + 4 * (n_out + 1)
+    else:
+        n_out = X.shape[1]
+        launch = lambda i: sets[i % nsets].mean([0])  # noqa: E731
+        name = "seg_gmr ring kernel (pool over dim 0, unsorted key, mean)"
+        alg = 4 * hidden * (nX + n_out) + 4 * (n_out + 1) + 4 * nX
+    for i in range(3):
+        launch(i)
+    us, timing = _time_launches(launch, 5 * nsets, device)
+    return _roofline_obj(name, alg, us, timing, peaks, "pool3d" if three_d else "pool_cross",
+                         {"rows_in": nX, "rows_out": int(n_out), "operand_sets": nsets, "l2_bytes": l2})
+
+
+# ------------------------------------------------------------------------ own arm
 def run_b200(args):
     import torch.distributed as dist
-    from examples.zinc_models import SpModel
+    from examples.zinc_models import MaModel, SpModel
     from pygho_b200 import _lib
     from pygho_b200.dist import FlatGradBucket, broadcast_parameters
-    from pygho_b200.hodata.device import attach_host_plans, sp_datadict
-    from pygho_b200.hodata.synthetic import make_batch
+    from pygho_b200.hodata.device import (DeferredScalar, DevicePrefetcher, attach_host_plans,
+                                          ma_datadict, sp_datadict)
     from pygho_b200.honn.SpOperator import parse_precomputekey
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -297,27 +502,38 @@ def run_b200(args):
     torch.backends.cuda.matmul.allow_tf32 = True      # reference: set_float32_matmul_precision('high')
     torch.backends.cudnn.allow_tf32 = True
     _lib.load()
+    per_gpu, glob = split(args, world)
+    sparse = args.mode == "sparse"
 
     torch.manual_seed(0)
-    model = SpModel(args.conv, num_layer=args.layers, hiddim=args.hidden).to(device)
+    if sparse:
+        model = SpModel(args.conv, num_layer=args.layers, hiddim=args.hidden).to(device)
+        keys = parse_precomputekey(model)
+    else:
+        model = MaModel(args.conv, num_layer=args.layers, hiddim=args.hidden).to(device)
+        keys = []
     broadcast_parameters(model)
-    keys = parse_precomputekey(model)
+    if args.syncbn and world > 1:
+        from pygho_b200.dist import enable_sync_batchnorm
+        enable_sync_batchnorm(model)
     bucket = FlatGradBucket(model.parameters())
     # capturable: the step counter lives on the device, so the optimizer can be graph-captured
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True, capturable=True)
 
-    # synthetic data: `num_batches` distinct batches per rank (weak scaling: fixed per-GPU work)
-    hbs = [make_batch(args.batch, seed=1000 * rank + i) for i in range(args.num_batches)]
+    hbs = host_batches(args, per_gpu, rank, args.num_batches)
     pinned = {}
     dds = []
     for hb in hbs:
-        dd = sp_datadict(hb, device, keys, pinned)
-        attach_host_plans(hb, dd, keys)
+        if sparse:
+            dd = sp_datadict(hb, device, keys, pinned)
+            attach_host_plans(hb, dd, keys)
+        else:
+            dd = ma_datadict(hb, device, pinned=pinned)
         dds.append(dd)
-    # pin the host plans too (they are what the reference's loader would ship)
-    for hb in hbs:
-        for k, v in hb.plans.items():
-            pinned[id(v)] = torch.from_numpy(v).pin_memory()
+    if sparse:   # pin the host plans too (they are what the reference's loader would ship)
+        for hb in hbs:
+            for v in hb.plans.values():
+                pinned[id(v)] = torch.from_numpy(v).pin_memory()
     h2d_bytes = int(np.mean([hb.nbytes() for hb in hbs]))
 
     def train_step(dd):
@@ -334,13 +550,17 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    def timed(fn, steps, finish=None):
+    def timed(fn, steps, finish=None, per_step=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launches()
         e0.record()
         for i in range(steps):
             fn(i)
+            if per_step is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                per_step.append(ev)
         if finish is not None:
             finish()
         e1.record()
@@ -348,15 +568,17 @@ def run_b200(args):
         ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if per_step is not None:
+            evs = [e0] + per_step
+            per_step[:] = [a.elapsed_time(b) for a, b in zip(evs[:-1], evs[1:])]
         return float(ms.item()), _lib.launches() - l0
 
     warm = max(3, args.warmup)
     for i in range(warm):
         train_step(dds[i % len(dds)])
     # Resident batches: the whole step (fwd, loss, bwd, all-reduce, AdamW) of each batch is
-    # captured into one CUDA graph and replayed (pygho_b200/graph.py) -- the eager step needs
-    # 14.8 ms of host time for 16.4 ms of device time, i.e. it is nearly launch-bound.  If
-    # capture fails on this rank the eager step is used (it issues the same collectives).
+    # captured into one CUDA graph and replayed (pygho_b200/graph.py).  If capture fails on this
+    # rank the eager step is used (it issues the same collectives).
     graphs, graph_note = None, "eager (--no-graph)"
     if not args.no_graph:
         try:
@@ -380,124 +602,134 @@ def run_b200(args):
         launches = sum(graphs[i % len(graphs)].launches for i in range(args.steps))
     clock_summary = clocks.summary()
     ms_step = ms_total / args.steps
-    value = args.batch * world / (ms_step * 1e-3)
+    value = glob / (ms_step * 1e-3)
 
     # ---- end to end: pinned host buffers in, loss out -------------------------------
-    # every step's inputs come from pinned host memory (reference datadict format incl. the
-    # acd plans); the copies + CSR regrouping of batch i+1 are issued on a side stream right
-    # after step i has been launched (DevicePrefetcher), the loss is read back every step
-    from pygho_b200.hodata.device import DevicePrefetcher
-    tables = {"x": model.x_encoder.num_embeddings, "A": model.ea_encoder.num_embeddings,
-              "X": model.tuplefeat_encoder.num_embeddings}
-    feeder = DevicePrefetcher(hbs, device, keys, pinned, embeddings=tables)
+    e2e = None
+    if not args.no_e2e:
+        reader = DeferredScalar()
+        losses = []
+        if sparse:
+            # every step's inputs come from pinned host memory (reference datadict format incl.
+            # the acd plans); the copies + CSR regrouping of batch i+1 are issued on a side
+            # stream right after step i has been launched, the loss is read back every step
+            tables = {"x": model.x_encoder.num_embeddings, "A": model.ea_encoder.num_embeddings}
+            if hasattr(model.tuplefeat_encoder, "num_embeddings") and hbs[0].tuplefeat.ndim == 1:
+                tables["X"] = model.tuplefeat_encoder.num_embeddings
+            feeder = DevicePrefetcher(hbs, device, keys, pinned, embeddings=tables)
 
-    # The loss of every step is copied to pinned host memory and read by the host ONE step
-    # late (deferred logging): the host launches step i, then waits for step i-1's loss,
-    # then issues the prefetch of batch i+1 -- the GPU never idles while the host blocks.
-    # That wait is also the synchronisation DevicePrefetcher.advance() asks for (batch i-1
-    # is fully consumed before its buffers are recycled).
-    from pygho_b200.hodata.device import DeferredScalar
-    reader = DeferredScalar()
-    losses = []
+            def e2e_step(i):
+                dd = feeder.get()
+                loss = train_step(dd)
+                prev = reader.push(loss)                 # loss of the step before this one
+                if prev is not None:
+                    losses.append(prev)
+                feeder.advance()                         # next batch's H2D + plans, side stream
+        else:
+            feeder = None
 
-    def read_pending():
-        v = reader.flush()
-        if v is not None:
-            losses.append(v)                             # D2H read of the result
+            def e2e_step(i):
+                dd = ma_datadict(hbs[i % len(hbs)], device, pinned=pinned)   # H2D + device padding
+                loss = train_step(dd)
+                prev = reader.push(loss)
+                if prev is not None:
+                    losses.append(prev)
 
-    def e2e_step(i):
-        dd = feeder.get()
-        loss = train_step(dd)
-        prev = reader.push(loss)                         # loss of the step before this one
-        if prev is not None:
-            losses.append(prev)
-        feeder.advance()                                 # next batch's H2D + plans, side stream
+        def read_pending():
+            v = reader.flush()
+            if v is not None:
+                losses.append(v)                         # D2H read of the result
 
-    def e2e_steps(n):
-        for i in range(n):
-            e2e_step(i)
-        read_pending()                                   # every timed step's loss is read
+        def e2e_steps(n):
+            for i in range(n):
+                e2e_step(i)
+            read_pending()
 
-    # two full cycles over the host batches: every allocation size of both streams has been
-    # seen (a growth of an expandable segment inside the timed region costs 10-100 ms)
-    e2e_steps(max(args.warmup, 2 * len(hbs) + 1))
-    if os.environ.get("PYGHO_B200_BENCH_DEBUG"):
-        for i in range(12):
-            torch.cuda.synchronize(device)
-            t0 = time.perf_counter()
-            e2e_step(i)
-            torch.cuda.synchronize(device)
-            print(f"[debug] e2e step {i}: {1e3 * (time.perf_counter() - t0):.2f} ms", file=sys.stderr)
-        read_pending()
-    losses.clear()
-    import gc
-    gc.collect()
-    gc.freeze()        # long-lived objects out of the collector's way: no multi-ms gen-2 pauses
-    trace = [] if os.environ.get("PYGHO_B200_BENCH_TRACE") else None
-    timed_step = e2e_step
-    if trace is not None:
-        def timed_step(i):
-            e2e_step(i)
-            trace.append(time.perf_counter())
-    mem0 = torch.cuda.memory_stats(device)
-    e2e_ms, _ = timed(timed_step, args.steps, finish=read_pending)
-    if trace is not None:
-        mem1 = torch.cuda.memory_stats(device)
-        gaps = [round(1e3 * (b - a), 2) for a, b in zip(trace[:-1], trace[1:])]
-        grew = {k: mem1[k] - mem0[k] for k in ("num_alloc_retries", "num_device_alloc", "num_device_free")}
-        print(f"[trace] e2e host ms between steps: {gaps}; allocator: {grew}", file=sys.stderr)
-    assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: every step's loss is read"
-    e2e_value = args.batch * world / (e2e_ms / args.steps * 1e-3)
-    feeder.close()                                       # no stray side-stream work below
-    torch.cuda.synchronize(device)
+        # two full cycles over the host batches: every allocation size of both streams was seen
+        e2e_steps(max(args.warmup, 2 * len(hbs) + 1))
+        losses.clear()
+        import gc
+        gc.collect()
+        gc.freeze()    # long-lived objects out of the collector's way: no multi-ms gen-2 pauses
+        per_step = []
+        e2e_ms, _ = timed(e2e_step, args.steps, finish=read_pending, per_step=per_step)
+        assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: every step's loss is read"
+        e2e = {"value": glob / (e2e_ms / args.steps * 1e-3), "unit": "graphs/s",
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+               "ms_per_step": e2e_ms / args.steps,
+               "step_ms": {"min": float(np.min(per_step)), "median": float(np.median(per_step)),
+                           "max": float(np.max(per_step))}}
+        if feeder is not None:
+            feeder.close()                               # no stray side-stream work below
+        torch.cuda.synchronize(device)
 
     out = None
+    peaks = {}
     if rank == 0:
-        peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        nX, nA, N = dds[0]["X"].nnz, dds[0]["A"].nnz, hbs[0].num_nodes
         out = {
-            "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world,
+            "metric": args.metric, "value": value, "unit": "graphs/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args, world), "global_batch": args.batch * world,
-                       "per_gpu_batch": args.batch, "nodes": N, "edges": nA, "tuples": nX,
-                       "triples_per_key": int(dds[0][keys[0] + "___acd"].shape[1]),
-                       "matmul": "tf32 (reference sets float32_matmul_precision('high'))",
-                       "l2": f"step working set >> L2; {len(dds)} distinct batches rotated",
-                       "launch": graph_note,
-                       "parallelism": f"dp{world} (graphs sharded, flat-bucket NCCL all-reduce)"},
-            "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches,
-            "clocks": clock_summary,
+            "config": config_of(args, world, batch_stats(args, hbs[0], keys)),
+            "launch": graph_note,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary,
         }
     if rank == 0 and not args.no_roofline:
-        out["roofline"] = roofline_spspmm(dds, args.hidden, device, peaks)
+        try:
+            if args.workload == "ppgn_dd":
+                out["roofline"] = roofline_mamamm(dds[0], args.hidden, device, peaks)
+            elif args.workload == "dssgnn_sr25":
+                out["roofline"] = roofline_pool(dds[0], args.hidden, device, peaks, False)
+                out["roofline_spspmm"] = roofline_spspmm(dds[0], args.hidden, device, peaks)
+            elif args.workload == "i2_sr25":
+                out["roofline"] = roofline_pool(dds[0], args.hidden, device, peaks, True)
+                out["roofline_spspmm"] = roofline_spspmm(dds[0], args.hidden, device, peaks,
+                                                         "X___X___2___A___0")
+            else:
+                out["roofline"] = roofline_spspmm(dds[0], args.hidden, device, peaks)
+        except Exception as e:  # noqa: BLE001
+            out["roofline"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     if world > 1:
         dist.barrier()
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1:
         del dds
+        graphs = None
+        run_step = None
         torch.cuda.empty_cache()
-        v, ms, cores = oracle_train_throughput(args, 3, 1, args.ref_batch)
-        out["cpu_baseline"] = {"value": v, "unit": "graphs/s", "cores": cores, "kind": "port",
-                               "sample": f"3 steps of {args.ref_batch} graphs, oracle port of the "
-                                         "reference (torch CPU ops), same model and generator"}
+        if not args.no_stock_gpu:
+            try:
+                out["stock_gpu_baseline"] = stock_gpu_throughput(args, device, per_gpu)
+                out["stock_gpu_baseline"]["own_over_stock"] = value / out["stock_gpu_baseline"]["value"]
+            except Exception as e:  # noqa: BLE001
+                out["stock_gpu_baseline"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.empty_cache()
+        if not args.no_cpu_baseline:
+            v, ms, cores, ran, _ = oracle_cpu_throughput(args, 3, 1, args.ref_batch)
+            out["cpu_baseline"] = {"value": v, "unit": "graphs/s", "cores": cores, "kind": "port",
+                                   "sample": f"{ran} steps (+1 warm-up) of {args.ref_batch} graphs, "
+                                             "oracle port of the reference (torch CPU ops), same "
+                                             "model and generator as the GPU arm"}
     if rank == 0:
         print(json.dumps(out), flush=True)
-    # Orderly teardown: prefetch thread first, then the CUDA graphs (they hold captured NCCL
-    # kernels and must go before the communicator), then the process group.  A watchdog ends
-    # the process with status 0 if NCCL's shutdown blocks: the result line is already out.
+    # Orderly teardown: prefetch thread first (closed above), then the CUDA graphs (they hold
+    # captured NCCL kernels and must go before the communicator), then the process group.  If the
+    # shutdown hangs, fail LOUDLY (non-zero status) instead of waiting for the driver's limit.
     sys.stdout.flush()
     sys.stderr.flush()
-    killer = threading.Timer(30.0, lambda: os._exit(0))
+
+    def _hung():
+        print(f"[bench] rank {rank}: teardown did not finish within 120 s", file=sys.stderr, flush=True)
+        os._exit(3)
+
+    killer = threading.Timer(120.0, _hung)
     killer.daemon = True
     killer.start()
-    del feeder, run_step
+    run_step = None
     graphs = None
     import gc
     gc.collect()

@@ -55,6 +55,8 @@ class SpModel(nn.Module):
             self.tuplefeat_encoder2 = Embedding(16, hiddim)
         self.lin_tupleinit0 = nn.Linear(hiddim, hiddim)
         self.lin_tupleinit1 = nn.Linear(hiddim, hiddim)
+        if conv == "I2GNN":
+            self.lin_tupleinit2 = nn.Linear(hiddim, hiddim)
         self.subggnns = nn.ModuleList(
             [make_conv(conv, hiddim, "SS", convmlp, aggr, cpool) for _ in range(num_layer)])
         self.lpool = (nn.Sequential(OpPoolingSubg3D("S", lpool), OpPoolingSubg2D("S", lpool))
@@ -76,6 +78,10 @@ class SpModel(nn.Module):
         # zinc.py:270-276 indexes with X.indices[0] / [1]; use the gather kernel
         root = X.unpooling_fromdense1dim(0, self.lin_tupleinit0(x)).values
         node = X.unpooling_fromdense1dim(1, self.lin_tupleinit1(x)).values
+        if self.conv_name == "I2GNN":
+            # zinc.py:271-273: the third factor is gathered with X.indices[1] too (kept as is)
+            third = X.unpooling_fromdense1dim(1, self.lin_tupleinit2(x)).values
+            return X.tuplewiseapply(lambda val: root * node * third * val)
         return X.tuplewiseapply(lambda val: root * node * val)
 
     def forward(self, datadict: dict) -> torch.Tensor:

@@ -76,9 +76,7 @@ def mamamm(A: MaskedTensor, dim1: int, B: MaskedTensor, dim2: int, mask: BoolTen
         b3 = tB.reshape(b, tB.shape[1], -1, dense)
     n_i = a3.shape[2] if trans_a else a3.shape[1]
     n_k = b3.shape[1] if trans_b else b3.shape[2]
-    algo = default_algo()
-    if algo in (1, 2) and (dense % 8 != 0 or n_i > 128 or n_k > 64 or a3.shape[1 if trans_a else 2] > 128):
-        algo = 0      # shapes outside the tensor-core kernel's tile limits
+    algo = default_algo()     # ops._mm falls back to algo 0 per call when a shape does not fit
     omask = mask if mask.ndim == 3 else mask.reshape(b, n_i, n_k)
     out = MaMaMM.apply(a3, trans_a, m_a, b3, trans_b, m_b, omask, algo)
     out = out.reshape((b,) + a_rest + b_rest + tuple(dshape))

@@ -214,7 +214,11 @@ class SparseTensor:
             # the reference raises here (torch.sum(..., dims=0), SpTensor.py:417); give the
             # obviously intended result instead: reduce over all tuples
             flat = self._values
-            return {"sum": flat.sum(0), "mean": flat.mean(0), "max": flat.amax(0)}[reduce]
+            if reduce == "sum":
+                return flat.sum(0)
+            if reduce == "mean":
+                return flat.mean(0)
+            return flat.amax(0) if reduce == "max" else flat.amin(0)
         if return_sparse:
             return self._reduce_to_sparse(dims, reduce)
         return self._reduce_to_dense(dims, reduce)
@@ -278,15 +282,18 @@ class SparseTensor:
         dims = list(dims)
         keep = tuple(i for i in range(tarX.sparse_dim) if i not in dims)
         cache = P._cache(tarX.indices)
+        # the cache lives on the (long-lived) target pattern; the entry keeps the source index
+        # tensor it was built for, so a recycled id() can never return another pattern's plan
         ck = ("unpool_from", id(self._indices), keep)
-        plan = cache.get(ck)
+        hit = cache.get(ck)
+        plan = hit[0] if hit is not None and hit[1] is self._indices else None
         if plan is None:
             self_key = P.pack_keys(self._indices, check=__debug__)
             if __debug__:
                 assert P.is_sorted(self_key, strict=True), "self is not coalesced"
             pos = P.lookup_sorted(self_key, P.pack_keys(tarX.indices, rows=keep))
             plan = _gather_plan(pos, self.nnz)
-            cache[ck] = plan
+            cache[ck] = (plan, self._indices)
         flat, dshape = _flatten_dense(self._values)
         vals = seg_gmr(flat, None, plan, "sum").reshape((tarX.nnz,) + dshape)
         return tarX.tuplewiseapply(lambda _x: vals)

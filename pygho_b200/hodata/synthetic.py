@@ -23,7 +23,7 @@ import numpy as np
 
 __all__ = [
     "HostGraph", "HostBatch", "zinc_like_graph", "khop_tuples", "i2_tuples",
-    "make_graphs", "collate", "make_batch", "graph_from_edges",
+    "make_graphs", "collate", "make_batch", "graph_from_edges", "sr25_like_graph",
 ]
 
 
@@ -189,9 +189,41 @@ def i2_tuples(n: int, edge_index: np.ndarray, hop: int) -> Tuple[np.ndarray, np.
     return tid, np.concatenate(f).astype(np.int64)
 
 
-def make_graphs(num: int, seed: int = 0, hop: int = 3,
-                tuples: str = "khop") -> List[HostGraph]:
+# Two Latin squares of order 5 from different main classes: the Cayley table of Z5 and a
+# non-group square.  Their Latin-square graphs L3(5) are the strongly regular graphs (25, 12, 5, 6)
+# number 1 (= the Paley graph of GF(25)) and number 0 of the reference's sr25 set
+# (dataset/sr25/raw/sr251256.g6, 15 graphs; checked with networkx in tests/test_hodata_oracle.py).
+_LATIN5 = (
+    ((0, 1, 2, 3, 4), (1, 2, 3, 4, 0), (2, 3, 4, 0, 1), (3, 4, 0, 1, 2), (4, 0, 1, 2, 3)),
+    ((1, 0, 4, 3, 2), (3, 4, 2, 1, 0), (0, 1, 3, 2, 4), (4, 2, 1, 0, 3), (2, 3, 0, 4, 1)),
+)
+
+
+def sr25_like_graph(rng: np.random.Generator, hop: int = 3, tuples: str = "khop",
+                    which: Optional[int] = None) -> HostGraph:
+    """A strongly regular graph with the sr25 parameters (25 nodes, 12-regular, lambda 5, mu 6,
+    diameter 2) under a random relabelling: cells of a 5 x 5 Latin square, adjacent when they
+    share a row, a column or a symbol.  Per graph: 300 directed edges, 625 2-tuples at hop >= 2,
+    7500 3-tuples (I2), 7500 / 90 000 plan triples."""
+    L = _LATIN5[int(rng.integers(len(_LATIN5))) if which is None else which]
+    perm = rng.permutation(25)
+    edges = []
+    for a in range(25):
+        for b in range(a + 1, 25):
+            i, j = divmod(a, 5)
+            k, l = divmod(b, 5)
+            if i == k or j == l or L[i][j] == L[k][l]:
+                edges.append((perm[a], perm[b]))
+    return graph_from_edges(25, np.array(edges, dtype=np.int64), rng, hop, tuples)
+
+
+def make_graphs(num: int, seed: int = 0, hop: int = 3, tuples: str = "khop",
+                shape: str = "zinc") -> List[HostGraph]:
     rng = np.random.default_rng(seed)
+    if shape == "sr25":
+        return [sr25_like_graph(rng, hop, tuples) for _ in range(num)]
+    if shape != "zinc":
+        raise ValueError(f"unknown graph shape {shape}")
     return [zinc_like_graph(rng, hop, tuples) for _ in range(num)]
 
 
@@ -223,6 +255,6 @@ def collate(graphs: List[HostGraph]) -> HostBatch:
     )
 
 
-def make_batch(num_graphs: int, seed: int = 0, hop: int = 3,
-               tuples: str = "khop") -> HostBatch:
-    return collate(make_graphs(num_graphs, seed, hop, tuples))
+def make_batch(num_graphs: int, seed: int = 0, hop: int = 3, tuples: str = "khop",
+               shape: str = "zinc") -> HostBatch:
+    return collate(make_graphs(num_graphs, seed, hop, tuples, shape))

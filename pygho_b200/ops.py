@@ -567,10 +567,21 @@ def _ext3(eX: Optional[Tensor], tx: bool, eY: Optional[Tensor], ty: bool, eM: Op
     return ext
 
 
+def mamamm_algo_for(algo: int, n_i: int, n_j: int, n_k: int, dense: int) -> int:
+    """The tensor-core kernels (algo 1 / 2) hold one (n_i x n_j) and one (n_j x n_k) tile per
+    channel: n_i, n_j <= 128, n_k <= 64, dense % 8 == 0.  Anything else runs on the exact-fp32
+    kernel (algo 0).  Decided per CALL: the gradient contractions of a forward that fits may
+    not fit themselves (their (n_i, n_j, n_k) roles are permuted)."""
+    if algo in (1, 2) and (dense % 8 != 0 or n_i > 128 or n_k > 64 or n_j > 128):
+        return 0
+    return algo
+
+
 def _mm(X, tx, eX, Y, ty, eY, mask, eM, algo):
     b = X.shape[0]
     n_i, n_j = (X.shape[2], X.shape[1]) if tx else (X.shape[1], X.shape[2])
     n_k = Y.shape[1] if ty else Y.shape[2]
+    algo = mamamm_algo_for(algo, n_i, n_j, n_k, X.shape[3])
     return _ops.mamamm(X, tx, Y, ty, mask, _ext3(eX, tx, eY, ty, eM, (b, n_i, n_j, n_k)), algo)
 
 

@@ -302,6 +302,76 @@ def g_conv():
     save("conv", **out)
 
 
+def g_conv_i2():
+    """I2Conv (Conv.py:107-147) on 3-D tuples with the read-out chain of example/zinc.py:258
+    (OpPoolingSubg3D -> OpPoolingSubg2D) and the 3-D tupleinit of zinc.py:270-273 (including its
+    use of X.indices[1] for the third factor): forward values, input and parameter gradients."""
+    hb = make_batch(3, seed=23, tuples="i2")
+    ei, tid = batch_tensors(hb)
+    N, d = hb.num_nodes, 8
+    gen = torch.Generator().manual_seed(8)
+    Av = torch.randn((ei.shape[1], d), generator=gen)
+    Xv = torch.randn((tid.shape[1], d), generator=gen)
+    xn = torch.randn((N, d), generator=gen)
+    out = {"edge_index": ei, "tupleid": tid, "N": np.array(N), "Av": Av, "Xv": Xv, "xn": xn}
+    mlp = {"numlayer": 2, "tailact": True, "norm": "bn", "act": "silu", "dp": 0.0}
+    key = "X___X___2___A___0"
+    acd = RSS.filterind(tid, *RSS.spspmm_ind(tid, 2, ei, 0))
+    datadict = {key + "___acd": acd}
+    out[key + "___acd"] = canon(acd)
+    for name, aggr, pool in (("I2", "sum", "mean"), ("I2max", "max", "max")):
+        torch.manual_seed(101)
+        conv = RConv.I2Conv(d, d, aggr, "SS", dict(mlp))
+        lins = torch.nn.ModuleList([torch.nn.Linear(d, d) for _ in range(3)])
+        lpool = torch.nn.Sequential(OpPoolingSubg3D("S", pool), OpPoolingSubg2D("S", pool))
+        A = SparseTensor(ei, Av.clone(), (N, N, d), True)
+        xv = Xv.clone().requires_grad_(True)
+        xnode = xn.clone().requires_grad_(True)
+        X = SparseTensor(tid, xv, (N, N, N, d), True)
+        X = X.tuplewiseapply(lambda val: lins[0](xnode)[X.indices[0]] * lins[1](xnode)[X.indices[1]]
+                             * lins[2](xnode)[X.indices[1]] * val)
+        Y = conv(A, X, datadict)
+        Z = X.add(Y, True)
+        h = lpool(Z)
+        loss = (h ** 2).mean() + (Y.values ** 2).mean()
+        loss.backward()
+        for k, v in conv.state_dict().items():
+            out[f"{name}.sd.{k}"] = v
+        for k, p in conv.named_parameters():
+            out[f"{name}.grad.{k}"] = p.grad
+        for i in range(3):
+            out[f"{name}.init{i}.weight"], out[f"{name}.init{i}.bias"] = lins[i].weight, lins[i].bias
+            out[f"{name}.init{i}.gweight"], out[f"{name}.init{i}.gbias"] = lins[i].weight.grad, lins[i].bias.grad
+        out[f"{name}.out"] = Y.values
+        out[f"{name}.readout"] = h
+        out[f"{name}.gradX"] = xv.grad
+        out[f"{name}.gradx"] = xnode.grad
+    save("conv_i2", **out)
+
+
+def g_conv_dd():
+    """PPGNConv in DD mode (Conv.py:200-236, mamamm) on graphs of EQUAL size (full masks): the
+    one case in which the reference's never-filled pads (MaTensor.py:103-118) cannot
+    leak into the result, so its output pins the dense layer's intended semantics."""
+    gen = torch.Generator().manual_seed(9)
+    b, n, d = 3, 6, 8
+    mask = torch.ones((b, n, n), dtype=torch.bool)
+    Xd = torch.randn((b, n, n, d), generator=gen)
+    mlp = {"numlayer": 2, "tailact": True, "norm": "bn", "act": "silu", "dp": 0.0}
+    torch.manual_seed(102)
+    conv = RConv.PPGNConv(d, d, "sum", "DD", dict(mlp))
+    xd = Xd.clone().requires_grad_(True)
+    X = MaskedTensor(xd, mask)
+    Y = conv(None, X, {})
+    (Y.data ** 2).mean().backward()
+    out = {"X": Xd, "mask": mask, "out": Y.data, "gradX": xd.grad}
+    for k, v in conv.state_dict().items():
+        out[f"sd.{k}"] = v
+    for k, p in conv.named_parameters():
+        out[f"grad.{k}"] = p.grad
+    save("conv_dd", **out)
+
+
 def golden_spmamm():
     """Reference spmamm (backend/Spmamm.py) on the inputs it can run: its masked_fill call (:60)
     only broadcasts when there are NO dense dims (mask (nnz, k) against mult (nnz, k)), and its
@@ -337,6 +407,14 @@ if __name__ == "__main__" and "spmamm" in sys.argv[1:]:
     golden_spmamm()
     sys.exit(0)
 
+if __name__ == "__main__" and "conv_i2" in sys.argv[1:]:
+    g_conv_i2()
+    sys.exit(0)
+
+if __name__ == "__main__" and "conv_dd" in sys.argv[1:]:
+    g_conv_dd()
+    sys.exit(0)
+
 
 if __name__ == "__main__":
     torch.set_num_threads(1)
@@ -347,3 +425,5 @@ if __name__ == "__main__":
     g_3d()
     g_masked()
     g_conv()
+    g_conv_i2()
+    g_conv_dd()

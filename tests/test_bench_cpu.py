@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SMALL = ["--steps", "2", "--warmup", "1", "--ref-batch", "8", "--layers", "1", "--hidden", "16"]
+SMALL = ["--steps", "2", "--warmup", "1", "--batch", "8", "--layers", "1", "--hidden", "16"]
 
 
 def run(args, env=None):
@@ -25,7 +25,8 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "graphs/s" and d["higher_is_better"] is True
     assert d["metric"] == "sswl_plus_zinc_shape_train_graphs_per_s" and d["value"] > 0
-    assert d["vs_baseline"] is None and d["scaling"] == "weak" and d["data"] == "synthetic"
+    assert d["vs_baseline"] is None and d["scaling"] == "strong" and d["data"] == "synthetic"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["config"]["global_batch"] == 8
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
@@ -44,3 +45,13 @@ def test_own_arm_needs_a_gpu():
     r = run(["--gpus", "1", "--steps", "1", "--warmup", "1"])
     assert r.returncode != 0
     assert "no CPU path" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_other_workloads():
+    """The dense PPGN and the sr25 DSSGNN / I2 arms run on the CPU oracle too."""
+    for wl in ("ppgn_dd", "dssgnn_sr25", "i2_sr25"):
+        r = run(["--impl", "reference", "--workload", wl, "--steps", "1", "--warmup", "1",
+                 "--ref-batch", "2", "--batch", "2", "--layers", "1", "--hidden", "8"])
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert d["value"] > 0 and d["config"]["global_batch"] == 2 and wl.split("_")[0] in d["metric"]

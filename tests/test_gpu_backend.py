@@ -329,6 +329,39 @@ def test_spmm_pool_unpool_gradients(B, golden, aggr):
         close(xg.grad, xr.grad, 2e-5)
 
 
+@pytest.mark.parametrize("aggr", ("sum", "mean", "max"))
+@pytest.mark.parametrize("key", ("XA", "AX"))
+def test_full_size_spspmm_vs_torch_oracle(B, aggr, key):
+    """BASELINE-size batch (B=1024 graphs, d=128): the kernels bench.py times (lean streaming
+    kernel for sum/mean, both operand-gradient groupings) compared DIRECTLY with the torch-CPU
+    oracle -- values and both operand gradients, no size reduction."""
+    from pygho_b200.hodata.synthetic import make_batch
+    hb = make_batch(1024, seed=0)
+    ei_c, tid_c = torch.from_numpy(hb.edge_index), torch.from_numpy(hb.tupleid)
+    Nn, d = hb.num_nodes, 128
+    gen = torch.Generator().manual_seed(5)
+    Xv = torch.randn((tid_c.shape[1], d), generator=gen)
+    Av = torch.randn((ei_c.shape[1], d), generator=gen)
+    w = torch.randn((tid_c.shape[1], d), generator=gen)
+    ei, tid = ei_c.to(DEV), tid_c.to(DEV)
+    if key == "XA":
+        acd = B.filterind(tid, *B.spspmm_ind(tid, 1, ei, 0))
+    else:
+        acd = B.filterind(tid, *B.spspmm_ind(ei, 1, tid, 0))
+    xr, ar = Xv.clone().requires_grad_(True), Av.clone().requires_grad_(True)
+    ops_ref = (xr, ar) if key == "XA" else (ar, xr)
+    ref = TO.spspmm(ops_ref[0], ops_ref[1], acd.cpu(), tid_c.shape[1], aggr)
+    (ref * w).sum().backward()
+    xg, ag = Xv.to(DEV).requires_grad_(True), Av.to(DEV).requires_grad_(True)
+    X, A = _sp(B, tid, xg, Nn), _sp(B, ei, ag, Nn)
+    P, Q = (X, A) if key == "XA" else (A, X)
+    out = B.spspmm(P, 1, Q, 0, aggr, acd=acd, tar_ind=tid).values
+    (out * w.to(DEV)).sum().backward()
+    close(out, ref, 1e-5)
+    close(xg.grad, xr.grad, 2e-5)
+    close(ag.grad, ar.grad, 2e-5)
+
+
 def test_full_size_properties(B):
     """BASELINE-size batch (B=1024 graphs): properties that do not need the oracle --
     linearity of sum, mean*count == sum, max >= mean, plan totals, sortedness."""

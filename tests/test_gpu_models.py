@@ -61,7 +61,9 @@ def test_convs_match_reference_golden(golden):
                                                    ("SSWL", "max", "max", "mean"),
                                                    ("NGNN", "mean", "sum", "max"),
                                                    ("DSSGNN", "sum", "mean", "sum"),
-                                                   ("PPGN", "sum", "mean", "sum")])
+                                                   ("PPGN", "sum", "mean", "sum"),
+                                                   ("I2GNN", "sum", "mean", "sum"),
+                                                   ("I2GNN", "max", "max", "mean")])
 def test_sp_model_matches_oracle_model(conv, aggr, lpool, npool):
     """Whole model, forward + backward, device-built plans: loss and every parameter
     gradient against the CPU oracle model with identical weights."""
@@ -70,7 +72,7 @@ def test_sp_model_matches_oracle_model(conv, aggr, lpool, npool):
     from pygho_b200.hodata.synthetic import make_batch
     from pygho_b200.honn.SpOperator import parse_precomputekey
     torch.manual_seed(0)
-    hb = make_batch(6, seed=3)
+    hb = make_batch(6, seed=3, tuples="i2" if conv == "I2GNN" else "khop")
     kw = dict(conv=conv, num_layer=2, hiddim=32, aggr=aggr, npool=npool, lpool=lpool,
               mlplayer=2, outlayer=2)
     model = SpModel(**kw)
@@ -95,6 +97,145 @@ def test_sp_model_matches_oracle_model(conv, aggr, lpool, npool):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         close(p.grad, ograds[k].grad, 2e-3)
+
+
+def test_i2conv_matches_reference_golden(golden):
+    """I2Conv on 3-D tuples, the 3-D tupleinit (zinc.py:270-273) and the read-out chain
+    OpPoolingSubg3D -> OpPoolingSubg2D (zinc.py:258) against the REAL reference
+    (tests/golden/conv_i2.npz): layer output, read-out, input and parameter gradients."""
+    from pygho_b200 import SparseTensor
+    from pygho_b200.honn import Conv
+    from pygho_b200.honn.TensorOp import OpPoolingSubg2D, OpPoolingSubg3D
+    g = golden("conv_i2")
+    ei, tid, N = T(g["edge_index"]), T(g["tupleid"]), int(g["N"])
+    dd = {k: T(v) for k, v in g.items() if k.endswith("___acd")}
+    for name, aggr, pool in (("I2", "sum", "mean"), ("I2max", "max", "max")):
+        conv = Conv.I2Conv(8, 8, aggr, "SS", dict(MLP))
+        conv.load_state_dict({k[len(name) + 4:]: torch.from_numpy(v) for k, v in g.items()
+                              if k.startswith(name + ".sd.")})
+        conv = conv.to(DEV)
+        lins = [torch.nn.Linear(8, 8) for _ in range(3)]
+        for i, lin in enumerate(lins):
+            lin.load_state_dict({"weight": torch.from_numpy(g[f"{name}.init{i}.weight"]),
+                                 "bias": torch.from_numpy(g[f"{name}.init{i}.bias"])})
+            lin.to(DEV)
+        lpool = torch.nn.Sequential(OpPoolingSubg3D("S", pool), OpPoolingSubg2D("S", pool))
+        A = SparseTensor(ei, T(g["Av"]), (N, N, 8), True)
+        xv = T(g["Xv"]).requires_grad_(True)
+        xn = T(g["xn"]).requires_grad_(True)
+        X = SparseTensor(tid, xv, (N, N, N, 8), True)
+        root = X.unpooling_fromdense1dim(0, lins[0](xn)).values
+        node = X.unpooling_fromdense1dim(1, lins[1](xn)).values
+        third = X.unpooling_fromdense1dim(1, lins[2](xn)).values
+        X = X.tuplewiseapply(lambda val: root * node * third * val)
+        Y = conv(A, X, dd)
+        h = lpool(X.add(Y, True))
+        ((h ** 2).mean() + (Y.values ** 2).mean()).backward()
+        close(Y.values, g[f"{name}.out"], 2e-5)
+        close(h, g[f"{name}.readout"], 2e-5)
+        close(xv.grad, g[f"{name}.gradX"], 1e-4)
+        close(xn.grad, g[f"{name}.gradx"], 1e-4)
+        for k, p in conv.named_parameters():
+            close(p.grad, g[f"{name}.grad.{k}"], 1e-4)
+        for i, lin in enumerate(lins):
+            close(lin.weight.grad, g[f"{name}.init{i}.gweight"], 1e-4)
+            close(lin.bias.grad, g[f"{name}.init{i}.gbias"], 1e-4)
+
+
+@pytest.mark.parametrize("aggr", ("sum", "mean"))
+def test_bench_path_sswl_6x128_matches_oracle_model(aggr):
+    """The configuration bench.py times -- SpModel("SSWL", 6 layers, hidden 128, residual folded
+    into the MLP's last kernel), i.e. the fused SswlAggregate epilogue + lean streaming kernel +
+    residual-in-BatchNorm + EmbeddingGather path (all need d % 128 == 0) -- on a 64-graph batch
+    against the CPU oracle model with identical weights: prediction, loss, every gradient."""
+    from examples.zinc_models import SpModel
+    from pygho_b200.hodata.device import attach_host_plans, sp_datadict
+    from pygho_b200.hodata.synthetic import make_batch
+    from pygho_b200.honn.SpOperator import parse_precomputekey
+    torch.manual_seed(0)
+    hb = make_batch(64, seed=17)
+    kw = dict(conv="SSWL", num_layer=6, hiddim=128, aggr=aggr)
+    model = SpModel(**kw)
+    oracle = MO.OSpModel(**kw)
+    oracle.load_state_dict(copy.deepcopy(model.state_dict()))
+    model = model.to(DEV)
+    keys = parse_precomputekey(model)
+    dd = sp_datadict(hb, DEV, keys)
+    attach_host_plans(hb, dd, keys)
+    g = MO.host_graph_dict(hb, {k + "___acd": torch.from_numpy(v) for k, v in hb.plans.items()})
+    from pygho_b200 import _lib
+    n0 = _lib.launches()
+    pred = model(dd)
+    loss = torch.nn.functional.l1_loss(dd["y"].unsqueeze(-1), pred)
+    loss.backward()
+    assert _lib.launches() - n0 > 100            # the CUDA kernels ran (no silent fallback)
+    opred = oracle(g)
+    oloss = torch.nn.functional.l1_loss(g["y"].unsqueeze(-1), opred)
+    oloss.backward()
+    close(pred, opred, 5e-4)
+    close(loss, oloss, 5e-4)
+    ograds = dict(oracle.named_parameters())
+    for k, p in model.named_parameters():
+        close(p.grad, ograds[k].grad, 5e-3)
+    # running statistics of every BatchNorm were updated identically
+    obuf = dict(oracle.named_buffers())
+    for k, b in model.named_buffers():
+        if b.dtype.is_floating_point:
+            close(b, obuf[k], 1e-4)
+
+
+@pytest.mark.parametrize("algo,tol", [(0, 1.0), (2, 200.0)])
+def test_ppgn_dense_conv_matches_reference_golden(golden, monkeypatch, algo, tol):
+    """PPGNConv DD (mamamm kernels) against the REAL reference on equal-size graphs
+    (tests/golden/conv_dd.npz); exact-fp32 kernel at 5e-5, TF32 tensor-core kernel at 1e-2."""
+    monkeypatch.setenv("PYGHO_B200_MAMAMM_ALGO", str(algo))
+    from pygho_b200 import MaskedTensor
+    from pygho_b200.honn import Conv
+    g = golden("conv_dd")
+    conv = Conv.PPGNConv(8, 8, "sum", "DD", dict(MLP))
+    conv.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")})
+    conv = conv.to(DEV)
+    xd = T(g["X"]).requires_grad_(True)
+    Y = conv(None, MaskedTensor(xd, T(g["mask"])), {})
+    (Y.data ** 2).mean().backward()
+    close(Y.data, g["out"], 5e-5 * tol)
+    close(xd.grad, g["gradX"], 5e-5 * tol)
+    for k, p in conv.named_parameters():
+        close(p.grad, g[f"grad.{k}"], 1e-4 * tol)
+
+
+@pytest.mark.parametrize("algo,tol", [(0, 1.0), (2, 50.0)])
+def test_ma_model_matches_oracle_model(monkeypatch, algo, tol):
+    """Dense PPGN model (example/zinc.py:155-219; bench.py --workload ppgn_dd) on ragged graphs:
+    prediction, loss and every parameter gradient against the CPU oracle model."""
+    monkeypatch.setenv("PYGHO_B200_MAMAMM_ALGO", str(algo))
+    from examples.zinc_models import MaModel
+    from pygho_b200.hodata.device import ma_datadict
+    from pygho_b200.hodata.synthetic import make_batch
+    torch.manual_seed(3)
+    hb = make_batch(7, seed=5)
+    kw = dict(num_layer=2, hiddim=32, npool="sum", lpool="mean", mlplayer=2, outlayer=2)
+    model = MaModel("PPGN", **kw)
+    oracle = MO.OMaModel(**kw)
+    oracle.load_state_dict(copy.deepcopy(model.state_dict()))
+    model = model.to(DEV)
+    dd = ma_datadict(hb, DEV)
+    g = MO.host_dense_dict(hb)
+    assert torch.equal(dd["X"].data.cpu(), g["X"]) and torch.equal(dd["A"].data.cpu(), g["A"])
+    pred = model(dd)
+    loss = torch.nn.functional.l1_loss(dd["y"].unsqueeze(-1), pred)
+    loss.backward()
+    opred = oracle(g)
+    oloss = torch.nn.functional.l1_loss(g["y"].unsqueeze(-1), opred)
+    oloss.backward()
+    close(pred, opred, 1e-4 * tol)
+    close(loss, oloss, 1e-4 * tol)
+    ograds = dict(oracle.named_parameters())
+    for k, p in model.named_parameters():
+        if ograds[k].grad is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        close(p.grad, ograds[k].grad, 2e-3 * tol)
 
 
 def test_sp_model_host_plans_equal_device_plans():

@@ -93,3 +93,32 @@ def test_host_generator_matches_oracle_sampler():
     t, f = H.khop_sampler(gr.edge_index, gr.num_nodes, 3)
     assert np.array_equal(spd[t[0], t[1]], f)
     assert (spd <= 3).sum() == t.shape[1]
+
+
+def test_sr25_like_graphs_are_strongly_regular():
+    """The synthetic cfg4 graphs have the sr25 parameters (25, 12, 5, 6) and the tuple / triple
+    counts SURVEY.md section 8 quotes for sr25; where the reference's dataset is mounted they are
+    isomorphic to members of dataset/sr25/raw/sr251256.g6."""
+    import os
+    from pygho_b200.hodata.synthetic import make_batch, sr25_like_graph
+    rng = np.random.default_rng(0)
+    mats = []
+    for which in (0, 1):
+        g = sr25_like_graph(rng, which=which)
+        A = np.zeros((25, 25), np.int64)
+        A[g.edge_index[0], g.edge_index[1]] = 1
+        assert (A == A.T).all() and (A.sum(0) == 12).all() and g.edge_index.shape[1] == 300
+        A2 = A @ A
+        off = ~np.eye(25, dtype=bool)
+        assert set(A2[(A == 1) & off]) == {5} and set(A2[(A == 0) & off]) == {6}
+        assert g.tupleid.shape[1] == 625 and g.tuplefeat.max() == 2
+        mats.append(A)
+    hb = make_batch(2, seed=1, tuples="i2", shape="sr25")
+    assert hb.tupleid.shape == (3, 2 * 7500) and hb.tuplefeat.shape == (2 * 7500, 2)
+    path = "/root/reference/dataset/sr25/raw/sr251256.g6"
+    if os.path.exists(path):
+        import networkx as nx
+        ref = nx.read_graph6(path)
+        hits = [[i for i, H in enumerate(ref) if nx.is_isomorphic(nx.from_numpy_array(A), H)]
+                for A in mats]
+        assert all(len(h) == 1 for h in hits) and hits[0] != hits[1]

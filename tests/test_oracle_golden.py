@@ -264,6 +264,57 @@ def test_oracle_convs_match_reference(golden):
             close(p.grad.numpy(), g[f"{name}.grad.{k}"], 5e-5)
 
 
+def test_oracle_i2conv_matches_reference(golden):
+    """I2Conv on 3-D tuples + the zinc.py 3-D tupleinit and read-out chain against the real
+    reference (tests/golden/conv_i2.npz): layer output, read-out, input / parameter gradients."""
+    import torch
+    from oracle import model_oracle as MO
+    g = golden("conv_i2")
+    ei, tid, N = torch.from_numpy(g["edge_index"]), torch.from_numpy(g["tupleid"]), int(g["N"])
+    gd = {k: torch.from_numpy(v) for k, v in g.items() if k.endswith("___acd")}
+    for name, aggr, pool in (("I2", "sum", "mean"), ("I2max", "max", "max")):
+        conv = MO.OI2(8, aggr, 2, 0.1)
+        conv.load_state_dict({k[len(name) + 4:]: torch.from_numpy(v) for k, v in g.items()
+                              if k.startswith(name + ".sd.")})
+        lins = [torch.nn.Linear(8, 8) for _ in range(3)]
+        for i, lin in enumerate(lins):
+            lin.load_state_dict({"weight": torch.from_numpy(g[f"{name}.init{i}.weight"]),
+                                 "bias": torch.from_numpy(g[f"{name}.init{i}.bias"])})
+        Av = torch.from_numpy(g["Av"])
+        xv = torch.from_numpy(g["Xv"]).clone().requires_grad_(True)
+        xn = torch.from_numpy(g["xn"]).clone().requires_grad_(True)
+        X = lins[0](xn)[tid[0]] * lins[1](xn)[tid[1]] * lins[2](xn)[tid[1]] * xv
+        Y = conv(Av, X, gd)
+        h = MO.pool3d_to_dense(X + Y, tid, N, pool)
+        ((h ** 2).mean() + (Y ** 2).mean()).backward()
+        close(Y.detach().numpy(), g[f"{name}.out"], 2e-5)
+        close(h.detach().numpy(), g[f"{name}.readout"], 2e-5)
+        close(xv.grad.numpy(), g[f"{name}.gradX"], 5e-5)
+        close(xn.grad.numpy(), g[f"{name}.gradx"], 5e-5)
+        for k, p in conv.named_parameters():
+            close(p.grad.numpy(), g[f"{name}.grad.{k}"], 5e-5)
+        for i, lin in enumerate(lins):
+            close(lin.weight.grad.numpy(), g[f"{name}.init{i}.gweight"], 5e-5)
+            close(lin.bias.grad.numpy(), g[f"{name}.init{i}.gbias"], 5e-5)
+
+
+def test_oracle_ppgn_dense_matches_reference(golden):
+    """Dense (DD) PPGNConv against the real reference on equal-size graphs
+    (tests/golden/conv_dd.npz): output, input gradient, every parameter gradient."""
+    import torch
+    from oracle import model_oracle as MO
+    g = golden("conv_dd")
+    conv = MO.OPPGNDense(8, 2, 0.1)
+    conv.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")})
+    X = torch.from_numpy(g["X"]).clone().requires_grad_(True)
+    out = conv(X, torch.from_numpy(g["mask"]))
+    (out ** 2).mean().backward()
+    close(out.detach().numpy(), g["out"], 2e-5)
+    close(X.grad.numpy(), g["gradX"], 5e-5)
+    for k, p in conv.named_parameters():
+        close(p.grad.numpy(), g[f"grad.{k}"], 5e-5)
+
+
 def test_spmamm_golden(golden):
     """oracle spmamm against the reference's spmamm on the inputs the reference can run
     (scalar features; see tests/golden/make_golden.py::golden_spmamm)."""
