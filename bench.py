@@ -90,6 +90,9 @@ def parse():
     ap.add_argument("--no-stock-gpu", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-static", action="store_true",
+                    help="host-fed path: eager steps on exact-size batches instead of graph "
+                         "replay on capacity-padded batches")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch the resident-batch steps eagerly instead of replaying CUDA graphs")
     ap.add_argument("--syncbn", action="store_true",
@@ -487,7 +490,7 @@ def run_b200(args):
     from pygho_b200 import _lib
     from pygho_b200.dist import FlatGradBucket, broadcast_parameters
     from pygho_b200.hodata.device import (DeferredScalar, DevicePrefetcher, attach_host_plans,
-                                          ma_datadict, sp_datadict)
+                                          ma_datadict, pin_host_batch, sp_datadict)
     from pygho_b200.honn.SpOperator import parse_precomputekey
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -532,14 +535,16 @@ def run_b200(args):
         dds.append(dd)
     if sparse:   # pin the host plans too (they are what the reference's loader would ship)
         for hb in hbs:
-            for v in hb.plans.values():
-                pinned[id(v)] = torch.from_numpy(v).pin_memory()
+            pin_host_batch(hb, pinned)
     h2d_bytes = int(np.mean([hb.nbytes() for hb in hbs]))
 
     def train_step(dd):
         bucket.zero()
-        pred = model(dd)
-        loss = torch.nn.functional.l1_loss(dd["y"].unsqueeze(-1), pred)
+        pred, y = model(dd), dd["y"].unsqueeze(-1)
+        nv = dd.get("num_valid_graphs")           # capacity-padded batch: drop the dummy graph
+        if nv is not None:
+            pred, y = pred[:nv], y[:nv]
+        loss = torch.nn.functional.l1_loss(y, pred)
         loss.backward()
         bucket.allreduce_mean()
         opt.step()
@@ -609,7 +614,29 @@ def run_b200(args):
     if not args.no_e2e:
         reader = DeferredScalar()
         losses = []
-        if sparse:
+        static_ok = sparse and hbs[0].tupleid.shape[0] == 2 and not args.no_graph and not args.no_static
+        e2e_mode = "eager step, threaded side-stream prefetch (DevicePrefetcher)"
+        if static_ok:
+            # Host-fed steps as CUDA-graph replays: the host batches are padded to fixed
+            # capacities at collate time (pygho_b200/static.py), so ONE captured graph per slot
+            # serves every batch; per step the host enqueues the H2D copies + plan regrouping of
+            # the next batch on a side stream and one graph launch.
+            from pygho_b200 import static as ST
+            caps = ST.capacities(hbs, keys)
+            padded = [ST.pad_host_batch(hb, caps, keys) for hb in hbs]
+            for hb in padded:
+                pin_host_batch(hb, pinned)
+            h2d_bytes = int(np.mean([hb.nbytes() for hb in padded]))
+            feeder = ST.StaticFeeder(padded, caps, device, keys, train_step, pinned)
+            e2e_mode = (f"cuda graph replay on capacity-padded batches (2 static slots, capacities "
+                        f"{ {k: v for k, v in caps.items() if len(k) < 3} }), threaded side-stream loader")
+
+            def e2e_step(i):
+                loss = feeder.step()
+                prev = reader.push(loss)                 # loss of the step before this one
+                if prev is not None:
+                    losses.append(prev)
+        elif sparse:
             # every step's inputs come from pinned host memory (reference datadict format incl.
             # the acd plans); the copies + CSR regrouping of batch i+1 are issued on a side
             # stream right after step i has been launched, the loss is read back every step
@@ -627,6 +654,7 @@ def run_b200(args):
                 feeder.advance()                         # next batch's H2D + plans, side stream
         else:
             feeder = None
+            e2e_mode = "eager step, H2D + device-side padding on the compute stream"
 
             def e2e_step(i):
                 dd = ma_datadict(hbs[i % len(hbs)], device, pinned=pinned)   # H2D + device padding
@@ -656,7 +684,7 @@ def run_b200(args):
         assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: every step's loss is read"
         e2e = {"value": glob / (e2e_ms / args.steps * 1e-3), "unit": "graphs/s",
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-               "ms_per_step": e2e_ms / args.steps,
+               "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode,
                "step_ms": {"min": float(np.min(per_step)), "median": float(np.median(per_step)),
                            "max": float(np.max(per_step))}}
         if feeder is not None:

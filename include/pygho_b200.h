@@ -224,26 +224,47 @@ int pgh_masked_fill_f32(const float* data, const uint8_t* mask, int64_t rows, in
 /* BatchNorm1d (training mode, statistics over ALL tuples of the batch) fused with the
  * activation that follows it in the reference MLP block Linear -> BatchNorm -> act
  * (honn/utils.py:46-61, 85-142).  act: 0 identity, 1 SiLU, 2 ReLU.  C % 4 == 0, C <= 1024.
- *   stats : mean[c], rstd[c] = 1/sqrt(biased var + eps); optional running-stat update
- *   fwd   : z = act(gamma * (y - mean) * rstd + beta)
- *   bwd   : dy (gradient w.r.t. the Linear output), dgamma, dbeta and, if dbias != NULL, the
- *           column sums of dy (the Linear bias gradient, mathematically 0 before a BatchNorm)
- * ws: pgh_bn_ws_bytes(rows, C) bytes of scratch for the deterministic two-stage reductions. */
+ *   stats      : mean[c], rstd[c] = 1/sqrt(biased var + eps); optional running-stat update
+ *   fwd        : z = act(gamma * (y - mean) * rstd + beta) (+ residual)
+ *   bwd_reduce : sums = (S1, S2) = (sum dyh, sum dyh * xh) over the rows, dbeta = S1, dgamma = S2
+ *   bwd_apply  : dy = gamma * rstd * (dyh - S1/n - xh * S2/n); dbias = column sums of dy
+ * Every reduction finishes inside its own launch (two-level "last CTA done" ticket, fixed
+ * summation order: deterministic).
+ *   ws       : pgh_bn_ws_bytes(rows, C) bytes of scratch
+ *   tickets  : 64 int32 words, zero before the first use; the kernels leave them zero
+ *   rows_dev : NULL, or a device int32 holding the number of VALID rows (<= rows): the tensors
+ *              are padded to a fixed capacity `rows` (CUDA-graph replay of steps whose batches
+ *              differ in size); pad rows are excluded from all sums, get z = 0 and dy = 0
+ *   accumulate : dgamma / dbeta / dbias += result (gradient buffers of a flat bucket) instead of =
+ * Cross-rank statistics (SyncBN, the single-process semantics of the reference under graph
+ * sharding): stats with local_out != NULL writes the rank-local (mean, M2, count) rows (3, C)
+ * and stops; pgh_bn_sync_finalize_f32 merges the all-gathered (world, 3, C) triples in rank
+ * order (Chan), writes mean / rstd / running stats and inv_n[0] = 1 / total rows.  bwd_reduce's
+ * `sums` are all-reduced (sum) by the caller before bwd_apply, which then takes inv_n. */
 size_t pgh_bn_ws_bytes(int64_t rows, int64_t C);
-int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, float eps, float momentum,
-                     float* mean, float* rstd, float* running_mean, float* running_var, void* ws,
-                     size_t ws_bytes, void* stream);
-int pgh_bn_act_fwd_f32(const float* y, const float* mean, const float* rstd, const float* gamma,
-                       const float* beta, int64_t rows, int64_t C, int act, float* z, void* stream);
-/* fwd with a residual input: z = act(...) + residual (the `X + conv(X)` of example/zinc.py:286
- * folded into the last block of the layer's MLP); residual may be NULL */
+int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, const int32_t* rows_dev, float eps,
+                     float momentum, float* mean, float* rstd, float* running_mean,
+                     float* running_var, float* local_out, void* ws, size_t ws_bytes,
+                     int32_t* tickets, void* stream);
+int pgh_bn_sync_finalize_f32(const float* gathered, int64_t world, int64_t C, float eps,
+                             float momentum, float* mean, float* rstd, float* running_mean,
+                             float* running_var, float* inv_n, void* stream);
+/* residual may be NULL; z = act(...) + residual is the `X + conv(X)` of example/zinc.py:286
+ * folded into the last block of the layer's MLP */
 int pgh_bn_act_res_fwd_f32(const float* y, const float* mean, const float* rstd,
-                           const float* gamma, const float* beta, int64_t rows, int64_t C, int act,
-                           const float* residual, float* z, void* stream);
-int pgh_bn_act_bwd_f32(const float* dz, const float* y, const float* mean, const float* rstd,
-                       const float* gamma, const float* beta, int64_t rows, int64_t C, int act,
-                       float* dy, float* dgamma, float* dbeta, float* dbias, void* ws,
-                       size_t ws_bytes, void* stream);
+                           const float* gamma, const float* beta, int64_t rows, int64_t C,
+                           const int32_t* rows_dev, int act, const float* residual, float* z,
+                           void* stream);
+int pgh_bn_act_bwd_reduce_f32(const float* dz, const float* y, const float* mean, const float* rstd,
+                              const float* gamma, const float* beta, int64_t rows, int64_t C,
+                              const int32_t* rows_dev, int act, float* sums, float* dgamma,
+                              float* dbeta, int accumulate, void* ws, size_t ws_bytes,
+                              int32_t* tickets, void* stream);
+int pgh_bn_act_bwd_apply_f32(const float* dz, const float* y, const float* mean, const float* rstd,
+                             const float* gamma, const float* beta, const float* sums,
+                             const float* inv_n, int64_t rows, int64_t C, const int32_t* rows_dev,
+                             int act, float* dy, float* dbias, int accumulate, void* ws,
+                             size_t ws_bytes, int32_t* tickets, void* stream);
 
 /* ------------------------------------- batch preparation on the device (SURVEY 8f rank 1 + 3) */
 

@@ -53,7 +53,11 @@ for C in (384, 128):
         tune(k, 0)
     m0, r0 = O.bn_stats(ys[0], 1e-5, 0.1, rm.clone(), rv.clone())
     z0 = O.bn_act_fwd(ys[0], m0, r0, gam, bet, 1)
-    dy0, dg0, db0, dbias0 = O.bn_act_bwd(dzs[0], ys[0], m0, r0, gam, bet, 1, True)
+    def bwd(dz, y):
+        sums, dg, db = O.bn_act_bwd_reduce(dz, y, m0, r0, gam, bet, 1, None, None, None)
+        dy, dbias = O.bn_act_bwd_apply(dz, y, m0, r0, gam, bet, sums, None, 1, None, True, None)
+        return dy, dg, db, dbias
+    dy0, dg0, db0, dbias0 = bwd(dzs[0], ys[0])
     print(f"# rows={ROWS} C={C}: fwd {fwd_bytes / 1e6:.0f} MB, bwd {bwd_bytes / 1e6:.0f} MB algorithmic")
     for bps, rev, un in itertools.product((4, 8), (0, 1), (1, 2, 4)):
         tune(2, bps); tune(4, rev); tune(5, un)
@@ -71,7 +75,7 @@ for C in (384, 128):
         tune(2, bps); tune(4, rev); tune(3, un)
 
         def bwd(i):
-            return O.bn_act_bwd(dzs[i % nset], ys[i % nset], m0, r0, gam, bet, 1, True)
+            return bwd(dzs[i % nset], ys[i % nset])
 
         dy, dg, db, dbias = bwd(0)
         err = max(float((dy - dy0).abs().max()), float((dg - dg0).abs().max() / dg0.abs().max()),

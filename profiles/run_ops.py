@@ -199,7 +199,10 @@ for C in (384, 128):
     t, tr = timeit(ours_fwd), timeit(ref_fwd, 5)
     report(f"BN(train)+SiLU fwd ({nX}x{C})", t, tr, 4 * C * nX * 3, "3 passes by design")
     _, m, r = ours_fwd(0)
-    t = timeit(lambda i: ops.bn_act_bwd(dz, ys[i % 3], m, r, gam, bet, 1, True))
+    def _bn_bwd(i):
+        sums, dg, db = ops.bn_act_bwd_reduce(dz, ys[i % 3], m, r, gam, bet, 1, None, None, None)
+        return ops.bn_act_bwd_apply(dz, ys[i % 3], m, r, gam, bet, sums, None, 1, None, True, None)
+    t = timeit(_bn_bwd)
     yr = [y.clone().requires_grad_(True) for y in ys]
 
     def ref_bwd(i):

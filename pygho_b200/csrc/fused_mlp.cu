@@ -13,7 +13,21 @@
 // Thread layout everywhere: a thread owns 4 consecutive channels (one 128-bit lane of the
 // row) and walks rows with stride, so every warp request is a contiguous 512 B piece of a row
 // and per-channel accumulators live in registers.  Partial sums go to a workspace and are
-// combined by a tiny second kernel in a fixed order (deterministic, no atomics).
+// combined IN THE SAME LAUNCH by a two-level "last CTA done" ticket: the last CTA of every group
+// of 16 adds that group's partials in block order, the last group adds the group sums in group
+// order and runs the per-channel epilogue.  Who combines depends on timing, WHAT is added in
+// which order does not: deterministic, no floating-point atomics, no second launch (round 1
+// used a separate *_final kernel per reduction: 51 tiny launches per SSWL+ step).
+//
+// Optional device-side row count (`rows_dev`): the tensors may be padded to a fixed capacity so
+// that a whole training step can be replayed as ONE CUDA graph for batches of different sizes
+// (pygho_b200/static.py).  Rows >= *rows_dev are excluded from every statistic, their forward
+// output is 0 and their gradient is 0.
+//
+// Optional cross-rank statistics (SyncBN): `stats` can emit the rank-local
+// (mean, M2, count) triple instead of finishing; after an all-gather `sync_finalize` merges the
+// ranks with Chan's formula in rank order (bitwise identical on every rank); the backward
+// `reduce` emits the local sums, which are all-reduced before `apply`.
 #include <math.h>
 
 #include "common.cuh"
@@ -30,11 +44,16 @@ constexpr int kBnThreads = 256;
 // reverse walk buys nothing (the L2 does not keep the tail of a streaming pass)
 static int bn_tune(int key, int dflt) { return g_tune[key] > 0 ? g_tune[key] : dflt; }
 
+constexpr int kBnMaxGroups = 63;   // ticket words per launch: 1 + groups <= 64
+
 struct BnGeom {
   int c4;        // float4 columns per row
   int ty;        // row lanes per block
   int blocks;
   long long rows_per_block;
+  int grp;       // partial CTAs per first-level group
+  int ngroups;
+  size_t smem;   // dynamic shared memory of the reduction kernels
 };
 
 static BnGeom bn_geom(int64_t rows, int64_t C) {
@@ -49,7 +68,63 @@ static BnGeom bn_geom(int64_t rows, int64_t C) {
   rpb = (rpb + g.ty - 1) / g.ty * g.ty;
   g.rows_per_block = rpb;
   g.blocks = (int)((rows + rpb - 1) / rpb);
+  g.grp = 16;
+  while ((g.blocks + g.grp - 1) / g.grp > kBnMaxGroups) g.grp *= 2;
+  g.ngroups = (g.blocks + g.grp - 1) / g.grp;
+  const size_t red = (size_t)g.c4 * g.ty * 2 * sizeof(float4);
+  const size_t fin = (size_t)2 * C * sizeof(double);
+  g.smem = red > fin ? red : fin;
   return g;
+}
+
+__device__ __forceinline__ long long valid_rows(long long rows, const int* __restrict__ rows_dev) {
+  if (!rows_dev) return rows;
+  const long long v = (long long)__ldg(rows_dev);
+  return v < rows ? (v < 0 ? 0 : v) : rows;
+}
+
+// Two-level ticketed combine.  Every CTA of the launch has written W floats to
+// part[blockIdx.x * W ..]; exactly one CTA returns true, with fin[0..W) (shared memory, double)
+// holding the sum over all CTAs added in a fixed order.  tickets[0..1+ngroups) must be zero on
+// entry and are zero again on exit (self-resetting: the buffer is reused by the next launch).
+__device__ bool ticketed_combine(const float* part, double* part2, int W, int blocks, int grp,
+                                 int ngroups, int* tickets, double* fin) {
+  __shared__ int s_last;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  const int g = blockIdx.x / grp;
+  const int g_lo = g * grp;
+  const int g_n = min(grp, blocks - g_lo);
+  __threadfence();                       // this CTA's partial is visible before its ticket
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(tickets + 1 + g, 1) == g_n - 1);
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  for (int e = tid; e < W; e += nt) {
+    double a = 0.0;
+    const float* p = part + (size_t)g_lo * W + e;
+#pragma unroll 4
+    for (int b = 0; b < g_n; ++b) a += (double)__ldcg(p + (size_t)b * W);
+    part2[(size_t)g * W + e] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    tickets[1 + g] = 0;
+    s_last = (atomicAdd(tickets, 1) == ngroups - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  for (int e = tid; e < W; e += nt) {
+    double a = 0.0;
+#pragma unroll 4
+    for (int b = 0; b < ngroups; ++b) a += __ldcg(part2 + (size_t)b * W + e);
+    fin[e] = a;
+  }
+  if (tid == 0) tickets[0] = 0;
+  __syncthreads();
+  return true;
 }
 
 template <int ACT>
@@ -86,9 +161,16 @@ __device__ __forceinline__ void reduce_rows(float4& a, float4& b, float4* sm, in
 }
 
 // ---- forward statistics: shifted sums (shift = row 0) to avoid cancellation -------------
-__global__ void bn_stats_partial_kernel(const float* __restrict__ y, long long rows, int C,
-                                        long long rows_per_block, float* __restrict__ part) {
+// local_out != NULL (SyncBN): emit the rank-local (mean, M2, count) rows instead of finishing.
+__global__ void bn_stats_kernel(const float* __restrict__ y, long long rows_cap, int C,
+                                const int* __restrict__ rows_dev, long long rows_per_block,
+                                float* __restrict__ part, double* __restrict__ part2, int blocks,
+                                int grp, int ngroups, int* __restrict__ tickets, float eps,
+                                float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                                float* __restrict__ running_mean, float* __restrict__ running_var,
+                                float* __restrict__ local_out) {
   extern __shared__ float4 sm[];
+  const long long rows = valid_rows(rows_cap, rows_dev);
   const int tx = threadIdx.x, c4 = blockDim.x, ty_n = blockDim.y;
   const float4 shift = __ldg(reinterpret_cast<const float4*>(y) + tx);
   const long long r0 = (long long)blockIdx.x * rows_per_block;
@@ -108,67 +190,78 @@ __global__ void bn_stats_partial_kernel(const float* __restrict__ y, long long r
     p[tx] = s;
     p[c4 + tx] = q;
   }
-}
-
-// Second stage of every reduction: block = 32 channels x 32 partial lanes; lane ty sums the
-// partials ty, ty+32, ... in double, then the 32 lanes are combined in a fixed order.
-__device__ __forceinline__ void combine_partials(const float* __restrict__ part, int blocks,
-                                                 size_t block_stride, int off0, int off1, int c,
-                                                 bool ok, double& s, double& q) {
-  __shared__ double sm[2][32][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  double a = 0.0, b2 = 0.0;
-  if (ok)
-    for (int b = ty; b < blocks; b += 32) {
-      a += (double)part[(size_t)b * block_stride + off0 + c];
-      if (off1 >= 0) b2 += (double)part[(size_t)b * block_stride + off1 + c];
-    }
-  sm[0][ty][tx] = a;
-  sm[1][ty][tx] = b2;
-  __syncthreads();
-  s = 0.0;
-  q = 0.0;
-  if (ty == 0)
-    for (int t = 0; t < 32; ++t) { s += sm[0][t][tx]; q += sm[1][t][tx]; }
-}
-
-__global__ void bn_stats_final_kernel(const float* __restrict__ y, const float* __restrict__ part,
-                                      int blocks, long long rows, int C, float eps, float momentum,
-                                      float* __restrict__ mean, float* __restrict__ rstd,
-                                      float* __restrict__ running_mean,
-                                      float* __restrict__ running_var) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double s, q;
-  combine_partials(part, blocks, (size_t)2 * C, 0, C, c, c < C, s, q);
-  if (threadIdx.y != 0 || c >= C) return;
+  double* fin = reinterpret_cast<double*>(sm);
+  if (!ticketed_combine(part, part2, 2 * C, blocks, grp, ngroups, tickets, fin)) return;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
   const double n = (double)rows;
-  const double ms = s / n;                       // mean of (y - shift)
-  double var = q / n - ms * ms;                  // biased variance
-  if (var < 0.0) var = 0.0;
-  const float m = (float)(ms + (double)y[c]);
-  mean[c] = m;
+  for (int c = tid; c < C; c += nt) {
+    const double sc = fin[c], qc = fin[C + c];
+    const double ms = n > 0.0 ? sc / n : 0.0;              // mean of (y - shift)
+    const double m = n > 0.0 ? ms + (double)y[c] : 0.0;
+    double m2 = qc - sc * ms;                               // sum of squared deviations
+    if (m2 < 0.0) m2 = 0.0;
+    if (local_out) {
+      local_out[c] = (float)m;
+      local_out[C + c] = (float)m2;
+      local_out[2 * C + c] = (float)n;
+      continue;
+    }
+    const double var = n > 0.0 ? m2 / n : 0.0;              // biased variance
+    mean[c] = (float)m;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      const double unbiased = n > 1.0 ? m2 / (n - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+}
+
+// SyncBN: merge the (mean, M2, count) triples of `world` ranks (gathered: (world, 3, C)) with
+// Chan's pairwise formula in rank order; every rank computes the same bits.
+__global__ void bn_sync_finalize_kernel(const float* __restrict__ gathered, int world, int C,
+                                        float eps, float momentum, float* __restrict__ mean,
+                                        float* __restrict__ rstd, float* __restrict__ running_mean,
+                                        float* __restrict__ running_var, float* __restrict__ inv_n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double n = 0.0, m = 0.0, m2 = 0.0;
+  for (int r = 0; r < world; ++r) {
+    const float* g = gathered + (size_t)r * 3 * C;
+    const double nb = (double)g[2 * C + c];
+    if (nb <= 0.0) continue;
+    const double mb = (double)g[c], m2b = (double)g[C + c];
+    const double tot = n + nb, delta = mb - m;
+    m += delta * (nb / tot);
+    m2 += m2b + delta * delta * (n * nb / tot);
+    n = tot;
+  }
+  const double var = n > 0.0 ? m2 / n : 0.0;
+  mean[c] = (float)m;
   rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
   if (running_mean) {
-    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+    const double unbiased = n > 1.0 ? m2 / (n - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
   }
+  if (c == 0 && inv_n) inv_n[0] = n > 0.0 ? (float)(1.0 / n) : 0.f;
 }
 
 // ---- forward apply ------------------------------------------------------------------------
 template <int ACT, int UN>
 __global__ void bn_act_fwd_kernel(const float4* __restrict__ y, const float4* __restrict__ mean,
                                   const float4* __restrict__ rstd, const float4* __restrict__ gamma,
-                                  const float4* __restrict__ beta, long long n4, int c4, int rev,
+                                  const float4* __restrict__ beta, long long n4_cap, int c4,
+                                  const int* __restrict__ rows_dev,
                                   const float4* __restrict__ residual, float4* __restrict__ z) {
+  const long long n4 = valid_rows(n4_cap / c4, rows_dev) * c4;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UN) {
     float4 v[UN], res[UN];
     long long idx[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const long long i = min(i0 + u * stride, n4 - 1);      // clamped: loads are unconditional
-      idx[u] = rev ? n4 - 1 - i : i;
+      idx[u] = min(i0 + u * stride, n4 - 1);                 // clamped: loads are unconditional
       v[u] = __ldg(y + idx[u]);
       if (residual) res[u] = __ldg(residual + idx[u]);
     }
@@ -188,16 +281,24 @@ __global__ void bn_act_fwd_kernel(const float4* __restrict__ y, const float4* __
       z[idx[u]] = o;
     }
   }
+  // padded rows (static-capacity tensors): defined, finite output
+  for (long long i = n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_cap; i += stride)
+    z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// ---- backward reduce: sum dyh and sum dyh * xh -------------------------------------------
+// ---- backward reduce: S1 = sum dyh, S2 = sum dyh * xh; epilogue writes dbeta / dgamma --------
 template <int ACT, int UN>
 __global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y,
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                         long long rows, int C, long long rows_per_block,
-                                         float* __restrict__ part) {
+                                         long long rows_cap, int C, const int* __restrict__ rows_dev,
+                                         long long rows_per_block, float* __restrict__ part,
+                                         double* __restrict__ part2, int blocks, int grp, int ngroups,
+                                         int* __restrict__ tickets, float* __restrict__ sums,
+                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                         int accumulate) {
   extern __shared__ float4 sm[];
+  const long long rows = valid_rows(rows_cap, rows_dev);
   const int tx = threadIdx.x, c4 = blockDim.x, ty_n = blockDim.y;
   const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + tx);
   const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd) + tx);
@@ -233,42 +334,45 @@ __global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const flo
     p[tx] = s;
     p[c4 + tx] = q;
   }
-}
-
-// writes dbeta = S1, dgamma = S2 and the per-channel means used by the apply pass
-__global__ void bn_bwd_final_kernel(const float* __restrict__ part, int blocks, long long rows, int C,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                    float* __restrict__ m1, float* __restrict__ m2) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double s, q;
-  combine_partials(part, blocks, (size_t)2 * C, 0, C, c, c < C, s, q);
-  if (threadIdx.y != 0 || c >= C) return;
-  if (dbeta) dbeta[c] = (float)s;
-  if (dgamma) dgamma[c] = (float)q;
-  m1[c] = (float)(s / (double)rows);
-  m2[c] = (float)(q / (double)rows);
+  double* fin = reinterpret_cast<double*>(sm);
+  if (!ticketed_combine(part, part2, 2 * C, blocks, grp, ngroups, tickets, fin)) return;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  for (int c = tid; c < C; c += nt) {
+    const float s1 = (float)fin[c], s2 = (float)fin[C + c];
+    sums[c] = s1;
+    sums[C + c] = s2;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + s1 : s1;
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + s2 : s2;
+  }
 }
 
 // ---- backward apply: dy and the column sums of dy (the Linear bias gradient) ------------------
+// sums = (S1, S2) over ALL rows of the statistics (all ranks under SyncBN); inv_n = 1 / that
+// row count (device scalar) or NULL = 1 / this tensor's valid rows.
 template <int ACT, int UN>
 __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y,
                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                        const float* __restrict__ m1, const float* __restrict__ m2,
-                                        long long rows, int C, long long rows_per_block, int rev,
-                                        float* __restrict__ dy, float* __restrict__ part) {
+                                        const float* __restrict__ sums, const float* __restrict__ inv_n,
+                                        long long rows_cap, int C, const int* __restrict__ rows_dev,
+                                        long long rows_per_block, float* __restrict__ dy,
+                                        float* __restrict__ part, double* __restrict__ part2,
+                                        int blocks, int grp, int ngroups, int* __restrict__ tickets,
+                                        float* __restrict__ dbias, int accumulate) {
   extern __shared__ float4 sm[];
+  const long long rows = valid_rows(rows_cap, rows_dev);
   const int tx = threadIdx.x, c4 = blockDim.x, ty_n = blockDim.y;
   const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + tx);
   const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd) + tx);
   const float4 g = gamma ? __ldg(reinterpret_cast<const float4*>(gamma) + tx) : make_float4(1.f, 1.f, 1.f, 1.f);
   const float4 bt = beta ? __ldg(reinterpret_cast<const float4*>(beta) + tx) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 a1 = __ldg(reinterpret_cast<const float4*>(m1) + tx);
-  const float4 a2 = __ldg(reinterpret_cast<const float4*>(m2) + tx);
+  const float in = inv_n ? __ldg(inv_n) : (rows > 0 ? 1.f / (float)rows : 0.f);
+  float4 a1 = __ldcg(reinterpret_cast<const float4*>(sums) + tx);
+  float4 a2 = __ldcg(reinterpret_cast<const float4*>(sums + C) + tx);
+  a1 = make_float4(a1.x * in, a1.y * in, a1.z * in, a1.w * in);
+  a2 = make_float4(a2.x * in, a2.y * in, a2.z * in, a2.w * in);
   const float4 sc = make_float4(g.x * rs.x, g.y * rs.y, g.z * rs.z, g.w * rs.w);
-  // rev: CTA 0 takes the LAST row slab (the rows the reduce pass touched most recently)
-  const long long slab = rev ? (long long)(gridDim.x - 1 - blockIdx.x) : (long long)blockIdx.x;
-  const long long r0 = slab * rows_per_block;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), unused = s;
   const float4* yb = reinterpret_cast<const float4*>(y) + tx;
@@ -299,18 +403,18 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const floa
       s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
     }
   }
-  if (part) {
-    reduce_rows(s, unused, sm, c4, ty_n);
-    if (threadIdx.y == 0) reinterpret_cast<float4*>(part + (size_t)slab * C)[tx] = s;
+  // padded rows of this CTA's slab: zero gradient
+  if (rows < rows_cap) {
+    const long long p0 = max(r0, rows), p1 = min(rows_cap, r0 + rows_per_block);
+    for (long long r = p0 + threadIdx.y; r < p1; r += ty_n) ob[r * c4] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-}
-
-__global__ void colsum_final_kernel(const float* __restrict__ part, int blocks, int C,
-                                    float* __restrict__ out) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double s, q;
-  combine_partials(part, blocks, (size_t)C, 0, -1, c, c < C, s, q);
-  if (threadIdx.y == 0 && c < C) out[c] = (float)s;
+  if (!dbias) return;
+  reduce_rows(s, unused, sm, c4, ty_n);
+  if (threadIdx.y == 0) reinterpret_cast<float4*>(part + (size_t)blockIdx.x * C)[tx] = s;
+  double* fin = reinterpret_cast<double*>(sm);
+  if (!ticketed_combine(part, part2, C, blocks, grp, ngroups, tickets, fin)) return;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  for (int c = tid; c < C; c += nt) dbias[c] = accumulate ? dbias[c] + (float)fin[c] : (float)fin[c];
 }
 
 static bool bn_ok(int64_t rows, int64_t C) {
@@ -324,30 +428,44 @@ using namespace pgh;
 extern "C" size_t pgh_bn_ws_bytes(int64_t rows, int64_t C) {
   if (!bn_ok(rows, C)) return 256;
   const BnGeom g = bn_geom(rows, C);
-  return (size_t)g.blocks * 2 * C * sizeof(float) + 2 * C * sizeof(float) + 256;
+  return (size_t)g.blocks * 2 * C * sizeof(float) + 256 + (size_t)g.ngroups * 2 * C * sizeof(double);
 }
 
-extern "C" int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, float eps, float momentum,
-                                float* mean, float* rstd, float* running_mean, float* running_var,
-                                void* ws, size_t ws_bytes, void* stream) {
-  if (!y || !mean || !rstd || !ws) return arg_error("bn_stats: null pointer");
+static double* bn_part2(void* ws, const BnGeom& g, int64_t C) {
+  size_t off = ((size_t)g.blocks * 2 * C * sizeof(float) + 255) & ~(size_t)255;
+  return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + off);
+}
+
+extern "C" int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, const int32_t* rows_dev,
+                                float eps, float momentum, float* mean, float* rstd,
+                                float* running_mean, float* running_var, float* local_out,
+                                void* ws, size_t ws_bytes, int32_t* tickets, void* stream) {
+  if (!y || !ws || !tickets || (!local_out && (!mean || !rstd))) return arg_error("bn_stats: null pointer");
   if (!bn_ok(rows, C)) return arg_error("bn_stats: need rows > 0, C % 4 == 0, C <= 1024");
   if ((reinterpret_cast<uintptr_t>(y) & 15)) return arg_error("bn_stats: y must be 16-byte aligned");
   const BnGeom g = bn_geom(rows, C);
   if (ws_bytes < pgh_bn_ws_bytes(rows, C)) return arg_error("bn_stats: workspace too small");
-  cudaStream_t s = as_stream(stream);
-  float* part = reinterpret_cast<float*>(ws);
-  const size_t smem = (size_t)g.c4 * g.ty * 2 * sizeof(float4);
-  bn_stats_partial_kernel<<<g.blocks, dim3(g.c4, g.ty), smem, s>>>(y, rows, (int)C, g.rows_per_block, part);
-  bn_stats_final_kernel<<<blocks_for(C, 32), dim3(32, 32), 0, s>>>(y, part, g.blocks, rows, (int)C, eps, momentum,
-                                                            mean, rstd, running_mean, running_var);
+  bn_stats_kernel<<<g.blocks, dim3(g.c4, g.ty), g.smem, as_stream(stream)>>>(
+      y, rows, (int)C, rows_dev, g.rows_per_block, reinterpret_cast<float*>(ws), bn_part2(ws, g, C),
+      g.blocks, g.grp, g.ngroups, tickets, eps, momentum, mean, rstd, running_mean, running_var,
+      local_out);
   return check_launch("bn_stats");
+}
+
+extern "C" int pgh_bn_sync_finalize_f32(const float* gathered, int64_t world, int64_t C, float eps,
+                                        float momentum, float* mean, float* rstd,
+                                        float* running_mean, float* running_var, float* inv_n,
+                                        void* stream) {
+  if (!gathered || !mean || !rstd || world < 1 || C < 1) return arg_error("bn_sync_finalize: arguments");
+  bn_sync_finalize_kernel<<<blocks_for(C, 128), 128, 0, as_stream(stream)>>>(
+      gathered, (int)world, (int)C, eps, momentum, mean, rstd, running_mean, running_var, inv_n);
+  return check_launch("bn_sync_finalize");
 }
 
 extern "C" int pgh_bn_act_res_fwd_f32(const float* y, const float* mean, const float* rstd,
                                       const float* gamma, const float* beta, int64_t rows,
-                                      int64_t C, int act, const float* residual, float* z,
-                                      void* stream) {
+                                      int64_t C, const int32_t* rows_dev, int act,
+                                      const float* residual, float* z, void* stream) {
   if (!y || !mean || !rstd || !z) return arg_error("bn_act_fwd: null pointer");
   if (!bn_ok(rows, C)) return arg_error("bn_act_fwd: need rows > 0, C % 4 == 0, C <= 1024");
   if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z) |
@@ -357,10 +475,9 @@ extern "C" int pgh_bn_act_res_fwd_f32(const float* y, const float* mean, const f
   long long nb = (n4 + 255) / 256;
   if (nb > 148 * 16) nb = 148 * 16;
   cudaStream_t s = as_stream(stream);
-  const int rev = bn_tune(4, 0) == 1;
 #define PGH_FWD_U(A, U) bn_act_fwd_kernel<A, U><<<(unsigned)nb, 256, 0, s>>>(                        \
       (const float4*)y, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,             \
-      (const float4*)beta, n4, (int)(C / 4), rev, (const float4*)residual, (float4*)z)
+      (const float4*)beta, n4, (int)(C / 4), rows_dev, (const float4*)residual, (float4*)z)
 #define PGH_FWD(A)                                                                                   \
   do {                                                                                               \
     const int un_ = bn_tune(5, 2);                                                                   \
@@ -373,45 +490,62 @@ extern "C" int pgh_bn_act_res_fwd_f32(const float* y, const float* mean, const f
   return check_launch("bn_act_fwd");
 }
 
-extern "C" int pgh_bn_act_fwd_f32(const float* y, const float* mean, const float* rstd,
-                                  const float* gamma, const float* beta, int64_t rows, int64_t C,
-                                  int act, float* z, void* stream) {
-  return pgh_bn_act_res_fwd_f32(y, mean, rstd, gamma, beta, rows, C, act, nullptr, z, stream);
+extern "C" int pgh_bn_act_bwd_reduce_f32(const float* dz, const float* y, const float* mean,
+                                         const float* rstd, const float* gamma, const float* beta,
+                                         int64_t rows, int64_t C, const int32_t* rows_dev, int act,
+                                         float* sums, float* dgamma, float* dbeta, int accumulate,
+                                         void* ws, size_t ws_bytes, int32_t* tickets, void* stream) {
+  if (!dz || !y || !mean || !rstd || !sums || !ws || !tickets) return arg_error("bn_act_bwd_reduce: null pointer");
+  if (!bn_ok(rows, C)) return arg_error("bn_act_bwd_reduce: need rows > 0, C % 4 == 0, C <= 1024");
+  if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dz)) & 15)
+    return arg_error("bn_act_bwd_reduce: tensors must be 16-byte aligned");
+  if (act < 0 || act > 2) return arg_error("bn_act_bwd_reduce: act");
+  const BnGeom g = bn_geom(rows, C);
+  if (ws_bytes < pgh_bn_ws_bytes(rows, C)) return arg_error("bn_act_bwd_reduce: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  const dim3 blk(g.c4, g.ty);
+#define PGH_RED_U(A, U)                                                                              \
+  bn_act_bwd_reduce_kernel<A, U><<<g.blocks, blk, g.smem, s>>>(                                      \
+      dz, y, mean, rstd, gamma, beta, rows, (int)C, rows_dev, g.rows_per_block,                      \
+      reinterpret_cast<float*>(ws), bn_part2(ws, g, C), g.blocks, g.grp, g.ngroups, tickets, sums,   \
+      dgamma, dbeta, accumulate)
+#define PGH_RED(A)                                                                                   \
+  do {                                                                                               \
+    if (bn_tune(3, 2) >= 4) { PGH_RED_U(A, 4); } else { PGH_RED_U(A, 2); }                           \
+  } while (0)
+  if (act == 1) { PGH_RED(1); } else if (act == 2) { PGH_RED(2); } else { PGH_RED(0); }
+#undef PGH_RED_U
+#undef PGH_RED
+  return check_launch("bn_act_bwd_reduce");
 }
 
-extern "C" int pgh_bn_act_bwd_f32(const float* dz, const float* y, const float* mean, const float* rstd,
-                                  const float* gamma, const float* beta, int64_t rows, int64_t C,
-                                  int act, float* dy, float* dgamma, float* dbeta, float* dbias,
-                                  void* ws, size_t ws_bytes, void* stream) {
-  if (!dz || !y || !mean || !rstd || !dy || !ws) return arg_error("bn_act_bwd: null pointer");
-  if (!bn_ok(rows, C)) return arg_error("bn_act_bwd: need rows > 0, C % 4 == 0, C <= 1024");
-  if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dy)) & 15)
-    return arg_error("bn_act_bwd: tensors must be 16-byte aligned");
-  if (act < 0 || act > 2) return arg_error("bn_act_bwd: act");
+extern "C" int pgh_bn_act_bwd_apply_f32(const float* dz, const float* y, const float* mean,
+                                        const float* rstd, const float* gamma, const float* beta,
+                                        const float* sums, const float* inv_n, int64_t rows,
+                                        int64_t C, const int32_t* rows_dev, int act, float* dy,
+                                        float* dbias, int accumulate, void* ws, size_t ws_bytes,
+                                        int32_t* tickets, void* stream) {
+  if (!dz || !y || !mean || !rstd || !sums || !dy || !ws || !tickets) return arg_error("bn_act_bwd_apply: null pointer");
+  if (!bn_ok(rows, C)) return arg_error("bn_act_bwd_apply: need rows > 0, C % 4 == 0, C <= 1024");
+  if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dy) |
+       reinterpret_cast<uintptr_t>(sums)) & 15)
+    return arg_error("bn_act_bwd_apply: tensors must be 16-byte aligned");
+  if (act < 0 || act > 2) return arg_error("bn_act_bwd_apply: act");
   const BnGeom g = bn_geom(rows, C);
-  if (ws_bytes < pgh_bn_ws_bytes(rows, C)) return arg_error("bn_act_bwd: workspace too small");
+  if (ws_bytes < pgh_bn_ws_bytes(rows, C)) return arg_error("bn_act_bwd_apply: workspace too small");
   cudaStream_t s = as_stream(stream);
-  float* part = reinterpret_cast<float*>(ws);
-  float* m1 = part + (size_t)g.blocks * 2 * C;
-  float* m2 = m1 + C;
-  const size_t smem = (size_t)g.c4 * g.ty * 2 * sizeof(float4);
   const dim3 blk(g.c4, g.ty);
-  const int rev = bn_tune(4, 0) == 1;
-#define PGH_BWD_U(A, U)                                                                              \
-  bn_act_bwd_reduce_kernel<A, U><<<g.blocks, blk, smem, s>>>(dz, y, mean, rstd, gamma, beta, rows,  \
-                                                              (int)C, g.rows_per_block, part);       \
-  bn_bwd_final_kernel<<<blocks_for(C, 32), dim3(32, 32), 0, s>>>(part, g.blocks, rows, (int)C, dgamma,      \
-                                                          dbeta, m1, m2);                            \
-  bn_act_bwd_apply_kernel<A, U><<<g.blocks, blk, smem, s>>>(dz, y, mean, rstd, gamma, beta, m1, m2, \
-                                                             rows, (int)C, g.rows_per_block, rev,    \
-                                                             dy, dbias ? part : nullptr)
-#define PGH_BWD(A)                                                                                   \
+#define PGH_APP_U(A, U)                                                                              \
+  bn_act_bwd_apply_kernel<A, U><<<g.blocks, blk, g.smem, s>>>(                                       \
+      dz, y, mean, rstd, gamma, beta, sums, inv_n, rows, (int)C, rows_dev, g.rows_per_block, dy,     \
+      reinterpret_cast<float*>(ws), bn_part2(ws, g, C), g.blocks, g.grp, g.ngroups, tickets, dbias,  \
+      accumulate)
+#define PGH_APP(A)                                                                                   \
   do {                                                                                               \
-    if (bn_tune(3, 2) >= 4) { PGH_BWD_U(A, 4); } else { PGH_BWD_U(A, 2); }                           \
+    if (bn_tune(3, 2) >= 4) { PGH_APP_U(A, 4); } else { PGH_APP_U(A, 2); }                           \
   } while (0)
-  if (act == 1) { PGH_BWD(1); } else if (act == 2) { PGH_BWD(2); } else { PGH_BWD(0); }
-#undef PGH_BWD_U
-#undef PGH_BWD
-  if (dbias) colsum_final_kernel<<<blocks_for(C, 32), dim3(32, 32), 0, s>>>(part, g.blocks, (int)C, dbias);
-  return check_launch("bn_act_bwd");
+  if (act == 1) { PGH_APP(1); } else if (act == 2) { PGH_APP(2); } else { PGH_APP(0); }
+#undef PGH_APP_U
+#undef PGH_APP
+  return check_launch("bn_act_bwd_apply");
 }

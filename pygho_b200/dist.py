@@ -73,3 +73,27 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> N
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+
+
+def enable_sync_batchnorm(module: torch.nn.Module, group=None) -> int:
+    """Cross-rank BatchNorm statistics for every fused Linear-BatchNorm-activation block of
+    ``module`` (reference semantics: ``honn/utils.py:46-61`` normalises over ALL tuples of the
+    batch; under graph sharding that means the tuples of all ranks -- SURVEY.md Q11).  The fused
+    block then all-gathers the per-rank (mean, M2, count) triples forward and all-reduces the
+    two backward sums (csrc/fused_mlp.cu), which makes N-rank training on a sharded batch equal
+    to single-process training on the whole batch.  Returns the number of layers switched."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    grp = group if group is not None else dist.group.WORLD
+    n = 0
+    for m in module.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m._pgh_sync_group = grp
+            n += 1
+    return n
+
+
+def disable_sync_batchnorm(module: torch.nn.Module) -> None:
+    for m in module.modules():
+        if hasattr(m, "_pgh_sync_group"):
+            del m._pgh_sync_group

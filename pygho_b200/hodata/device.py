@@ -33,15 +33,28 @@ def parse_key(key: str):
     return op0, op1, int(dim1), op2, int(dim2)
 
 
-def _h2d(arr: np.ndarray, device, pinned: Optional[Dict[int, torch.Tensor]] = None):
+def _h2d(arr: np.ndarray, device, pinned: Optional[Dict[int, tuple]] = None):
+    """Asynchronous copy of a host array; ``pinned`` caches the page-locked staging copy per
+    array OBJECT (the entry keeps the array alive, so a recycled id() can never alias it)."""
     t = torch.from_numpy(arr)
     if pinned is not None:
-        p = pinned.get(id(arr))
-        if p is None:
-            p = t.pin_memory()
-            pinned[id(arr)] = p
-        t = p
+        hit = pinned.get(id(arr))
+        if hit is None or hit[0] is not arr:
+            hit = (arr, t.pin_memory())
+            pinned[id(arr)] = hit
+        t = hit[1]
     return t.to(device, non_blocking=True)
+
+
+def pin_host_batch(hb: HostBatch, pinned: dict) -> None:
+    """Page-lock every array of a host batch (incl. its plans) ahead of time."""
+    arrs = [hb.x, hb.edge_index, hb.edge_attr, hb.tupleid, hb.tuplefeat, hb.batch, hb.y]
+    arrs += list(hb.plans.values())
+    if getattr(hb, "valid", None) is not None:
+        arrs.append(hb.valid)
+    for a in arrs:
+        if id(a) not in pinned or pinned[id(a)][0] is not a:
+            pinned[id(a)] = (a, torch.from_numpy(a).pin_memory())
 
 
 def sp_datadict(hb: HostBatch, device, keys: Iterable[str] = (),
@@ -61,6 +74,8 @@ def sp_datadict(hb: HostBatch, device, keys: Iterable[str] = (),
         "num_graphs": hb.num_graphs,
         "y": _h2d(hb.y, device, pinned),
     }
+    if getattr(hb, "valid", None) is not None:     # capacity-padded batch (pygho_b200/static.py)
+        dd["valid_rows"] = _h2d(hb.valid, device, pinned)
     for key in keys:
         name = key + KEYSEP + "acd"
         if key in hb.plans:
@@ -184,6 +199,10 @@ class DevicePrefetcher:
         self._submit()
 
     def next(self) -> dict:
+        """``get()`` + ``advance()`` for simple loops.  Safe without any caller-side fence: it
+        first waits (on the host) for everything queued on the compute stream so far -- i.e. for
+        the step that consumed the batch whose buffers ``advance()`` is about to recycle."""
+        torch.cuda.current_stream(self.device).synchronize()
         dd = self.get()
         self.advance()
         return dd

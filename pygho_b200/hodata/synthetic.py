@@ -55,6 +55,8 @@ class HostBatch:
     edge_ptr: np.ndarray     # (B+1,)
     tuple_ptr: np.ndarray    # (B+1,)
     plans: Dict[str, np.ndarray] = field(default_factory=dict)
+    # capacity-padded batches (pygho_b200/static.py): valid (tuples, nodes, graphs), int32
+    valid: Optional[np.ndarray] = None
 
     def nbytes(self) -> int:
         tot = 0
@@ -63,6 +65,8 @@ class HostBatch:
             tot += v.nbytes
         for v in self.plans.values():
             tot += v.nbytes
+        if self.valid is not None:
+            tot += self.valid.nbytes
         return tot
 
 

@@ -125,6 +125,7 @@ class MLP(nn.Module):
             return out if residual is None else out + residual
         # Linear -> BatchNorm(train) -> SiLU/ReLU blocks go through the fused kernels
         # (pygho_b200/csrc/fused_mlp.cu); anything else runs module by module.
+        from .. import static
         from ..ops import ACT_CODE, LinearBNAct
         mods = list(self.lins)
         shape = x.shape
@@ -141,7 +142,9 @@ class MLP(nn.Module):
                 if residual is not None and i + 3 == len(mods):
                     res, residual = residual.reshape(-1, residual.shape[-1]), None
                 h = LinearBNAct.apply(h, m.weight, m.bias, bn.weight, bn.bias, bn.running_mean,
-                                      bn.running_var, bn.momentum, bn.eps, ACT_CODE[act], res)
+                                      bn.running_var, bn.momentum, bn.eps, ACT_CODE[act], res,
+                                      static.rows_dev_for(h.shape[0]),
+                                      getattr(bn, "_pgh_sync_group", None))
                 i += 3
             else:
                 h = m(h)

@@ -372,24 +372,46 @@ def _masked_fill_fake(data, mask, value):
 
 
 # ---------------------------------------------------------------- fused BatchNorm + act
-_LIB.define("bn_stats(Tensor y, float eps, float momentum, Tensor? running_mean, "
-            "Tensor? running_var) -> (Tensor, Tensor)")
-
-
 def _bn_ws(rows, C, device):
     n = int(_lib.load().pgh_bn_ws_bytes(int(rows), int(C)))
     return torch.empty((n,), dtype=torch.uint8, device=device)
 
 
-def _bn_stats_cuda(y, eps, momentum, running_mean, running_var):
+_TICKETS = {}
+
+
+def _tickets(device) -> int:
+    """Device address of 64 zeroed int32 ticket words for one launch of a ticketed reduction
+    (csrc/fused_mlp.cu).  The kernels leave them zero; 64 slots are handed out round-robin so
+    that launches in flight on different streams never share a slot."""
+    ent = _TICKETS.get(device)
+    if ent is None:
+        ent = [torch.zeros((64 * 64,), dtype=torch.int32, device=device), 0]
+        _TICKETS[device] = ent
+    ent[1] = (ent[1] + 1) & 63
+    return ent[0].data_ptr() + ent[1] * 64 * 4
+
+
+def _rows_dev(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is not None and (t.dtype != torch.int32 or t.numel() != 1 or not t.is_cuda):
+        raise TypeError("rows_dev must be a one-element int32 CUDA tensor")
+    return t
+
+
+_LIB.define("bn_stats(Tensor y, float eps, float momentum, Tensor? running_mean, "
+            "Tensor? running_var, Tensor? rows_dev=None) -> (Tensor, Tensor)")
+
+
+def _bn_stats_cuda(y, eps, momentum, running_mean, running_var, rows_dev=None):
     y = _f32c(y)
     rows, C = y.shape
     mean = torch.empty((C,), dtype=torch.float32, device=y.device)
     rstd = torch.empty_like(mean)
     ws = _bn_ws(rows, C, y.device)
-    call("pgh_bn_stats_f32", ptr(y), rows, C, float(eps), float(momentum), ptr(mean), ptr(rstd),
-         ptr(running_mean), ptr(running_var), ptr(ws), ws.numel(), stream_ptr(y.device))
-    _lib.count_launch(2)
+    call("pgh_bn_stats_f32", ptr(y), rows, C, ptr(_rows_dev(rows_dev)), float(eps), float(momentum),
+         ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var), None, ptr(ws), ws.numel(),
+         _tickets(y.device), stream_ptr(y.device))
+    _lib.count_launch()
     return mean, rstd
 
 
@@ -397,22 +419,73 @@ _LIB.impl("bn_stats", _bn_stats_cuda, "CUDA")
 
 
 @torch.library.register_fake("pygho_b200::bn_stats")
-def _bn_stats_fake(y, eps, momentum, running_mean, running_var):
+def _bn_stats_fake(y, eps, momentum, running_mean, running_var, rows_dev=None):
     return y.new_empty((y.shape[1],)), y.new_empty((y.shape[1],))
 
 
+_LIB.define("bn_stats_local(Tensor y, Tensor? rows_dev=None) -> Tensor")
+
+
+def _bn_stats_local_cuda(y, rows_dev=None):
+    """Rank-local (mean, M2, count) rows (3, C) for cross-rank statistics (SyncBN)."""
+    y = _f32c(y)
+    rows, C = y.shape
+    local = torch.empty((3, C), dtype=torch.float32, device=y.device)
+    ws = _bn_ws(rows, C, y.device)
+    call("pgh_bn_stats_f32", ptr(y), rows, C, ptr(_rows_dev(rows_dev)), 0.0, 0.0, None, None, None,
+         None, ptr(local), ptr(ws), ws.numel(), _tickets(y.device), stream_ptr(y.device))
+    _lib.count_launch()
+    return local
+
+
+_LIB.impl("bn_stats_local", _bn_stats_local_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::bn_stats_local")
+def _bn_stats_local_fake(y, rows_dev=None):
+    return y.new_empty((3, y.shape[1]))
+
+
+_LIB.define("bn_sync_finalize(Tensor gathered, float eps, float momentum, Tensor? running_mean, "
+            "Tensor? running_var) -> (Tensor, Tensor, Tensor)")
+
+
+def _bn_sync_finalize_cuda(gathered, eps, momentum, running_mean, running_var):
+    gathered = _f32c(gathered)
+    world, three, C = gathered.shape
+    if three != 3:
+        raise ValueError("bn_sync_finalize: gathered must be (world, 3, C)")
+    mean = torch.empty((C,), dtype=torch.float32, device=gathered.device)
+    rstd = torch.empty_like(mean)
+    inv_n = torch.empty((1,), dtype=torch.float32, device=gathered.device)
+    call("pgh_bn_sync_finalize_f32", ptr(gathered), world, C, float(eps), float(momentum), ptr(mean),
+         ptr(rstd), ptr(running_mean), ptr(running_var), ptr(inv_n), stream_ptr(gathered.device))
+    _lib.count_launch()
+    return mean, rstd, inv_n
+
+
+_LIB.impl("bn_sync_finalize", _bn_sync_finalize_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::bn_sync_finalize")
+def _bn_sync_finalize_fake(gathered, eps, momentum, running_mean, running_var):
+    C = gathered.shape[2]
+    return gathered.new_empty((C,)), gathered.new_empty((C,)), gathered.new_empty((1,))
+
+
 _LIB.define("bn_act_fwd(Tensor y, Tensor mean, Tensor rstd, Tensor? gamma, Tensor? beta, int act, "
-            "Tensor? residual=None) -> Tensor")
+            "Tensor? residual=None, Tensor? rows_dev=None) -> Tensor")
 
 
-def _bn_act_fwd_cuda(y, mean, rstd, gamma, beta, act, residual=None):
+def _bn_act_fwd_cuda(y, mean, rstd, gamma, beta, act, residual=None, rows_dev=None):
     y, residual = _f32c(y), _f32c(residual)
     rows, C = y.shape
     if residual is not None and residual.shape != y.shape:
         raise ValueError("bn_act_fwd: residual must have the shape of y")
     z = torch.empty_like(y)
     call("pgh_bn_act_res_fwd_f32", ptr(y), ptr(mean), ptr(rstd), ptr(_f32c(gamma)),
-         ptr(_f32c(beta)), rows, C, act, ptr(residual), ptr(z), stream_ptr(y.device))
+         ptr(_f32c(beta)), rows, C, ptr(_rows_dev(rows_dev)), act, ptr(residual), ptr(z),
+         stream_ptr(y.device))
     _lib.count_launch()
     return z
 
@@ -421,36 +494,85 @@ _LIB.impl("bn_act_fwd", _bn_act_fwd_cuda, "CUDA")
 
 
 @torch.library.register_fake("pygho_b200::bn_act_fwd")
-def _bn_act_fwd_fake(y, mean, rstd, gamma, beta, act, residual=None):
+def _bn_act_fwd_fake(y, mean, rstd, gamma, beta, act, residual=None, rows_dev=None):
     return torch.empty_like(y)
 
 
-_LIB.define("bn_act_bwd(Tensor dz, Tensor y, Tensor mean, Tensor rstd, Tensor? gamma, Tensor? beta, "
-            "int act, bool want_bias) -> (Tensor, Tensor, Tensor, Tensor)")
+_LIB.define("bn_act_bwd_reduce(Tensor dz, Tensor y, Tensor mean, Tensor rstd, Tensor? gamma, "
+            "Tensor? beta, int act, Tensor? rows_dev, Tensor(a!)? dgamma_acc, "
+            "Tensor(b!)? dbeta_acc) -> (Tensor, Tensor, Tensor)")
 
 
-def _bn_act_bwd_cuda(dz, y, mean, rstd, gamma, beta, act, want_bias):
+def _grad_target(t: Optional[Tensor], C: int, name: str) -> Optional[Tensor]:
+    if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != C):
+        raise ValueError(f"{name}: gradient buffer must be a contiguous float32 tensor of {C} elements")
+    return t
+
+
+def _bn_act_bwd_reduce_cuda(dz, y, mean, rstd, gamma, beta, act, rows_dev, dgamma_acc, dbeta_acc):
+    """-> (sums (2, C), dgamma, dbeta).  With ``dgamma_acc`` / ``dbeta_acc`` the kernel ADDS into
+    those buffers (a parameter's ``.grad`` view of the flat bucket) and the returned tensors are
+    empty placeholders."""
     dz, y = _f32c(dz), _f32c(y)
     rows, C = y.shape
-    dy = torch.empty_like(y)
-    dgamma = torch.empty((C,), dtype=torch.float32, device=y.device)
-    dbeta = torch.empty_like(dgamma)
-    dbias = torch.empty_like(dgamma) if want_bias else None
+    sums = torch.empty((2, C), dtype=torch.float32, device=y.device)
+    acc = dgamma_acc is not None or dbeta_acc is not None
+    if acc:
+        dgamma, dbeta = _grad_target(dgamma_acc, C, "dgamma"), _grad_target(dbeta_acc, C, "dbeta")
+    else:
+        dgamma = torch.empty((C,), dtype=torch.float32, device=y.device)
+        dbeta = torch.empty_like(dgamma)
     ws = _bn_ws(rows, C, y.device)
-    call("pgh_bn_act_bwd_f32", ptr(dz), ptr(y), ptr(mean), ptr(rstd), ptr(_f32c(gamma)),
-         ptr(_f32c(beta)), rows, C, act, ptr(dy), ptr(dgamma), ptr(dbeta), ptr(dbias), ptr(ws),
-         ws.numel(), stream_ptr(y.device))
-    _lib.count_launch(4 if want_bias else 3)
-    return dy, dgamma, dbeta, (dbias if want_bias else dgamma.new_zeros((0,)))
+    call("pgh_bn_act_bwd_reduce_f32", ptr(dz), ptr(y), ptr(mean), ptr(rstd), ptr(_f32c(gamma)),
+         ptr(_f32c(beta)), rows, C, ptr(_rows_dev(rows_dev)), act, ptr(sums), ptr(dgamma),
+         ptr(dbeta), int(acc), ptr(ws), ws.numel(), _tickets(y.device), stream_ptr(y.device))
+    _lib.count_launch()
+    if acc:
+        e = sums.new_empty((0,))
+        return sums, e, e
+    return sums, dgamma, dbeta
 
 
-_LIB.impl("bn_act_bwd", _bn_act_bwd_cuda, "CUDA")
+_LIB.impl("bn_act_bwd_reduce", _bn_act_bwd_reduce_cuda, "CUDA")
 
 
-@torch.library.register_fake("pygho_b200::bn_act_bwd")
-def _bn_act_bwd_fake(dz, y, mean, rstd, gamma, beta, act, want_bias):
+@torch.library.register_fake("pygho_b200::bn_act_bwd_reduce")
+def _bn_act_bwd_reduce_fake(dz, y, mean, rstd, gamma, beta, act, rows_dev, dgamma_acc, dbeta_acc):
     C = y.shape[1]
-    return torch.empty_like(y), y.new_empty((C,)), y.new_empty((C,)), y.new_empty((C if want_bias else 0,))
+    n = 0 if (dgamma_acc is not None or dbeta_acc is not None) else C
+    return y.new_empty((2, C)), y.new_empty((n,)), y.new_empty((n,))
+
+
+_LIB.define("bn_act_bwd_apply(Tensor dz, Tensor y, Tensor mean, Tensor rstd, Tensor? gamma, "
+            "Tensor? beta, Tensor sums, Tensor? inv_n, int act, Tensor? rows_dev, bool want_bias, "
+            "Tensor(a!)? dbias_acc) -> (Tensor, Tensor)")
+
+
+def _bn_act_bwd_apply_cuda(dz, y, mean, rstd, gamma, beta, sums, inv_n, act, rows_dev, want_bias,
+                           dbias_acc):
+    dz, y, sums = _f32c(dz), _f32c(y), _f32c(sums)
+    rows, C = y.shape
+    dy = torch.empty_like(y)
+    acc = dbias_acc is not None
+    dbias = _grad_target(dbias_acc, C, "dbias") if acc else (
+        torch.empty((C,), dtype=torch.float32, device=y.device) if want_bias else None)
+    ws = _bn_ws(rows, C, y.device)
+    call("pgh_bn_act_bwd_apply_f32", ptr(dz), ptr(y), ptr(mean), ptr(rstd), ptr(_f32c(gamma)),
+         ptr(_f32c(beta)), ptr(sums), ptr(_f32c(inv_n)), rows, C, ptr(_rows_dev(rows_dev)), act,
+         ptr(dy), ptr(dbias), int(acc), ptr(ws), ws.numel(), _tickets(y.device),
+         stream_ptr(y.device))
+    _lib.count_launch()
+    return dy, (dbias if (want_bias and not acc) else dy.new_empty((0,)))
+
+
+_LIB.impl("bn_act_bwd_apply", _bn_act_bwd_apply_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::bn_act_bwd_apply")
+def _bn_act_bwd_apply_fake(dz, y, mean, rstd, gamma, beta, sums, inv_n, act, rows_dev, want_bias,
+                           dbias_acc):
+    C = y.shape[1]
+    return torch.empty_like(y), y.new_empty((C if (want_bias and dbias_acc is None) else 0,))
 
 
 _ops = torch.ops.pygho_b200
@@ -727,7 +849,7 @@ class EmbeddingGather(torch.autograd.Function):
     def forward(ctx, weight: Tensor, idx: Tensor, plan):
         n = plan.idx32.numel()
         out = _ops.seg_gmr(weight, plan.idx32, None, None, None, None, n, 0)
-        ctx.plan = plan
+        ctx.plan, ctx.weight = plan, weight
         return out.reshape(tuple(idx.shape) + (weight.shape[1],))
 
     @staticmethod
@@ -736,7 +858,12 @@ class EmbeddingGather(torch.autograd.Function):
         plan = ctx.plan
         cur = g.reshape(-1, g.shape[-1])
         perm = plan.perm
-        for rowptr in plan.levels:
+        acc = _acc_target(ctx.weight, True)
+        last = len(plan.levels) - 1
+        for i, rowptr in enumerate(plan.levels):
+            if i == last and acc is not None:        # last level adds into weight.grad directly
+                _ops.seg_gmr_out(cur, perm, None, None, None, rowptr, rowptr.numel() - 1, 0, acc, True)
+                return None, None, None
             cur = _ops.seg_gmr(cur, perm, None, None, None, rowptr, rowptr.numel() - 1, 0)
             perm = None
         return cur, None, None
@@ -745,51 +872,142 @@ class EmbeddingGather(torch.autograd.Function):
 ACT_CODE = {"none": 0, "silu": 1, "relu": 2}
 
 
-def _tall_skinny_tn(a: Tensor, b: Tensor, chunks: int = 64) -> Tensor:
+_SPLITK_PLANS = {}
+
+
+def _splitk_plan(chunks: int, m: int, device):
+    """Plan of out[r] = sum_k part[k * m + r]: the reduction over the split-K slabs as ONE
+    segmented-sum launch that can also accumulate into a gradient buffer."""
+    key = (chunks, m, device)
+    hit = _SPLITK_PLANS.get(key)
+    if hit is None:
+        if len(_SPLITK_PLANS) > 64:
+            _SPLITK_PLANS.clear()
+        r = torch.arange(m, dtype=torch.int32, device=device)
+        k = torch.arange(chunks, dtype=torch.int32, device=device)
+        c = (r.unsqueeze(1) + k.unsqueeze(0) * m).reshape(-1).contiguous()
+        rowptr = (torch.arange(m + 1, dtype=torch.int32, device=device) * chunks).contiguous()
+        hit = (c, rowptr)
+        _SPLITK_PLANS[key] = hit
+    return hit
+
+
+def _tall_skinny_tn(a: Tensor, b: Tensor, chunks: int = 64, acc: Optional[Tensor] = None
+                    ) -> Optional[Tensor]:
     """a^T @ b for (rows, m) and (rows, n) with rows >> m, n (weight gradients over all
     tuples).  cuBLAS does not split K for this shape and leaves most SMs idle; cutting the
     rows into `chunks` slabs turns it into one batched GEMM that fills the GPU, followed by a
-    tiny reduction over the slabs."""
+    reduction over the slabs.  With ``acc`` (a (m, n) gradient buffer) the result is ADDED to it
+    in the same launches (cuBLAS beta = 1 / accumulate flag of the segmented sum) and None is
+    returned: no separate gradient-accumulation kernel."""
     rows = a.shape[0]
     if rows < 64 * chunks or a.shape[1] > 1024 or b.shape[1] > 1024:
+        if acc is not None:
+            acc.addmm_(a.t(), b)
+            return None
         return a.t().mm(b)
     per = rows // chunks
     main = per * chunks
-    part = torch.bmm(a[:main].view(chunks, per, a.shape[1]).transpose(1, 2),
-                     b[:main].view(chunks, per, b.shape[1]))
-    out = part.sum(0)
+    m, n = a.shape[1], b.shape[1]
+    part = torch.bmm(a[:main].view(chunks, per, m).transpose(1, 2), b[:main].view(chunks, per, n))
+    if n % 4 == 0 and part.data_ptr() % 16 == 0:
+        c, rowptr = _splitk_plan(chunks, m, a.device)
+        out = acc if acc is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
+        _ops.seg_gmr_out(part.view(chunks * m, n), c, None, None, None, rowptr, m, 0, out,
+                         acc is not None)
+    elif acc is not None:
+        acc.add_(part.sum(0))
+        out = acc
+    else:
+        out = part.sum(0)
     if main < rows:
         out.addmm_(a[main:].t(), b[main:])
-    return out
+    return None if acc is not None else out
+
+
+_DIRECT_GRADS = True
+
+
+def set_direct_grad_accumulation(flag: bool) -> None:
+    """When a parameter already has a ``.grad`` buffer (e.g. a view of the flat all-reduce
+    bucket, pygho_b200/dist.py), the fused backward kernels ADD their parameter gradients into
+    it directly and hand autograd ``None`` -- no AccumulateGrad add kernel per parameter
+    (90 tiny launches per SSWL+ step).  Semantics are unchanged (gradients accumulate)."""
+    global _DIRECT_GRADS
+    _DIRECT_GRADS = bool(flag)
+
+
+def _acc_target(p: Optional[Tensor], need: bool) -> Optional[Tensor]:
+    """``p.grad`` if the gradient of parameter ``p`` can be accumulated in place."""
+    if not (_DIRECT_GRADS and need) or p is None:
+        return None
+    g = getattr(p, "grad", None)
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape \
+            or g.data_ptr() % 16 or not g.is_cuda:
+        return None
+    return g
 
 
 class LinearBNAct(torch.autograd.Function):
     """z = act(BatchNorm_train(x @ W^T + b)) for 2-D x: the reference MLP block
     (honn/utils.py:85-142) with the normalisation/activation passes fused.  The GEMMs stay
     with cuBLAS (torch.addmm / mm); only the HBM-bound elementwise + reduction work is ours.
-    Saves x and the Linear output y; the normalised tensor is recomputed in the backward."""
+    Saves x and the Linear output y; the normalised tensor is recomputed in the backward.
+
+    ``rows_dev``: device count of valid rows of capacity-padded tensors (pygho_b200/static.py).
+    ``group``: a torch.distributed process group -> statistics over the rows of ALL ranks
+    (SyncBN: sharded training equals single-process training on the global batch)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, momentum, eps, act,
-                residual=None):
+                residual=None, rows_dev=None, group=None):
         y = torch.nn.functional.linear(x, weight, bias)
-        mean, rstd = _ops.bn_stats(y, eps, momentum, running_mean, running_var)
-        z = _ops.bn_act_fwd(y, mean, rstd, gamma, beta, act, residual)   # + residual if given
+        inv_n = None
+        if group is None:
+            mean, rstd = _ops.bn_stats(y, eps, momentum, running_mean, running_var, rows_dev)
+        else:
+            import torch.distributed as dist
+            local = _ops.bn_stats_local(y, rows_dev)
+            gathered = torch.empty((dist.get_world_size(group),) + tuple(local.shape),
+                                   dtype=local.dtype, device=local.device)
+            if dist.get_backend(group) == "nccl":
+                dist.all_gather_into_tensor(gathered, local, group=group)
+            else:       # gloo (tests) has no CUDA all-gather: sum of one-hot placed triples
+                gathered.zero_()
+                gathered[dist.get_rank(group)].copy_(local)
+                dist.all_reduce(gathered, op=dist.ReduceOp.SUM, group=group)
+            mean, rstd, inv_n = _ops.bn_sync_finalize(gathered, eps, momentum, running_mean,
+                                                      running_var)
+        z = _ops.bn_act_fwd(y, mean, rstd, gamma, beta, act, residual, rows_dev)  # + residual
         ctx.save_for_backward(x, weight, y, mean, rstd, gamma, beta)
         ctx.act = act
-        ctx.has_bias = bias is not None
+        ctx.extra = (bias, rows_dev, group, inv_n)
         return z
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dz):
         x, weight, y, mean, rstd, gamma, beta = ctx.saved_tensors
+        bias, rows_dev, group, inv_n = ctx.extra
         need = ctx.needs_input_grad
-        dy, dgamma, dbeta, dbias = _ops.bn_act_bwd(dz, y, mean, rstd, gamma, beta, ctx.act,
-                                                   ctx.has_bias and need[2])
+        need_bias = bias is not None and need[2]
+        acc_w, acc_b = _acc_target(weight, need[1]), _acc_target(bias, need_bias)
+        acc_g = _acc_target(gamma, gamma is not None and need[3])
+        acc_be = _acc_target(beta, beta is not None and need[4])
+        if (acc_g is None) != (acc_be is None):
+            acc_g = acc_be = None
+        sums, dgamma, dbeta = _ops.bn_act_bwd_reduce(dz, y, mean, rstd, gamma, beta, ctx.act,
+                                                     rows_dev, acc_g, acc_be)
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        dy, dbias = _ops.bn_act_bwd_apply(dz, y, mean, rstd, gamma, beta, sums, inv_n, ctx.act,
+                                          rows_dev, need_bias, acc_b)
         dx = dy.mm(weight) if need[0] else None
-        dw = _tall_skinny_tn(dy, x) if need[1] else None
-        return (dx, dw, dbias if (ctx.has_bias and need[2]) else None,
-                dgamma if (gamma is not None and need[3]) else None,
-                dbeta if (beta is not None and need[4]) else None, None, None, None, None, None,
-                dz if (len(need) > 10 and need[10]) else None)   # residual: gradient passes through
+        dw = _tall_skinny_tn(dy, x, acc=acc_w) if need[1] else None
+        return (dx, dw, dbias if (need_bias and acc_b is None) else None,
+                dgamma if (gamma is not None and need[3] and acc_g is None) else None,
+                dbeta if (beta is not None and need[4] and acc_be is None) else None,
+                None, None, None, None, None,
+                dz if (len(need) > 10 and need[10]) else None,   # residual: gradient passes through
+                None, None)
