@@ -682,6 +682,15 @@ def run_b200(args):
         per_step = []
         e2e_ms, _ = timed(e2e_step, args.steps, finish=read_pending, per_step=per_step)
         assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: every step's loss is read"
+        if os.environ.get("PYGHO_B200_BENCH_TRACE"):
+            print(f"[trace] rank {rank} e2e device ms per step: {[round(v, 2) for v in per_step]}",
+                  file=sys.stderr)
+            if hasattr(feeder, "load_ms"):
+                print(f"[trace] loader host ms: {[round(v, 2) for v in feeder.load_ms[-args.steps:]]}; "
+                      f"arrays mirrored per load: {feeder.copies}", file=sys.stderr)
+            ms_ = torch.cuda.memory_stats(device)
+            print(f"[trace] allocator: device_alloc {ms_['num_device_alloc']} device_free "
+                  f"{ms_['num_device_free']} retries {ms_['num_alloc_retries']}", file=sys.stderr)
         e2e = {"value": glob / (e2e_ms / args.steps * 1e-3), "unit": "graphs/s",
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode,

@@ -232,6 +232,7 @@ int pgh_masked_fill_f32(const float* data, const uint8_t* mask, int64_t rows, in
  * summation order: deterministic).
  *   ws       : pgh_bn_ws_bytes(rows, C) bytes of scratch
  *   tickets  : 64 int32 words, zero before the first use; the kernels leave them zero
+ *   num_batches_tracked : NULL or the BatchNorm1d counter (int64), incremented by stats
  *   rows_dev : NULL, or a device int32 holding the number of VALID rows (<= rows): the tensors
  *              are padded to a fixed capacity `rows` (CUDA-graph replay of steps whose batches
  *              differ in size); pad rows are excluded from all sums, get z = 0 and dy = 0
@@ -244,11 +245,16 @@ int pgh_masked_fill_f32(const float* data, const uint8_t* mask, int64_t rows, in
 size_t pgh_bn_ws_bytes(int64_t rows, int64_t C);
 int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, const int32_t* rows_dev, float eps,
                      float momentum, float* mean, float* rstd, float* running_mean,
-                     float* running_var, float* local_out, void* ws, size_t ws_bytes,
-                     int32_t* tickets, void* stream);
+                     float* running_var, float* local_out, int64_t* num_batches_tracked,
+                     void* ws, size_t ws_bytes, int32_t* tickets, void* stream);
 int pgh_bn_sync_finalize_f32(const float* gathered, int64_t world, int64_t C, float eps,
                              float momentum, float* mean, float* rstd, float* running_mean,
                              float* running_var, float* inv_n, void* stream);
+/* out[e] (+)= sum_k part[k * n + e], k < slabs, n % 4 == 0: reduction over the row slabs of a
+ * split-K weight-gradient GEMM (dW = dy^T x over all tuples, honn/utils.py:85-142 backward),
+ * optionally accumulating into the parameter's gradient buffer; fixed order */
+int pgh_sum_slabs_f32(const float* part, int64_t slabs, int64_t n, float* out, int accumulate,
+                      void* stream);
 /* residual may be NULL; z = act(...) + residual is the `X + conv(X)` of example/zinc.py:286
  * folded into the last block of the layer's MLP */
 int pgh_bn_act_res_fwd_f32(const float* y, const float* mean, const float* rstd,

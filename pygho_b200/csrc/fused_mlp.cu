@@ -83,10 +83,12 @@ __device__ __forceinline__ long long valid_rows(long long rows, const int* __res
   return v < rows ? (v < 0 ? 0 : v) : rows;
 }
 
-// Two-level ticketed combine.  Every CTA of the launch has written W floats to
+// Two-level ticketed combine.  Every CTA of the launch has written W floats (W % 4 == 0) to
 // part[blockIdx.x * W ..]; exactly one CTA returns true, with fin[0..W) (shared memory, double)
 // holding the sum over all CTAs added in a fixed order.  tickets[0..1+ngroups) must be zero on
 // entry and are zero again on exit (self-resetting: the buffer is reused by the next launch).
+// The combining CTA issues its loads 8 partials at a time (128-bit each) before adding them in
+// order: the tail costs a few L2 round trips, not one per partial.
 __device__ bool ticketed_combine(const float* part, double* part2, int W, int blocks, int grp,
                                  int ngroups, int* tickets, double* fin) {
   __shared__ int s_last;
@@ -94,18 +96,27 @@ __device__ bool ticketed_combine(const float* part, double* part2, int W, int bl
   const int g = blockIdx.x / grp;
   const int g_lo = g * grp;
   const int g_n = min(grp, blocks - g_lo);
+  const int W4 = W >> 2;
   __threadfence();                       // this CTA's partial is visible before its ticket
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(tickets + 1 + g, 1) == g_n - 1);
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
-  for (int e = tid; e < W; e += nt) {
-    double a = 0.0;
-    const float* p = part + (size_t)g_lo * W + e;
-#pragma unroll 4
-    for (int b = 0; b < g_n; ++b) a += (double)__ldcg(p + (size_t)b * W);
-    part2[(size_t)g * W + e] = a;
+  for (int e = tid; e < W4; e += nt) {
+    double ax = 0.0, ay = 0.0, az = 0.0, aw = 0.0;
+    const float4* p = reinterpret_cast<const float4*>(part + (size_t)g_lo * W) + e;
+    for (int b0 = 0; b0 < g_n; b0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + (size_t)min(b0 + u, g_n - 1) * W4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (b0 + u < g_n) { ax += (double)v[u].x; ay += (double)v[u].y; az += (double)v[u].z; aw += (double)v[u].w; }
+    }
+    double2* o = reinterpret_cast<double2*>(part2 + (size_t)g * W) + 2 * e;
+    o[0] = make_double2(ax, ay);
+    o[1] = make_double2(az, aw);
   }
   __threadfence();
   __syncthreads();
@@ -116,11 +127,22 @@ __device__ bool ticketed_combine(const float* part, double* part2, int W, int bl
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
-  for (int e = tid; e < W; e += nt) {
-    double a = 0.0;
-#pragma unroll 4
-    for (int b = 0; b < ngroups; ++b) a += __ldcg(part2 + (size_t)b * W + e);
-    fin[e] = a;
+  for (int e = tid; e < W4; e += nt) {
+    double ax = 0.0, ay = 0.0, az = 0.0, aw = 0.0;
+    const double2* p = reinterpret_cast<const double2*>(part2) + 2 * e;
+    for (int b0 = 0; b0 < ngroups; b0 += 8) {
+      double2 v[8], w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double2* q = p + (size_t)min(b0 + u, ngroups - 1) * (W >> 1);
+        v[u] = __ldcg(q);
+        w[u] = __ldcg(q + 1);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (b0 + u < ngroups) { ax += v[u].x; ay += v[u].y; az += w[u].x; aw += w[u].y; }
+    }
+    fin[4 * e] = ax; fin[4 * e + 1] = ay; fin[4 * e + 2] = az; fin[4 * e + 3] = aw;
   }
   if (tid == 0) tickets[0] = 0;
   __syncthreads();
@@ -168,7 +190,7 @@ __global__ void bn_stats_kernel(const float* __restrict__ y, long long rows_cap,
                                 int grp, int ngroups, int* __restrict__ tickets, float eps,
                                 float momentum, float* __restrict__ mean, float* __restrict__ rstd,
                                 float* __restrict__ running_mean, float* __restrict__ running_var,
-                                float* __restrict__ local_out) {
+                                float* __restrict__ local_out, long long* __restrict__ nbt) {
   extern __shared__ float4 sm[];
   const long long rows = valid_rows(rows_cap, rows_dev);
   const int tx = threadIdx.x, c4 = blockDim.x, ty_n = blockDim.y;
@@ -194,6 +216,7 @@ __global__ void bn_stats_kernel(const float* __restrict__ y, long long rows_cap,
   if (!ticketed_combine(part, part2, 2 * C, blocks, grp, ngroups, tickets, fin)) return;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
   const double n = (double)rows;
+  if (tid == 0 && nbt) nbt[0] += 1;       // BatchNorm1d.num_batches_tracked (one launch less)
   for (int c = tid; c < C; c += nt) {
     const double sc = fin[c], qc = fin[C + c];
     const double ms = n > 0.0 ? sc / n : 0.0;              // mean of (y - shift)
@@ -417,6 +440,24 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const floa
   for (int c = tid; c < C; c += nt) dbias[c] = accumulate ? dbias[c] + (float)fin[c] : (float)fin[c];
 }
 
+// out[e] (+)= sum_k part[k * n4 + e]  (float4 elements): the reduction over the split-K slabs
+// of the tall-skinny weight-gradient GEMMs, 8 slabs in flight per thread, fixed order.
+__global__ void sum_slabs_kernel(const float4* __restrict__ part, int slabs, long long n4,
+                                 float4* __restrict__ out, int accumulate) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n4) return;
+  float4 a = accumulate ? out[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k0 = 0; k0 < slabs; k0 += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(part + (size_t)min(k0 + u, slabs - 1) * n4 + e);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (k0 + u < slabs) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+  }
+  out[e] = a;
+}
+
 static bool bn_ok(int64_t rows, int64_t C) {
   return rows > 0 && C >= 4 && C % 4 == 0 && C / 4 <= kBnThreads;
 }
@@ -439,7 +480,8 @@ static double* bn_part2(void* ws, const BnGeom& g, int64_t C) {
 extern "C" int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, const int32_t* rows_dev,
                                 float eps, float momentum, float* mean, float* rstd,
                                 float* running_mean, float* running_var, float* local_out,
-                                void* ws, size_t ws_bytes, int32_t* tickets, void* stream) {
+                                int64_t* num_batches_tracked, void* ws, size_t ws_bytes,
+                                int32_t* tickets, void* stream) {
   if (!y || !ws || !tickets || (!local_out && (!mean || !rstd))) return arg_error("bn_stats: null pointer");
   if (!bn_ok(rows, C)) return arg_error("bn_stats: need rows > 0, C % 4 == 0, C <= 1024");
   if ((reinterpret_cast<uintptr_t>(y) & 15)) return arg_error("bn_stats: y must be 16-byte aligned");
@@ -448,8 +490,20 @@ extern "C" int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, const i
   bn_stats_kernel<<<g.blocks, dim3(g.c4, g.ty), g.smem, as_stream(stream)>>>(
       y, rows, (int)C, rows_dev, g.rows_per_block, reinterpret_cast<float*>(ws), bn_part2(ws, g, C),
       g.blocks, g.grp, g.ngroups, tickets, eps, momentum, mean, rstd, running_mean, running_var,
-      local_out);
+      local_out, reinterpret_cast<long long*>(num_batches_tracked));
   return check_launch("bn_stats");
+}
+
+extern "C" int pgh_sum_slabs_f32(const float* part, int64_t slabs, int64_t n, float* out,
+                                 int accumulate, void* stream) {
+  if (!part || !out || slabs < 1 || n < 0 || (n & 3)) return arg_error("sum_slabs: arguments (n % 4 == 0)");
+  if ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return arg_error("sum_slabs: tensors must be 16-byte aligned");
+  if (n == 0) return 0;
+  const long long n4 = n / 4;
+  sum_slabs_kernel<<<blocks_for(n4, 128), 128, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(part), (int)slabs, n4, reinterpret_cast<float4*>(out), accumulate);
+  return check_launch("sum_slabs");
 }
 
 extern "C" int pgh_bn_sync_finalize_f32(const float* gathered, int64_t world, int64_t C, float eps,

@@ -195,6 +195,8 @@ class DevicePrefetcher:
         execution.  The caller must synchronise with the step BEFORE the one just launched
         (e.g. read its loss back) before calling this: the buffers of that older batch are
         released here and reused."""
+        from ..static import release_datadict
+        release_datadict(self._inflight)        # free the older batch now, not at the next GC
         self._inflight = self._ready
         self._submit()
 

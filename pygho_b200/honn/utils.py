@@ -136,15 +136,14 @@ class MLP(nn.Module):
             blk = _match_block(mods, i)
             if blk is not None:
                 bn, act = blk
-                if bn.track_running_stats:
-                    bn.num_batches_tracked.add_(1)
                 res = None
                 if residual is not None and i + 3 == len(mods):
                     res, residual = residual.reshape(-1, residual.shape[-1]), None
                 h = LinearBNAct.apply(h, m.weight, m.bias, bn.weight, bn.bias, bn.running_mean,
                                       bn.running_var, bn.momentum, bn.eps, ACT_CODE[act], res,
                                       static.rows_dev_for(h.shape[0]),
-                                      getattr(bn, "_pgh_sync_group", None))
+                                      getattr(bn, "_pgh_sync_group", None),
+                                      bn.num_batches_tracked if bn.track_running_stats else None)
                 i += 3
             else:
                 h = m(h)

@@ -398,19 +398,28 @@ def _rows_dev(t: Optional[Tensor]) -> Optional[Tensor]:
     return t
 
 
-_LIB.define("bn_stats(Tensor y, float eps, float momentum, Tensor? running_mean, "
-            "Tensor? running_var, Tensor? rows_dev=None) -> (Tensor, Tensor)")
+def _nbt(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is not None and (t.dtype != torch.int64 or t.numel() != 1 or not t.is_cuda):
+        raise TypeError("num_batches_tracked must be a one-element int64 CUDA tensor")
+    return t
 
 
-def _bn_stats_cuda(y, eps, momentum, running_mean, running_var, rows_dev=None):
+_LIB.define("bn_stats(Tensor y, float eps, float momentum, Tensor(a!)? running_mean, "
+            "Tensor(b!)? running_var, Tensor? rows_dev=None, Tensor(c!)? num_batches_tracked=None) "
+            "-> (Tensor, Tensor)")
+
+
+def _bn_stats_cuda(y, eps, momentum, running_mean, running_var, rows_dev=None,
+                   num_batches_tracked=None):
     y = _f32c(y)
     rows, C = y.shape
     mean = torch.empty((C,), dtype=torch.float32, device=y.device)
     rstd = torch.empty_like(mean)
     ws = _bn_ws(rows, C, y.device)
     call("pgh_bn_stats_f32", ptr(y), rows, C, ptr(_rows_dev(rows_dev)), float(eps), float(momentum),
-         ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var), None, ptr(ws), ws.numel(),
-         _tickets(y.device), stream_ptr(y.device))
+         ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var), None,
+         ptr(_nbt(num_batches_tracked)), ptr(ws), ws.numel(), _tickets(y.device),
+         stream_ptr(y.device))
     _lib.count_launch()
     return mean, rstd
 
@@ -419,21 +428,24 @@ _LIB.impl("bn_stats", _bn_stats_cuda, "CUDA")
 
 
 @torch.library.register_fake("pygho_b200::bn_stats")
-def _bn_stats_fake(y, eps, momentum, running_mean, running_var, rows_dev=None):
+def _bn_stats_fake(y, eps, momentum, running_mean, running_var, rows_dev=None,
+                   num_batches_tracked=None):
     return y.new_empty((y.shape[1],)), y.new_empty((y.shape[1],))
 
 
-_LIB.define("bn_stats_local(Tensor y, Tensor? rows_dev=None) -> Tensor")
+_LIB.define("bn_stats_local(Tensor y, Tensor? rows_dev=None, "
+            "Tensor(a!)? num_batches_tracked=None) -> Tensor")
 
 
-def _bn_stats_local_cuda(y, rows_dev=None):
+def _bn_stats_local_cuda(y, rows_dev=None, num_batches_tracked=None):
     """Rank-local (mean, M2, count) rows (3, C) for cross-rank statistics (SyncBN)."""
     y = _f32c(y)
     rows, C = y.shape
     local = torch.empty((3, C), dtype=torch.float32, device=y.device)
     ws = _bn_ws(rows, C, y.device)
     call("pgh_bn_stats_f32", ptr(y), rows, C, ptr(_rows_dev(rows_dev)), 0.0, 0.0, None, None, None,
-         None, ptr(local), ptr(ws), ws.numel(), _tickets(y.device), stream_ptr(y.device))
+         None, ptr(local), ptr(_nbt(num_batches_tracked)), ptr(ws), ws.numel(), _tickets(y.device),
+         stream_ptr(y.device))
     _lib.count_launch()
     return local
 
@@ -442,7 +454,7 @@ _LIB.impl("bn_stats_local", _bn_stats_local_cuda, "CUDA")
 
 
 @torch.library.register_fake("pygho_b200::bn_stats_local")
-def _bn_stats_local_fake(y, rows_dev=None):
+def _bn_stats_local_fake(y, rows_dev=None, num_batches_tracked=None):
     return y.new_empty((3, y.shape[1]))
 
 
@@ -573,6 +585,28 @@ def _bn_act_bwd_apply_fake(dz, y, mean, rstd, gamma, beta, sums, inv_n, act, row
                            dbias_acc):
     C = y.shape[1]
     return torch.empty_like(y), y.new_empty((C if (want_bias and dbias_acc is None) else 0,))
+
+
+_LIB.define("sum_slabs(Tensor part, Tensor(a!) out, bool accumulate) -> ()")
+
+
+def _sum_slabs_cuda(part, out, accumulate):
+    """out (+)= part.sum(0) for a contiguous float32 (slabs, ...) tensor, fixed order."""
+    part = _f32c(part)
+    n = part[0].numel()
+    if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != n:
+        raise ValueError("sum_slabs: out must be a contiguous float32 tensor of part[0]'s size")
+    call("pgh_sum_slabs_f32", ptr(part), part.shape[0], n, ptr(out), int(accumulate),
+         stream_ptr(part.device))
+    _lib.count_launch()
+
+
+_LIB.impl("sum_slabs", _sum_slabs_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::sum_slabs")
+def _sum_slabs_fake(part, out, accumulate):
+    return None
 
 
 _ops = torch.ops.pygho_b200
@@ -872,26 +906,6 @@ class EmbeddingGather(torch.autograd.Function):
 ACT_CODE = {"none": 0, "silu": 1, "relu": 2}
 
 
-_SPLITK_PLANS = {}
-
-
-def _splitk_plan(chunks: int, m: int, device):
-    """Plan of out[r] = sum_k part[k * m + r]: the reduction over the split-K slabs as ONE
-    segmented-sum launch that can also accumulate into a gradient buffer."""
-    key = (chunks, m, device)
-    hit = _SPLITK_PLANS.get(key)
-    if hit is None:
-        if len(_SPLITK_PLANS) > 64:
-            _SPLITK_PLANS.clear()
-        r = torch.arange(m, dtype=torch.int32, device=device)
-        k = torch.arange(chunks, dtype=torch.int32, device=device)
-        c = (r.unsqueeze(1) + k.unsqueeze(0) * m).reshape(-1).contiguous()
-        rowptr = (torch.arange(m + 1, dtype=torch.int32, device=device) * chunks).contiguous()
-        hit = (c, rowptr)
-        _SPLITK_PLANS[key] = hit
-    return hit
-
-
 def _tall_skinny_tn(a: Tensor, b: Tensor, chunks: int = 64, acc: Optional[Tensor] = None
                     ) -> Optional[Tensor]:
     """a^T @ b for (rows, m) and (rows, n) with rows >> m, n (weight gradients over all
@@ -910,11 +924,9 @@ def _tall_skinny_tn(a: Tensor, b: Tensor, chunks: int = 64, acc: Optional[Tensor
     main = per * chunks
     m, n = a.shape[1], b.shape[1]
     part = torch.bmm(a[:main].view(chunks, per, m).transpose(1, 2), b[:main].view(chunks, per, n))
-    if n % 4 == 0 and part.data_ptr() % 16 == 0:
-        c, rowptr = _splitk_plan(chunks, m, a.device)
+    if (m * n) % 4 == 0 and part.data_ptr() % 16 == 0 and (acc is None or acc.data_ptr() % 16 == 0):
         out = acc if acc is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
-        _ops.seg_gmr_out(part.view(chunks * m, n), c, None, None, None, rowptr, m, 0, out,
-                         acc is not None)
+        _ops.sum_slabs(part, out, acc is not None)
     elif acc is not None:
         acc.add_(part.sum(0))
         out = acc
@@ -960,14 +972,15 @@ class LinearBNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, momentum, eps, act,
-                residual=None, rows_dev=None, group=None):
+                residual=None, rows_dev=None, group=None, num_batches_tracked=None):
         y = torch.nn.functional.linear(x, weight, bias)
         inv_n = None
         if group is None:
-            mean, rstd = _ops.bn_stats(y, eps, momentum, running_mean, running_var, rows_dev)
+            mean, rstd = _ops.bn_stats(y, eps, momentum, running_mean, running_var, rows_dev,
+                                       num_batches_tracked)
         else:
             import torch.distributed as dist
-            local = _ops.bn_stats_local(y, rows_dev)
+            local = _ops.bn_stats_local(y, rows_dev, num_batches_tracked)
             gathered = torch.empty((dist.get_world_size(group),) + tuple(local.shape),
                                    dtype=local.dtype, device=local.device)
             if dist.get_backend(group) == "nccl":
@@ -1010,4 +1023,4 @@ class LinearBNAct(torch.autograd.Function):
                 dbeta if (beta is not None and need[4] and acc_be is None) else None,
                 None, None, None, None, None,
                 dz if (len(need) > 10 and need[10]) else None,   # residual: gradient passes through
-                None, None)
+                None, None, None)

@@ -27,6 +27,7 @@ size inside the step (3-D pooling to a sparse pattern) is rejected.
 from __future__ import annotations
 
 import threading
+import time
 from contextlib import contextmanager
 from dataclasses import replace
 from typing import Dict, Iterable, List, Optional, Sequence
@@ -181,6 +182,7 @@ class _Mirror:
     def __init__(self):
         self.pairs: List = []
         self.seen = set()
+        self.src_objs: List = []       # tensors / plans of the fresh batch (released after copy)
 
     def tensor(self, dst: torch.Tensor, src: torch.Tensor, dd_src: dict):
         if id(dst) in self.seen:
@@ -190,6 +192,7 @@ class _Mirror:
             raise RuntimeError(f"static batches: array shapes differ ({tuple(dst.shape)} vs "
                                f"{tuple(src.shape)})")
         self.pairs.append((dst, src))
+        self.src_objs.append(src)
         cache = getattr(dst, "_pgh_cache", None)
         if cache:
             for key, dobj in cache.items():
@@ -213,6 +216,7 @@ class _Mirror:
         if id(d) in self.seen:
             return
         self.seen.add(id(d))
+        self.src_objs.append(s)
         for k in ("a", "c", "d"):
             if d.idx[k] is not None:
                 self.tensor(d.idx[k], s.idx[k], dd_src)
@@ -225,6 +229,27 @@ class _Mirror:
         t = getattr(d, "_transposed", None)
         if t is not None:
             self.plan(t, s.transposed(), dd_src)
+
+
+    def release(self):
+        """Break the reference cycles of the fresh batch's plan objects (plan <-> swapped /
+        transposed plan, tensor -> cache -> plan -> tensor): its device memory then goes back to
+        the allocator as soon as the caller drops the datadict, instead of whenever the cyclic
+        garbage collector next runs (which made the pool grow -- a cuMemMap stall of tens of
+        milliseconds -- at unpredictable steps)."""
+        for o in self.src_objs:
+            if isinstance(o, torch.Tensor):
+                c = getattr(o, "_pgh_cache", None)
+                if c is not None:
+                    c.clear()
+            else:
+                o._groups = {}
+                o._swapped = None
+                o._inv = None
+                if hasattr(o, "_transposed"):
+                    o._transposed = None
+        self.src_objs = []
+        self.pairs = []
 
 
 def mirror_into(template: dict, fresh: dict) -> int:
@@ -244,7 +269,47 @@ def mirror_into(template: dict, fresh: dict) -> int:
             m.tensor(d, s, fresh)
     for dst, src in m.pairs:
         dst.copy_(src, non_blocking=True)
-    return len(m.pairs)
+    n = len(m.pairs)
+    m.release()
+    return n
+
+
+def release_datadict(dd: Optional[dict]) -> None:
+    """Drop every cached plan reachable from a datadict that is no longer needed and break the
+    plan objects' reference cycles, so its device memory is freed by reference counting at once
+    (see :meth:`_Mirror.release`)."""
+    if not dd:
+        return
+    seen = set()
+
+    def visit(o):
+        if o is None or id(o) in seen:
+            return
+        seen.add(id(o))
+        if isinstance(o, torch.Tensor):
+            c = getattr(o, "_pgh_cache", None)
+            if c:
+                vals = list(c.values())
+                c.clear()
+                for v in vals:
+                    visit(v)
+        elif isinstance(o, P.TriplePlan):
+            subs = list(o.idx.values()) + list(dict.values(o._groups)) + [o._swapped, o._inv,
+                                                                       getattr(o, "_transposed", None)]
+            o._groups, o._swapped, o._inv = {}, None, None
+            if hasattr(o, "_transposed"):
+                o._transposed = None
+            for v in subs:
+                visit(v)
+        elif isinstance(o, SparseTensor):
+            visit(o.indices)
+            visit(o.values)
+        elif isinstance(o, (tuple, list)):
+            for v in o:
+                visit(v)
+
+    for v in list(dd.values()):
+        visit(v)
 
 
 # ------------------------------------------------------------------------------ feeding
@@ -283,6 +348,7 @@ class StaticFeeder:
         self._done = [threading.Event(), threading.Event()]
         self._error = None
         self.copies = 0
+        self.load_ms: List[float] = []     # host time of every load (enqueue only)
         if threaded:
             import queue
             self._jobs = queue.Queue()
@@ -299,11 +365,14 @@ class StaticFeeder:
     def _load(self, index: int):
         slot = index & 1
         hb = self.hbs[index % len(self.hbs)]
+        t0 = time.perf_counter()
         with torch.cuda.stream(self.side):
             self.side.wait_event(self.consumed[slot])      # the slot's last replay is over
             fresh = self._sp_datadict(hb, self.device, self.keys, self.pinned)
             self.copies = mirror_into(self.slots[slot], fresh)
             self.loaded[slot].record(self.side)
+            del fresh
+        self.load_ms.append(1e3 * (time.perf_counter() - t0))
 
     def _run(self):
         torch.cuda.set_device(self.device)
