@@ -89,7 +89,7 @@ __device__ __forceinline__ long long valid_rows(long long rows, const int* __res
 // entry and are zero again on exit (self-resetting: the buffer is reused by the next launch).
 // The combining CTA issues its loads 8 partials at a time (128-bit each) before adding them in
 // order: the tail costs a few L2 round trips, not one per partial.
-__device__ bool ticketed_combine(const float* part, double* part2, int W, int blocks, int grp,
+__device__ bool ticketed_combine(const float* part, float* part2, int W, int blocks, int grp,
                                  int ngroups, int* tickets, double* fin) {
   __shared__ int s_last;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
@@ -97,26 +97,26 @@ __device__ bool ticketed_combine(const float* part, double* part2, int W, int bl
   const int g_lo = g * grp;
   const int g_n = min(grp, blocks - g_lo);
   const int W4 = W >> 2;
-  __threadfence();                       // this CTA's partial is visible before its ticket
+  constexpr int kInFlight = 8;
+  __threadfence();                       // release: this CTA's partial is visible before its ticket
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(tickets + 1 + g, 1) == g_n - 1);
   __syncthreads();
   if (!s_last) return false;
-  __threadfence();
+  // acquire side: the partials are read with ld.global.cg (L2, never a stale L1 line) after the
+  // barrier that follows the ticket -- the pattern of CUDA's threadFenceReduction sample
   for (int e = tid; e < W4; e += nt) {
     double ax = 0.0, ay = 0.0, az = 0.0, aw = 0.0;
     const float4* p = reinterpret_cast<const float4*>(part + (size_t)g_lo * W) + e;
-    for (int b0 = 0; b0 < g_n; b0 += 8) {
-      float4 v[8];
+    for (int b0 = 0; b0 < g_n; b0 += kInFlight) {
+      float4 v[kInFlight];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + (size_t)min(b0 + u, g_n - 1) * W4);
+      for (int u = 0; u < kInFlight; ++u) v[u] = __ldcg(p + (size_t)min(b0 + u, g_n - 1) * W4);
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < kInFlight; ++u)
         if (b0 + u < g_n) { ax += (double)v[u].x; ay += (double)v[u].y; az += (double)v[u].z; aw += (double)v[u].w; }
     }
-    double2* o = reinterpret_cast<double2*>(part2 + (size_t)g * W) + 2 * e;
-    o[0] = make_double2(ax, ay);
-    o[1] = make_double2(az, aw);
+    reinterpret_cast<float4*>(part2 + (size_t)g * W)[e] = make_float4((float)ax, (float)ay, (float)az, (float)aw);
   }
   __threadfence();
   __syncthreads();
@@ -126,21 +126,16 @@ __device__ bool ticketed_combine(const float* part, double* part2, int W, int bl
   }
   __syncthreads();
   if (!s_last) return false;
-  __threadfence();
   for (int e = tid; e < W4; e += nt) {
     double ax = 0.0, ay = 0.0, az = 0.0, aw = 0.0;
-    const double2* p = reinterpret_cast<const double2*>(part2) + 2 * e;
-    for (int b0 = 0; b0 < ngroups; b0 += 8) {
-      double2 v[8], w[8];
+    const float4* p = reinterpret_cast<const float4*>(part2) + e;
+    for (int b0 = 0; b0 < ngroups; b0 += kInFlight) {
+      float4 v[kInFlight];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const double2* q = p + (size_t)min(b0 + u, ngroups - 1) * (W >> 1);
-        v[u] = __ldcg(q);
-        w[u] = __ldcg(q + 1);
-      }
+      for (int u = 0; u < kInFlight; ++u) v[u] = __ldcg(p + (size_t)min(b0 + u, ngroups - 1) * W4);
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (b0 + u < ngroups) { ax += v[u].x; ay += v[u].y; az += w[u].x; aw += w[u].y; }
+      for (int u = 0; u < kInFlight; ++u)
+        if (b0 + u < ngroups) { ax += (double)v[u].x; ay += (double)v[u].y; az += (double)v[u].z; aw += (double)v[u].w; }
     }
     fin[4 * e] = ax; fin[4 * e + 1] = ay; fin[4 * e + 2] = az; fin[4 * e + 3] = aw;
   }
@@ -184,9 +179,9 @@ __device__ __forceinline__ void reduce_rows(float4& a, float4& b, float4* sm, in
 
 // ---- forward statistics: shifted sums (shift = row 0) to avoid cancellation -------------
 // local_out != NULL (SyncBN): emit the rank-local (mean, M2, count) rows instead of finishing.
-__global__ void bn_stats_kernel(const float* __restrict__ y, long long rows_cap, int C,
+__global__ void __launch_bounds__(kBnThreads, 4) bn_stats_kernel(const float* __restrict__ y, long long rows_cap, int C,
                                 const int* __restrict__ rows_dev, long long rows_per_block,
-                                float* __restrict__ part, double* __restrict__ part2, int blocks,
+                                float* __restrict__ part, float* __restrict__ part2, int blocks,
                                 int grp, int ngroups, int* __restrict__ tickets, float eps,
                                 float momentum, float* __restrict__ mean, float* __restrict__ rstd,
                                 float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -311,12 +306,12 @@ __global__ void bn_act_fwd_kernel(const float4* __restrict__ y, const float4* __
 
 // ---- backward reduce: S1 = sum dyh, S2 = sum dyh * xh; epilogue writes dbeta / dgamma --------
 template <int ACT, int UN>
-__global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y,
+__global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y,
                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          long long rows_cap, int C, const int* __restrict__ rows_dev,
                                          long long rows_per_block, float* __restrict__ part,
-                                         double* __restrict__ part2, int blocks, int grp, int ngroups,
+                                         float* __restrict__ part2, int blocks, int grp, int ngroups,
                                          int* __restrict__ tickets, float* __restrict__ sums,
                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                          int accumulate) {
@@ -373,13 +368,13 @@ __global__ void bn_act_bwd_reduce_kernel(const float* __restrict__ dz, const flo
 // sums = (S1, S2) over ALL rows of the statistics (all ranks under SyncBN); inv_n = 1 / that
 // row count (device scalar) or NULL = 1 / this tensor's valid rows.
 template <int ACT, int UN>
-__global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y,
+__global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y,
                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                         const float* __restrict__ sums, const float* __restrict__ inv_n,
                                         long long rows_cap, int C, const int* __restrict__ rows_dev,
                                         long long rows_per_block, float* __restrict__ dy,
-                                        float* __restrict__ part, double* __restrict__ part2,
+                                        float* __restrict__ part, float* __restrict__ part2,
                                         int blocks, int grp, int ngroups, int* __restrict__ tickets,
                                         float* __restrict__ dbias, int accumulate) {
   extern __shared__ float4 sm[];
@@ -441,21 +436,38 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const floa
 }
 
 // out[e] (+)= sum_k part[k * n4 + e]  (float4 elements): the reduction over the split-K slabs
-// of the tall-skinny weight-gradient GEMMs, 8 slabs in flight per thread, fixed order.
+// of the tall-skinny weight-gradient GEMMs.  Block = 32 elements x 8 slab lanes: lane y adds the
+// slabs y, y+8, ... (all loads of a thread in flight at once), then the 8 lanes are added in
+// lane order: one L2 round trip, fixed order.
+constexpr int kSlabLanes = 8, kSlabMax = 8;    // <= 64 slabs per call
 __global__ void sum_slabs_kernel(const float4* __restrict__ part, int slabs, long long n4,
                                  float4* __restrict__ out, int accumulate) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n4) return;
-  float4 a = accumulate ? out[e] : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k0 = 0; k0 < slabs; k0 += 8) {
-    float4 v[8];
+  __shared__ float4 sm[kSlabLanes][32];
+  const long long e = (long long)blockIdx.x * 32 + threadIdx.x;
+  const int y = threadIdx.y;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e < n4) {
+    float4 v[kSlabMax];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(part + (size_t)min(k0 + u, slabs - 1) * n4 + e);
+    for (int u = 0; u < kSlabMax; ++u) {
+      const int k = y + u * kSlabLanes;
+      v[u] = __ldg(part + (size_t)min(k, slabs - 1) * n4 + e);
+    }
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (k0 + u < slabs) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+    for (int u = 0; u < kSlabMax; ++u)
+      if (y + u * kSlabLanes < slabs) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
   }
-  out[e] = a;
+  sm[y][threadIdx.x] = a;
+  __syncthreads();
+  if (y == 0 && e < n4) {
+    float4 r = accumulate ? out[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < kSlabLanes; ++t) {
+      const float4 x = sm[t][threadIdx.x];
+      r.x += x.x; r.y += x.y; r.z += x.z; r.w += x.w;
+    }
+    out[e] = r;
+  }
 }
 
 static bool bn_ok(int64_t rows, int64_t C) {
@@ -469,12 +481,12 @@ using namespace pgh;
 extern "C" size_t pgh_bn_ws_bytes(int64_t rows, int64_t C) {
   if (!bn_ok(rows, C)) return 256;
   const BnGeom g = bn_geom(rows, C);
-  return (size_t)g.blocks * 2 * C * sizeof(float) + 256 + (size_t)g.ngroups * 2 * C * sizeof(double);
+  return (size_t)g.blocks * 2 * C * sizeof(float) + 256 + (size_t)g.ngroups * 2 * C * sizeof(float);
 }
 
-static double* bn_part2(void* ws, const BnGeom& g, int64_t C) {
+static float* bn_part2(void* ws, const BnGeom& g, int64_t C) {
   size_t off = ((size_t)g.blocks * 2 * C * sizeof(float) + 255) & ~(size_t)255;
-  return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + off);
+  return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + off);
 }
 
 extern "C" int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, const int32_t* rows_dev,
@@ -496,12 +508,13 @@ extern "C" int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, const i
 
 extern "C" int pgh_sum_slabs_f32(const float* part, int64_t slabs, int64_t n, float* out,
                                  int accumulate, void* stream) {
-  if (!part || !out || slabs < 1 || n < 0 || (n & 3)) return arg_error("sum_slabs: arguments (n % 4 == 0)");
+  if (!part || !out || slabs < 1 || slabs > kSlabLanes * kSlabMax || n < 0 || (n & 3))
+    return arg_error("sum_slabs: arguments (1 <= slabs <= 64, n % 4 == 0)");
   if ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(out)) & 15)
     return arg_error("sum_slabs: tensors must be 16-byte aligned");
   if (n == 0) return 0;
   const long long n4 = n / 4;
-  sum_slabs_kernel<<<blocks_for(n4, 128), 128, 0, as_stream(stream)>>>(
+  sum_slabs_kernel<<<blocks_for(n4, 32), dim3(32, kSlabLanes), 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(part), (int)slabs, n4, reinterpret_cast<float4*>(out), accumulate);
   return check_launch("sum_slabs");
 }
