@@ -250,6 +250,20 @@ int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, const int32_t* row
 int pgh_bn_sync_finalize_f32(const float* gathered, int64_t world, int64_t C, float eps,
                              float momentum, float* mean, float* rstd, float* running_mean,
                              float* running_var, float* inv_n, void* stream);
+/* Linear layer with the BatchNorm statistics in its epilogue (honn/utils.py:85-142: nn.Linear
+ * followed by BatchNorm1d over all tuples): y = x @ w^T + bias for row-major x (M, K), w (N, K),
+ * and mean / rstd / running statistics of y over the valid rows exactly as pgh_bn_stats_f32
+ * would compute them from y (same argument meaning incl. rows_dev, local_out,
+ * num_batches_tracked, tickets) -- without a second pass over y.  TMA-fed tcgen05 TF32 GEMM
+ * (csrc/linear_stats.cu).  Supported shapes: pgh_linear_stats_supported() (N == 128, K % 32 == 0);
+ * ws: pgh_linear_stats_ws_bytes(M). */
+int pgh_linear_stats_supported(int64_t M, int64_t K, int64_t N);
+size_t pgh_linear_stats_ws_bytes(int64_t M);
+int pgh_linear_stats_f32(const float* x, int64_t M, int64_t K, const float* w, int64_t N,
+                         const float* bias, const int32_t* rows_dev, float* y, float eps,
+                         float momentum, float* mean, float* rstd, float* running_mean,
+                         float* running_var, float* local_out, int64_t* num_batches_tracked,
+                         void* ws, size_t ws_bytes, int32_t* tickets, void* stream);
 /* out[e] (+)= sum_k part[k * n + e], k < slabs, n % 4 == 0: reduction over the row slabs of a
  * split-K weight-gradient GEMM (dW = dy^T x over all tuples, honn/utils.py:85-142 backward),
  * optionally accumulating into the parameter's gradient buffer; fixed order */

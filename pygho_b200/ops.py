@@ -11,6 +11,7 @@ which call only these operators in both directions.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -431,6 +432,58 @@ _LIB.impl("bn_stats", _bn_stats_cuda, "CUDA")
 def _bn_stats_fake(y, eps, momentum, running_mean, running_var, rows_dev=None,
                    num_batches_tracked=None):
     return y.new_empty((y.shape[1],)), y.new_empty((y.shape[1],))
+
+
+_LIB.define("linear_stats(Tensor x, Tensor weight, Tensor? bias, float eps, float momentum, "
+            "Tensor(a!)? running_mean, Tensor(b!)? running_var, Tensor? rows_dev, "
+            "Tensor(c!)? num_batches_tracked, bool local) -> (Tensor, Tensor, Tensor)")
+
+
+def linear_stats_ok(x: Tensor, weight: Tensor) -> bool:
+    """The TMA / tcgen05 GEMM with the BatchNorm statistics in its epilogue (csrc/linear_stats.cu)
+    computes in TF32: it replaces cuBLAS only where cuBLAS would use TF32 too (the reference sets
+    float32_matmul_precision('high'), example/zinc.py:30) and for the shapes it supports."""
+    return (torch.backends.cuda.matmul.allow_tf32 and x.dtype == torch.float32 and x.ndim == 2
+            and x.is_cuda and weight.dtype == torch.float32 and x.shape[0] > 0
+            and bool(_lib.load().pgh_linear_stats_supported(x.shape[0], x.shape[1], weight.shape[0])))
+
+
+def _linear_stats_cuda(x, weight, bias, eps, momentum, running_mean, running_var, rows_dev,
+                       num_batches_tracked, local):
+    """-> (y, mean, rstd), or (y, local (3, C), empty) with ``local`` (SyncBN)."""
+    x, weight, bias = _f32c(x), _f32c(weight), _f32c(bias)
+    M, K = x.shape
+    N = weight.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    if local:
+        a = torch.empty((3, N), dtype=torch.float32, device=x.device)
+        b = a.new_empty((0,))
+        mean = rstd = None
+    else:
+        a = torch.empty((N,), dtype=torch.float32, device=x.device)
+        b = torch.empty_like(a)
+        mean, rstd = a, b
+    nws = int(_lib.load().pgh_linear_stats_ws_bytes(int(M)))
+    ws = torch.empty((nws,), dtype=torch.uint8, device=x.device)
+    call("pgh_linear_stats_f32", ptr(x), M, K, ptr(weight), N, ptr(bias), ptr(_rows_dev(rows_dev)),
+         ptr(y), float(eps), float(momentum), ptr(mean), ptr(rstd), ptr(running_mean),
+         ptr(running_var), ptr(a) if local else None, ptr(_nbt(num_batches_tracked)), ptr(ws),
+         ws.numel(), _tickets(x.device), stream_ptr(x.device))
+    _lib.count_launch()
+    return y, a, b
+
+
+_LIB.impl("linear_stats", _linear_stats_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::linear_stats")
+def _linear_stats_fake(x, weight, bias, eps, momentum, running_mean, running_var, rows_dev,
+                       num_batches_tracked, local):
+    N = weight.shape[0]
+    y = x.new_empty((x.shape[0], N))
+    if local:
+        return y, x.new_empty((3, N)), x.new_empty((0,))
+    return y, x.new_empty((N,)), x.new_empty((N,))
 
 
 _LIB.define("bn_stats_local(Tensor y, Tensor? rows_dev=None, "
@@ -938,6 +991,15 @@ def _tall_skinny_tn(a: Tensor, b: Tensor, chunks: int = 64, acc: Optional[Tensor
 
 
 _DIRECT_GRADS = True
+_FUSED_GEMM = os.environ.get("PYGHO_B200_FUSED_GEMM", "1") != "0"
+
+
+def set_fused_linear_stats(flag: bool) -> None:
+    """Use the TMA / tcgen05 GEMM with the statistics epilogue for Linear -> BatchNorm blocks
+    (default on; off = cuBLAS GEMM + separate statistics pass)."""
+    global _FUSED_GEMM
+    _FUSED_GEMM = bool(flag)
+
 
 
 def set_direct_grad_accumulation(flag: bool) -> None:
@@ -973,14 +1035,21 @@ class LinearBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, momentum, eps, act,
                 residual=None, rows_dev=None, group=None, num_batches_tracked=None):
-        y = torch.nn.functional.linear(x, weight, bias)
+        fused_gemm = _FUSED_GEMM and linear_stats_ok(x, weight)
         inv_n = None
+        if fused_gemm:      # GEMM + statistics in one pass (TMA + tcgen05, csrc/linear_stats.cu)
+            y, mean, rstd = _ops.linear_stats(x, weight, bias, eps, momentum, running_mean,
+                                              running_var, rows_dev, num_batches_tracked,
+                                              group is not None)
+        else:
+            y = torch.nn.functional.linear(x, weight, bias)
         if group is None:
-            mean, rstd = _ops.bn_stats(y, eps, momentum, running_mean, running_var, rows_dev,
-                                       num_batches_tracked)
+            if not fused_gemm:
+                mean, rstd = _ops.bn_stats(y, eps, momentum, running_mean, running_var, rows_dev,
+                                           num_batches_tracked)
         else:
             import torch.distributed as dist
-            local = _ops.bn_stats_local(y, rows_dev, num_batches_tracked)
+            local = mean if fused_gemm else _ops.bn_stats_local(y, rows_dev, num_batches_tracked)
             gathered = torch.empty((dist.get_world_size(group),) + tuple(local.shape),
                                    dtype=local.dtype, device=local.device)
             if dist.get_backend(group) == "nccl":

@@ -121,10 +121,12 @@ def rowptr_from_sorted(key32: Tensor, n_rows: int) -> Tensor:
 def csr_of(key32: Tensor, n_rows: int, assume_sorted: bool = False
            ) -> Tuple[Tensor, Optional[Tensor]]:
     """(rowptr, perm) of an int32 key array; ``perm`` is None when the caller knows the
-    keys are non-decreasing.  Sorting is stable, so a segment keeps the input order."""
+    keys are non-decreasing.  Sorting is stable, so a segment keeps the input order.
+    A key equal to ``n_rows`` means "no row": such entries sort behind ``rowptr[n_rows]`` and
+    are never visited (filler entries of capacity-padded plans, pygho_b200/static.py)."""
     if assume_sorted or key32.numel() == 0:
         return rowptr_from_sorted(key32, n_rows), None
-    ks, perm = sort_keys(to_i64(key32), max(1, int(n_rows - 1).bit_length()))
+    ks, perm = sort_keys(to_i64(key32), max(1, int(n_rows).bit_length()))
     return rowptr_from_sorted(to_i32(ks), n_rows), perm
 
 

@@ -8,8 +8,10 @@ is padded, at collate time, to a fixed *capacity* and the pads are built so that
 
 * pad nodes / edges / tuples sit at the END of their arrays; pad edges and tuples point at the
   last pad node, pad nodes belong to one extra "dummy" graph (``num_graphs = B + 1``);
-* pad plan triples connect pad rows with pad rows only (spread over the pad rows, so no row
-  becomes long), hence every value that reaches a pad row comes from pad rows;
+* pad plan triples are (n_out, n_a, n_b): one past the last row of each array.  A CSR grouping
+  built by a stable sort puts them after ``rowptr[n_rows]``, i.e. into NO row: the kernels
+  never visit them (they only walk ``[rowptr[r], rowptr[r + 1])``), so a padded batch costs
+  the segmented-reduce kernels exactly what the exact-size batch costs and no row gets long;
 * the fused BatchNorm kernels take the number of VALID rows from device memory
   (``rows_dev``, csrc/fused_mlp.cu): pad rows are excluded from the statistics, get output 0
   and gradient 0, so no weight gradient ever sees them;
@@ -90,13 +92,6 @@ def capacities(host_batches: Iterable[HostBatch], keys: Sequence[str], margin: f
     return caps
 
 
-def _spread(lo: int, hi: int, count: int) -> np.ndarray:
-    """``count`` non-decreasing row ids spread evenly over the pad rows [lo, hi)."""
-    if count == 0:
-        return np.zeros((0,), np.int64)
-    return lo + (np.arange(count, dtype=np.int64) * (hi - lo)) // count
-
-
 def pad_host_batch(hb: HostBatch, caps: dict, keys: Sequence[str]) -> HostBatch:
     """Pad a collated batch (with its host plans) to ``caps``; see the module docstring."""
     if hb.tupleid.shape[0] != 2:
@@ -127,9 +122,9 @@ def pad_host_batch(hb: HostBatch, caps: dict, keys: Sequence[str]) -> HostBatch:
         ops = ["A" if o == "A" else "X" for o in (o1, o2)]
         out = np.empty((3, Tc), np.int64)
         out[:, :T] = acd
-        out[0, T:] = _spread(nX, Xc, Tc - T)
-        out[1, T:] = _spread(*n_rows[ops[0]], Tc - T)
-        out[2, T:] = _spread(*n_rows[ops[1]], Tc - T)
+        out[0, T:] = Xc                         # "no row" markers (see the module docstring)
+        out[1, T:] = n_rows[ops[0]][1]
+        out[2, T:] = n_rows[ops[1]][1]
         plans[key] = out
     padded = replace(
         hb, num_graphs=B + 1, num_nodes=Nc,
