@@ -75,17 +75,19 @@ int pgh_seg_gmr_ld_f32(const float* a_val, int64_t lda, const int32_t* c, const 
                        float* out, int64_t ldo, void* stream);
 
 /* pgh_seg_gmr_ld_f32 with a fused row epilogue (dense % 128 == 0, 16-byte aligned rows, sum or
- * mean):  out[r,:] = (add_src ? add_src[r,:] : 0) + reduction(r)   and, if copy_src != NULL,
- * copy_dst[r,:] = copy_src[r,:].  One SSWL layer uses it twice: the forward writes X next to
- * X (x) A in the concatenated buffer (reference Conv.py:97-103 `catvalue`) without a separate
- * copy, the backward starts the accumulation of dX from the gradient slice instead of cloning
- * it first.                                                                                   */
+ * mean):  out[r,:] = add_src[r,:] + reduction(r) (+ add_src2[r,:])   and, if copy_src != NULL,
+ * copy_dst[r,:] = copy_src[r,:]; add_src / add_src2 may be NULL (add_src2 needs add_src).  One
+ * SSWL layer uses it twice: the forward writes X next to X (x) A in the concatenated buffer
+ * (reference Conv.py:97-103 `catvalue`) without a separate copy; the backward adds the gradient
+ * slice of the concatenation AND the gradient of the residual connection (example/zinc.py:286,
+ * X + conv(X)) to dX inside the reduction instead of two more passes over the tuples.       */
 int pgh_seg_gmr_fused_f32(const float* a_val, int64_t lda, const int32_t* c, const float* a_scale,
                           const float* b_val, int64_t ldb, const int32_t* d, const int32_t* rowptr,
                           int64_t n_rows, int64_t n_entries, int64_t dense, int aggr,
-                          const float* add_src, int64_t ld_add, const float* copy_src,
-                          int64_t ld_copy_src, float* copy_dst, int64_t ld_copy_dst, float* out,
-                          int64_t ldo, void* stream);
+                          const float* add_src, int64_t ld_add, const float* add_src2,
+                          int64_t ld_add2, const float* copy_src, int64_t ld_copy_src,
+                          float* copy_dst, int64_t ld_copy_dst, float* out, int64_t ldo,
+                          void* stream);
 
 /* max/min backward, step 1: gscaled[r,:] = grad[r,:] / (#{t in seg(r): A(t)*B(t) == out[r,:]}
  *                                                       + [out[r,:] == 0])

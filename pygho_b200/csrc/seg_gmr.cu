@@ -295,6 +295,7 @@ seg_gmr_lean_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
                     const int* __restrict__ d, const int* __restrict__ rowptr,
                     long long n_rows, int dense, int lda, int ldb, int ldo, int rw,
                     const float* __restrict__ acc_src, int lds,
+                    const float* __restrict__ acc_src2, int lds2,
                     const float* __restrict__ copy_src, int ldcs, float* __restrict__ copy_dst,
                     int ldcd, float* __restrict__ out) {
   constexpr unsigned kFull = 0xffffffffu;
@@ -334,6 +335,12 @@ seg_gmr_lean_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
           acc_src + (size_t)(r0 + cur) * lds + col);                                    \
       r_ = make_float4(__fadd_rn(o_.x, r_.x), __fadd_rn(o_.y, r_.y),                    \
                        __fadd_rn(o_.z, r_.z), __fadd_rn(o_.w, r_.w));                   \
+      if (acc_src2) {  /* second addend (warp-uniform): out = (acc_src + red) + acc_src2 */ \
+        const float4 p_ = __ldg(reinterpret_cast<const float4*>(                        \
+            acc_src2 + (size_t)(r0 + cur) * lds2 + col));                               \
+        r_ = make_float4(__fadd_rn(r_.x, p_.x), __fadd_rn(r_.y, p_.y),                  \
+                         __fadd_rn(r_.z, p_.z), __fadd_rn(r_.w, p_.w));                 \
+      }                                                                                 \
     }                                                                                   \
     *reinterpret_cast<float4*>(o_ptr) = r_;                                             \
     o_ptr += ldo;                                                                       \
@@ -428,150 +435,6 @@ seg_gmr_lean_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
           }
         }
       }
-    }
-    while (cur < nr) PGH_FLUSH();
-#undef PGH_REDUCE
-#undef PGH_FLUSH
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// Software-pipelined lean variant (variants 34 / 35, opt-in; measured SLOWER: 61.2 us vs 52.2 us
-// for the default lean kernel on the SSWL key, profiles/gmr_variants.py): same split, order and
-// epilogue as seg_gmr_lean_kernel, but groups of 2 entries are double-buffered in registers
-// (the same 32 value registers as 4 entries single-buffered): the loads of group g+1 are in
-// flight while group g is reduced.  Motivation: 52 % of the lean kernel's stall samples sit on
-// the first FMA after a load group.
-template <int AGGR, bool HAS_B, bool HAS_SCALE, bool ACCUM, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
-seg_gmr_lean_pipe_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
-                    const float* __restrict__ a_scale, const float* __restrict__ b_val,
-                    const int* __restrict__ d, const int* __restrict__ rowptr,
-                    long long n_rows, int dense, int lda, int ldb, int ldo, int rw,
-                    const float* __restrict__ acc_src, int lds,
-                    const float* __restrict__ copy_src, int ldcs, float* __restrict__ copy_dst,
-                    int ldcd, float* __restrict__ out) {
-  constexpr unsigned kFull = 0xffffffffu;
-  constexpr bool kLen = (AGGR != PGH_SUM);          // row lengths matter (mean, empty max/min rows)
-  const int lane = threadIdx.x & 31;
-  const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  const long long r0 = warp * rw;
-  if (r0 >= n_rows) return;
-  const int nr = (int)min((long long)rw, n_rows - r0);
-  int rp = 0;
-  if (lane <= nr) rp = rowptr ? __ldg(rowptr + r0 + lane) : (int)(r0 + lane);
-  const int e_beg = __shfl_sync(kFull, rp, 0);
-  const int e_end = __shfl_sync(kFull, rp, nr);
-  const float init = (AGGR == PGH_MAX) ? -INFINITY : (AGGR == PGH_MIN) ? INFINITY : 0.f;
-  for (int col = lane * 4; col < dense; col += 128) {
-    const float* __restrict__ a_col = a_val + col;
-    const float* __restrict__ b_col = HAS_B ? b_val + col : nullptr;
-    float* __restrict__ o_ptr = out + (size_t)r0 * ldo + col;      // row being reduced
-    float4 acc = make_float4(init, init, init, init);
-    int cur = 0;
-    int cur_beg = e_beg;
-    int cur_end = __shfl_sync(kFull, rp, 1);
-#define PGH_FLUSH()                                                                     \
-  do {                                                                                  \
-    float4 r_ = acc;                                                                    \
-    if (kLen) {                                                                         \
-      const int len_ = cur_end - cur_beg;                                               \
-      cur_beg = cur_end;                                                                \
-      if (len_ == 0) r_ = make_float4(0.f, 0.f, 0.f, 0.f);                              \
-      else if (AGGR == PGH_MEAN) {                                                      \
-        const float n_ = (float)len_;                                                   \
-        r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);               \
-      }                                                                                 \
-    }                                                                                   \
-    if (ACCUM) {       /* out = acc_src + reduction (acc_src == out: accumulate in place) */ \
-      const float4 o_ = *reinterpret_cast<const float4*>(                               \
-          acc_src + (size_t)(r0 + cur) * lds + col);                                    \
-      r_ = make_float4(__fadd_rn(o_.x, r_.x), __fadd_rn(o_.y, r_.y),                    \
-                       __fadd_rn(o_.z, r_.z), __fadd_rn(o_.w, r_.w));                   \
-    }                                                                                   \
-    *reinterpret_cast<float4*>(o_ptr) = r_;                                             \
-    o_ptr += ldo;                                                                       \
-    if (copy_src)      /* fused row copy: copy_dst[row] = copy_src[row] (warp-uniform) */  \
-      *reinterpret_cast<float4*>(copy_dst + (size_t)(r0 + cur) * ldcd + col) =          \
-          __ldg(reinterpret_cast<const float4*>(copy_src + (size_t)(r0 + cur) * ldcs + col)); \
-    acc = make_float4(init, init, init, init);                                          \
-    ++cur;                                                                              \
-    cur_end = __shfl_sync(kFull, rp, cur + 1);      /* source lane wraps mod 32 */      \
-  } while (0)
-#define PGH_REDUCE(AV, BV, SS)                                                          \
-  do {                                                                                  \
-    float4 m_ = AV;                                                                     \
-    if (HAS_SCALE)                                                                      \
-      m_ = make_float4(__fmul_rn(m_.x, SS), __fmul_rn(m_.y, SS), __fmul_rn(m_.z, SS),   \
-                       __fmul_rn(m_.w, SS));                                            \
-    if (AGGR == PGH_MAX || AGGR == PGH_MIN) {                                           \
-      if (HAS_B)                                                                        \
-        m_ = make_float4(__fmul_rn(m_.x, BV.x), __fmul_rn(m_.y, BV.y),                  \
-                         __fmul_rn(m_.z, BV.z), __fmul_rn(m_.w, BV.w));                 \
-      if (AGGR == PGH_MAX)                                                              \
-        acc = make_float4(fmaxf(acc.x, m_.x), fmaxf(acc.y, m_.y), fmaxf(acc.z, m_.z),   \
-                          fmaxf(acc.w, m_.w));                                          \
-      else                                                                              \
-        acc = make_float4(fminf(acc.x, m_.x), fminf(acc.y, m_.y), fminf(acc.z, m_.z),   \
-                          fminf(acc.w, m_.w));                                          \
-    } else if (HAS_B) {                                                                 \
-      acc = make_float4(__fmaf_rn(m_.x, BV.x, acc.x), __fmaf_rn(m_.y, BV.y, acc.y),     \
-                        __fmaf_rn(m_.z, BV.z, acc.z), __fmaf_rn(m_.w, BV.w, acc.w));    \
-    } else {                                                                            \
-      acc = make_float4(__fadd_rn(acc.x, m_.x), __fadd_rn(acc.y, m_.y),                 \
-                        __fadd_rn(acc.z, m_.z), __fadd_rn(acc.w, m_.w));                \
-    }                                                                                   \
-  } while (0)
-    for (int base = e_beg; base < e_end; base += 32) {
-      const int t = base + lane;
-      int ci = 0, di = 0;
-      float sc = 1.f;
-      if (t < e_end) {
-        ci = c ? __ldg(c + t) : t;
-        if (HAS_B) di = d ? __ldg(d + t) : t;
-        if (HAS_SCALE) sc = __ldg(a_scale + ci);
-      }
-      const int chunk = min(32, e_end - base);
-      // software pipeline over groups of 2 entries with two register buffers: the loads of
-      // group g+1 are issued BEFORE group g is reduced, so a warp always has loads in flight
-      float4 a0[2], b0[2], a1[2], b1[2];
-      float s0[2], s1[2];
-#define PGH_LOAD2(K, AV, BV, SS)                                                        \
-  do {                                                                                  \
-    _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                     \
-      const int kk_ = min((K) + u, chunk - 1);       /* clamped: loads unconditional */   \
-      const int cc_ = __shfl_sync(kFull, ci, kk_);                                      \
-      AV[u] = __ldg(reinterpret_cast<const float4*>(a_col + (size_t)cc_ * lda));        \
-      if (HAS_B) {                                                                      \
-        const int dd_ = __shfl_sync(kFull, di, kk_);                                    \
-        BV[u] = __ldg(reinterpret_cast<const float4*>(b_col + (size_t)dd_ * ldb));      \
-      }                                                                                 \
-      if (HAS_SCALE) SS[u] = __shfl_sync(kFull, sc, kk_);                               \
-    }                                                                                   \
-  } while (0)
-#define PGH_REDUCE2(K, AV, BV, SS)                                                      \
-  do {                                                                                  \
-    _Pragma("unroll") for (int u = 0; u < 2; ++u) {                                     \
-      if ((K) + u < chunk) {                                                            \
-        const int tt = base + (K) + u;                                                  \
-        if (tt >= cur_end) {                                                            \
-          do PGH_FLUSH(); while (tt >= cur_end);                                        \
-        }                                                                               \
-        PGH_REDUCE(AV[u], BV[u], SS[u]);                                                \
-      }                                                                                 \
-    }                                                                                   \
-  } while (0)
-      PGH_LOAD2(0, a0, b0, s0);
-#pragma unroll 1
-      for (int k = 0; k < chunk; k += 4) {
-        if (k + 2 < chunk) PGH_LOAD2(k + 2, a1, b1, s1);
-        PGH_REDUCE2(k, a0, b0, s0);
-        if (k + 2 >= chunk) break;
-        if (k + 4 < chunk) PGH_LOAD2(k + 4, a0, b0, s0);
-        PGH_REDUCE2(k + 2, a1, b1, s1);
-      }
-#undef PGH_REDUCE2
-#undef PGH_LOAD2
     }
     while (cur < nr) PGH_FLUSH();
 #undef PGH_REDUCE
@@ -742,204 +605,6 @@ seg_gmr_ring_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
       }
     }
     cp_async_wait<0>();
-    while (cur < nr) PGH_FLUSH();
-#undef PGH_ISSUE
-#undef PGH_LOAD_PLAN
-#undef PGH_FLUSH
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// Bulk-copy variant (dense % 128 == 0): the same work split and the same sequential reduction
-// order again, but every 512 B value row travels global -> shared memory as ONE bulk async
-// copy (cp.async.bulk / UBLKCP, completion counted in bytes on an mbarrier) issued by a single
-// lane, instead of 32 lanes x LDG.128 / LDGSTS.  A warp owns NS stages of G plan entries
-// (G x OPS rows of 512 B each) and one mbarrier per stage; stages are refilled as soon as they
-// have been read, so up to NS*G*OPS rows per warp are in flight with no register cost and two
-// instructions per entry.  Ablation of the register-staged kernel (profiles/r1_gmr_ablate.txt):
-// with perfectly sequential operands and no stores it still needs 48 us for 148 MB -- it is
-// bound by its own load -> wait -> reduce cycle, not by HBM; this variant decouples the two.
-// Per-warp barriers only: no CTA-wide synchronisation, warps retire independently.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-// bounded wait: a lost completion traps (reported as a launch error) instead of hanging
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t spin = 0; spin < (1u << 14); ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(100000u)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-
-template <int AGGR, bool HAS_B, int G, int NS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-seg_gmr_bulk_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
-                    const float* __restrict__ a_scale, const float* __restrict__ b_val,
-                    const int* __restrict__ d, const int* __restrict__ rowptr,
-                    long long n_rows, int dense, int lda, int ldb, int ldo, int rw, int accum,
-                    float* __restrict__ out) {
-  static_assert(32 % G == 0 && NS * G + G <= 32, "stage geometry (plan registers span 64 entries)");
-  constexpr unsigned kFull = 0xffffffffu;
-  constexpr int OPS = HAS_B ? 2 : 1;
-  constexpr uint32_t kStage = G * OPS * 512;        // bytes per stage
-  extern __shared__ __align__(128) unsigned char bulk_smem[];
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const uint32_t data0 = smem_addr(bulk_smem) + (uint32_t)wib * NS * kStage;
-  const uint32_t bar0 = smem_addr(bulk_smem) + (uint32_t)WARPS * NS * kStage + (uint32_t)wib * NS * 8u;
-  if (lane < NS) mbar_init(bar0 + lane * 8u, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncwarp();
-  const long long warp = (long long)blockIdx.x * WARPS + wib;
-  const long long r0 = warp * rw;
-  if (r0 >= n_rows) return;
-  const int nr = (int)min((long long)rw, n_rows - r0);
-  int rp = 0;
-  if (lane <= nr) rp = rowptr ? __ldg(rowptr + r0 + lane) : (int)(r0 + lane);
-  const int e_beg = __shfl_sync(kFull, rp, 0);
-  const int e_end = __shfl_sync(kFull, rp, nr);
-  const float init = (AGGR == PGH_MAX) ? -INFINITY : (AGGR == PGH_MIN) ? INFINITY : 0.f;
-  uint32_t fill_idx = 0, cons_idx = 0;              // stage groups issued / consumed so far
-  for (int col0 = 0; col0 < dense; col0 += 128) {
-    const float* __restrict__ a_col = a_val + col0;
-    const float* __restrict__ b_col = HAS_B ? b_val + col0 : nullptr;
-    float* __restrict__ o_col = out + (size_t)r0 * ldo + col0 + lane * 4;
-    float4 acc = make_float4(init, init, init, init);
-    int cur = 0;
-    int cur_beg = e_beg;
-    int cur_end = __shfl_sync(kFull, rp, 1);
-#define PGH_FLUSH()                                                                     \
-  do {                                                                                  \
-    const int len_ = cur_end - cur_beg;                                                 \
-    float4 r_ = acc;                                                                    \
-    if (len_ == 0) r_ = make_float4(0.f, 0.f, 0.f, 0.f);                                \
-    else if (AGGR == PGH_MEAN) {                                                        \
-      const float n_ = (float)len_;                                                     \
-      r_ = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);                 \
-    }                                                                                   \
-    if (accum) {                                                                        \
-      const float4 o_ = *reinterpret_cast<const float4*>(o_col + (size_t)cur * ldo);    \
-      r_ = make_float4(__fadd_rn(o_.x, r_.x), __fadd_rn(o_.y, r_.y),                    \
-                       __fadd_rn(o_.z, r_.z), __fadd_rn(o_.w, r_.w));                   \
-    }                                                                                   \
-    *reinterpret_cast<float4*>(o_col + (size_t)cur * ldo) = r_;                         \
-    acc = make_float4(init, init, init, init);                                          \
-    ++cur;                                                                              \
-    cur_beg = cur_end;                                                                  \
-    cur_end = __shfl_sync(kFull, rp, min(cur + 1, 31));                                 \
-  } while (0)
-    int ci0 = 0, di0 = 0, ci1 = 0, di1 = 0;
-    float sc0 = 1.f, sc1 = 1.f;
-#define PGH_LOAD_PLAN(BASE, CI, DI, SC)                                                 \
-  do {                                                                                  \
-    const int t_ = (BASE) + lane;                                                       \
-    CI = 0; DI = 0; SC = 1.f;                                                           \
-    if (t_ < e_end) {                                                                   \
-      CI = c ? __ldg(c + t_) : t_;                                                      \
-      if (HAS_B) DI = d ? __ldg(d + t_) : t_;                                           \
-      if (a_scale) SC = __ldg(a_scale + CI);                                            \
-    }                                                                                   \
-  } while (0)
-    PGH_LOAD_PLAN(e_beg, ci0, di0, sc0);
-    PGH_LOAD_PLAN(e_beg + 32, ci1, di1, sc1);
-    int chunk_base = e_beg;                         // first entry held by ci0 / di0 / sc0
-    int ti = e_beg;                                 // next entry to issue
-// fill the next stage with entries ti .. ti+G-1: lane u issues the row copies of entry ti+u
-#define PGH_ISSUE()                                                                     \
-  do {                                                                                  \
-    if (ti < e_end) {                                                                   \
-      const uint32_t s_ = fill_idx % NS;                                                \
-      const int nvalid_ = min(G, e_end - ti);                                           \
-      const uint32_t bar_ = bar0 + s_ * 8u;                                             \
-      if (lane == 0) mbar_expect_tx(bar_, (uint32_t)nvalid_ * OPS * 512u);              \
-      __syncwarp();                                                                     \
-      const int off_ = ti + lane - chunk_base;      /* < 64 for the issuing lanes */      \
-      const int c_lo_ = __shfl_sync(kFull, ci0, off_ & 31);                             \
-      const int c_hi_ = __shfl_sync(kFull, ci1, off_ & 31);                             \
-      const int d_lo_ = HAS_B ? __shfl_sync(kFull, di0, off_ & 31) : 0;                 \
-      const int d_hi_ = HAS_B ? __shfl_sync(kFull, di1, off_ & 31) : 0;                 \
-      if (lane < nvalid_) {                                                             \
-        const uint32_t dst_ = data0 + s_ * kStage + (uint32_t)(lane * OPS) * 512u;      \
-        const int cc_ = off_ < 32 ? c_lo_ : c_hi_;                                      \
-        bulk_g2s(dst_, a_col + (size_t)cc_ * lda, 512u, bar_);                          \
-        if (HAS_B) {                                                                    \
-          const int dd_ = off_ < 32 ? d_lo_ : d_hi_;                                    \
-          bulk_g2s(dst_ + 512u, b_col + (size_t)dd_ * ldb, 512u, bar_);                 \
-        }                                                                               \
-      }                                                                                 \
-      ++fill_idx;                                                                       \
-      ti += G;                                                                          \
-    }                                                                                   \
-  } while (0)
-#pragma unroll
-    for (int g = 0; g < NS; ++g) PGH_ISSUE();
-    for (int tc = e_beg; tc < e_end; tc += G) {
-      const uint32_t s = cons_idx % NS;
-      mbar_wait(bar0 + s * 8u, (cons_idx / NS) & 1u);
-      const uint32_t base = data0 + s * kStage + (uint32_t)lane * 16u;
-      float4 av[G], bv[G];
-      float ss[G];
-#pragma unroll
-      for (int u = 0; u < G; ++u) {                 // unfilled slots hold stale bytes: unused
-        av[u] = lds128(base + (uint32_t)(u * OPS) * 512u);
-        if (HAS_B) bv[u] = lds128(base + (uint32_t)(u * OPS) * 512u + 512u);
-        ss[u] = a_scale ? __shfl_sync(kFull, sc0, (tc + u - chunk_base) & 31) : 1.f;
-      }
-#pragma unroll
-      for (int u = 0; u < G; ++u) {
-        if (tc + u < e_end) {
-          const int tt = tc + u;
-          while (tt >= cur_end) PGH_FLUSH();
-          float4 m = av[u];
-          if (a_scale)
-            m = make_float4(__fmul_rn(m.x, ss[u]), __fmul_rn(m.y, ss[u]), __fmul_rn(m.z, ss[u]),
-                            __fmul_rn(m.w, ss[u]));
-          if (HAS_B)
-            m = make_float4(__fmul_rn(m.x, bv[u].x), __fmul_rn(m.y, bv[u].y),
-                            __fmul_rn(m.z, bv[u].z), __fmul_rn(m.w, bv[u].w));
-          if (AGGR == PGH_MAX)
-            acc = make_float4(fmaxf(acc.x, m.x), fmaxf(acc.y, m.y), fmaxf(acc.z, m.z), fmaxf(acc.w, m.w));
-          else if (AGGR == PGH_MIN)
-            acc = make_float4(fminf(acc.x, m.x), fminf(acc.y, m.y), fminf(acc.z, m.z), fminf(acc.w, m.w));
-          else
-            acc = make_float4(__fadd_rn(acc.x, m.x), __fadd_rn(acc.y, m.y),
-                              __fadd_rn(acc.z, m.z), __fadd_rn(acc.w, m.w));
-        }
-      }
-      ++cons_idx;
-      // every lane has its values in registers: the stage may be overwritten
-      __syncwarp();
-      PGH_ISSUE();
-      if (tc + G - chunk_base >= 32) {              // consume pointer enters the next chunk
-        chunk_base += 32;
-        ci0 = ci1; di0 = di1; sc0 = sc1;
-        PGH_LOAD_PLAN(chunk_base + 32, ci1, di1, sc1);
-      }
-    }
     while (cur < nr) PGH_FLUSH();
 #undef PGH_ISSUE
 #undef PGH_LOAD_PLAN
@@ -1118,8 +783,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 
 // run-time tuning knobs (pgh_set_tuning): [0] seg_gmr variant (-1 = built-in choice),
-// [1] ring kernel: target plan entries per warp, [6] profiling: no row stores,
-// [7] bulk kernel: target plan entries per warp (default 32)
+// [1] ring kernel: target plan entries per warp, [6] profiling: no row stores
 // [2..5] fused BN kernels (fused_mlp.cu)
 int g_tune[8] = {-1, 16, 0, 0, 0, 0, 0, 0};
 
@@ -1174,59 +838,12 @@ static void launch_ring(int variant, cudaStream_t s, const float* a_val, const i
 }
 
 
-template <int AGGR, bool HAS_B, int G, int NS, int WARPS>
-static void launch_bulk_t(cudaStream_t s, const float* a_val, const int* c, const float* a_scale,
-                          const float* b_val, const int* d, const int* rowptr, int64_t n_rows,
-                          int dense, int lda, int ldb, int ldo, int rw, int accum, float* out) {
-  constexpr int smem = WARPS * NS * G * (HAS_B ? 2 : 1) * 512 + WARPS * NS * 8;
-  auto kern = seg_gmr_bulk_kernel<AGGR, HAS_B, G, NS, WARPS>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured = true;
-  }
-  const unsigned nb = blocks_for(n_rows, WARPS * rw);
-  kern<<<nb, WARPS * 32, smem, s>>>(a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb,
-                                    ldo, rw, accum, out);
-}
-
-// variants 20..: bulk-copy kernel; g_tune[1] = target plan entries per warp (as for the ring)
-template <int AGGR>
-static void launch_bulk(int variant, cudaStream_t s, const float* a_val, const int* c,
-                        const float* a_scale, const float* b_val, const int* d,
-                        const int* rowptr, int64_t n_rows, int64_t n_entries, int dense, int lda,
-                        int ldb, int ldo, int accum, float* out) {
-  int rw = 16;
-  if (n_entries > 0 && n_rows > 0) {
-    const double avg = (double)n_entries / (double)n_rows;
-    rw = (int)((double)(g_tune[7] > 0 ? g_tune[7] : 32) / (avg > 0.5 ? avg : 0.5));
-  }
-  if (rw < 1) rw = 1;
-  if (rw > 31) rw = 31;
-#define PGH_BULK(G, NS, W)                                                                   \
-  do {                                                                                       \
-    if (b_val) launch_bulk_t<AGGR, true, G, NS, W>(s, a_val, c, a_scale, b_val, d, rowptr,   \
-                                                   n_rows, dense, lda, ldb, ldo, rw, accum,  \
-                                                   out);                                     \
-    else launch_bulk_t<AGGR, false, G, NS, W>(s, a_val, c, a_scale, b_val, d, rowptr,        \
-                                              n_rows, dense, lda, ldb, ldo, rw, accum, out); \
-  } while (0)
-  switch (variant) {
-    case 21: PGH_BULK(8, 3, 4); break;    // 96 KB (two operands): 2 CTAs/SM
-    case 22: PGH_BULK(4, 4, 8); break;    // 128 KB: 1 CTA/SM, 8 warps
-    case 23: PGH_BULK(4, 6, 4); break;    // 96 KB: 2 CTAs/SM
-    case 24: PGH_BULK(8, 3, 2); break;    // 48 KB: 4 CTAs/SM
-    case 25: PGH_BULK(4, 2, 4); break;    // 32 KB: 6-7 CTAs/SM
-    default: PGH_BULK(4, 4, 4); break;    // 20: 64 KB: 3 CTAs/SM
-  }
-#undef PGH_BULK
-}
-
-
 // variants 30..: lean streaming kernel (see seg_gmr_lean_kernel)
 struct LeanExtra {                       // optional fused epilogue work, all row-aligned with out
   const float* add_src = nullptr;        // out = add_src + reduction (NULL + accum: in place)
   int ld_add = 0;
+  const float* add_src2 = nullptr;       // optional second addend (needs add_src or accum)
+  int ld_add2 = 0;
   const float* copy_src = nullptr;       // copy_dst[row] = copy_src[row]
   int ld_copy_src = 0;
   float* copy_dst = nullptr;
@@ -1245,35 +862,17 @@ static void launch_lean(cudaStream_t s, const float* a_val, const int* c, const 
 #define PGH_LEAN(B, S, A)                                                                      \
   seg_gmr_lean_kernel<AGGR, B, S, A, U, MINB><<<nb, kThreads, 0, s>>>(                         \
       a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, acc_src, lds,     \
-      x.copy_src, x.ld_copy_src, x.copy_dst, x.ld_copy_dst, out)
+      x.add_src2, x.ld_add2, x.copy_src, x.ld_copy_src, x.copy_dst, x.ld_copy_dst, out)
   const int sel = (b_val ? 4 : 0) | (a_scale ? 2 : 0) | (acc ? 1 : 0);
-  if constexpr (U == 0) {                             // U == 0 selects the pipelined kernel
-#define PGH_LEANP(B, S, A)                                                                     \
-  seg_gmr_lean_pipe_kernel<AGGR, B, S, A, MINB><<<nb, kThreads, 0, s>>>(                       \
-      a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, acc_src, lds,     \
-      x.copy_src, x.ld_copy_src, x.copy_dst, x.ld_copy_dst, out)
-    switch (sel) {
-      case 0: PGH_LEANP(false, false, false); break;
-      case 1: PGH_LEANP(false, false, true); break;
-      case 2: PGH_LEANP(false, true, false); break;
-      case 3: PGH_LEANP(false, true, true); break;
-      case 4: PGH_LEANP(true, false, false); break;
-      case 5: PGH_LEANP(true, false, true); break;
-      case 6: PGH_LEANP(true, true, false); break;
-      default: PGH_LEANP(true, true, true); break;
-    }
-#undef PGH_LEANP
-  } else {
-    switch (sel) {
-      case 0: PGH_LEAN(false, false, false); break;
-      case 1: PGH_LEAN(false, false, true); break;
-      case 2: PGH_LEAN(false, true, false); break;
-      case 3: PGH_LEAN(false, true, true); break;
-      case 4: PGH_LEAN(true, false, false); break;
-      case 5: PGH_LEAN(true, false, true); break;
-      case 6: PGH_LEAN(true, true, false); break;
-      default: PGH_LEAN(true, true, true); break;
-    }
+  switch (sel) {
+    case 0: PGH_LEAN(false, false, false); break;
+    case 1: PGH_LEAN(false, false, true); break;
+    case 2: PGH_LEAN(false, true, false); break;
+    case 3: PGH_LEAN(false, true, true); break;
+    case 4: PGH_LEAN(true, false, false); break;
+    case 5: PGH_LEAN(true, false, true); break;
+    case 6: PGH_LEAN(true, true, false); break;
+    default: PGH_LEAN(true, true, true); break;
   }
 #undef PGH_LEAN
 }
@@ -1313,16 +912,12 @@ static int launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, con
       const LeanExtra& x = extra ? *extra : none;
       if (variant == 31) launch_lean<AGGR, 8, 2>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
       else if (variant == 32) launch_lean<AGGR, 2, 5>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
-      else if (variant == 34) launch_lean<AGGR, 0, 4>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
-      else if (variant == 35) launch_lean<AGGR, 0, 5>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
       else if (variant == 33) launch_lean<AGGR, 4, 3>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
       else launch_lean<AGGR, 4, 4>(s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out, x);
       return 0;
     }
-    if (variant >= 20) {
-      launch_bulk<AGGR>(variant, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, n_entries, dense, lda, ldb, ldo, accum, out);
-      return 0;
-    }
+    if (variant >= 20)      // 20-25 (bulk copy) and 34/35 (register pipelining) were round-1
+      variant = 13;         // negative results: archived under profiles/probes/, not shipped
     if (variant >= 10) {
       launch_ring<AGGR>(variant, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, n_entries, dense, lda, ldb, ldo, accum, out);
       return 0;
@@ -1421,13 +1016,18 @@ extern "C" int pgh_seg_gmr_fused_f32(const float* a_val, int64_t lda, const int3
                                      const float* a_scale, const float* b_val, int64_t ldb,
                                      const int32_t* d, const int32_t* rowptr, int64_t n_rows,
                                      int64_t n_entries, int64_t dense, int aggr,
-                                     const float* add_src, int64_t ld_add, const float* copy_src,
+                                     const float* add_src, int64_t ld_add, const float* add_src2,
+                                     int64_t ld_add2, const float* copy_src,
                                      int64_t ld_copy_src, float* copy_dst, int64_t ld_copy_dst,
                                      float* out, int64_t ldo, void* stream) {
   if (!a_val || !out) return arg_error("seg_gmr_fused: a_val and out are required");
   if (n_rows < 0 || dense <= 0 || dense % 128 != 0) return arg_error("seg_gmr_fused: dense % 128");
   if (aggr < 0 || aggr > 1) return arg_error("seg_gmr_fused: sum or mean only");
   if ((copy_src == nullptr) != (copy_dst == nullptr)) return arg_error("seg_gmr_fused: copy pair");
+  if (add_src2 && !add_src) return arg_error("seg_gmr_fused: add_src2 needs add_src");
+  if (add_src2 && (ld_add2 < dense || ld_add2 > 0x7fffffff || ld_add2 % 4 ||
+                   (reinterpret_cast<uintptr_t>(add_src2) & 15)))
+    return arg_error("seg_gmr_fused: add_src2 layout");
   const int64_t lim = 0x7fffffff;
   if (lda < dense || ldo < dense || (b_val && ldb < dense) || lda > lim || ldb > lim || ldo > lim ||
       (add_src && (ld_add < dense || ld_add > lim)) ||
@@ -1445,6 +1045,7 @@ extern "C" int pgh_seg_gmr_fused_f32(const float* a_val, int64_t lda, const int3
   if (!rowptr) n_entries = n_rows;
   LeanExtra x;
   x.add_src = add_src; x.ld_add = (int)ld_add;
+  x.add_src2 = add_src2; x.ld_add2 = (int)ld_add2;
   x.copy_src = copy_src; x.ld_copy_src = (int)ld_copy_src;
   x.copy_dst = copy_dst; x.ld_copy_dst = (int)ld_copy_dst;
   const int la = (int)lda, lb = (int)(b_val ? ldb : dense), lo = (int)ldo;

@@ -48,17 +48,24 @@ class SSWLConv(Module):
         training scripts (example/zinc.py:286) without a separate pass over the tuples."""
         res = None if residual is None else (
             residual.values if isinstance(residual, SparseTensor) else residual.data)
-        lin = self.lin if res is None else (lambda v: self.lin(v, res))
-        fused = self._fused_cat(A, X, datadict)
+        # residual is X itself (the training scripts' X + conv(X)): tap it inside the aggregate
+        # so that its gradient is added to dX by the backward kernel (no extra pass)
+        tap = residual is not None and isinstance(X, SparseTensor) and res is X.values
+        fused = self._fused_cat(A, X, datadict, tap)
         if fused is not None:
-            return X.tuplewiseapply(lambda _v: lin(fused))
+            cat, tapped = fused
+            if tapped is not None:
+                res = tapped
+            return X.tuplewiseapply(lambda _v: self.lin(cat) if res is None else self.lin(cat, res))
+        lin = self.lin if res is None else (lambda v: self.lin(v, res))
         inside = self.aggr1.forward(A, X, datadict, X)
         across = self.aggr2.forward(A, X, datadict, X)
         return X.catvalue([inside, across], True).tuplewiseapply(lin)
 
-    def _fused_cat(self, A, X, datadict):
+    def _fused_cat(self, A, X, datadict, tap_residual=False):
         """[X, X(x)A, A(x)X] written into one buffer by the two spspmm launches (sparse mode,
-        precomputed plans, sum/mean, 2-D float32 values); None -> generic path."""
+        precomputed plans, sum/mean, 2-D float32 values) -> (buffer, tapped X or None);
+        None -> generic path."""
         from ..backend.SpTensor import SparseTensor as _Sp
         from ..honn.SpOperator import KEYSEP
         if not (isinstance(A, _Sp) and isinstance(X, _Sp)):
@@ -80,8 +87,11 @@ class SSWLConv(Module):
         from ..ops import SswlAggregate
         plan_xa = P.plan_from_acd(acd1, X.nnz, X.nnz, A.nnz)
         plan_ax = P.plan_from_acd(acd2, X.nnz, A.nnz, X.nnz)
-        return SswlAggregate.apply(xv.contiguous(), av.contiguous(), plan_xa, plan_ax,
-                                   0 if m1.aggr == "sum" else 1)
+        if tap_residual and not xv.is_contiguous():
+            tap_residual = False
+        out = SswlAggregate.apply(xv.contiguous(), av.contiguous(), plan_xa, plan_ax,
+                                  0 if m1.aggr == "sum" else 1, tap_residual)
+        return out if tap_residual else (out, None)
 
 
 class I2Conv(Module):

@@ -114,7 +114,7 @@ def _seg_gmr_out_fake(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, out, ac
 
 _LIB.define("seg_gmr_fused(Tensor a_val, Tensor? c, Tensor? a_scale, Tensor? b_val, Tensor? d, "
             "Tensor? rowptr, int n_rows, int aggr, Tensor? add_src, Tensor? copy_src, "
-            "Tensor(a!)? copy_dst, Tensor(b!) out) -> ()")
+            "Tensor(a!)? copy_dst, Tensor(b!) out, Tensor? add_src2=None) -> ()")
 
 
 def _row_view_ok(t: Optional[Tensor], n_rows: int, dense: int) -> bool:
@@ -131,11 +131,12 @@ def fused_epilogue_ok(dense: int, *views) -> bool:
 
 
 def _seg_gmr_fused_cuda(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, add_src, copy_src,
-                        copy_dst, out):
+                        copy_dst, out, add_src2=None):
     a_val, b_val, a_scale = _rows2d(a_val), _rows2d(b_val), _f32c(a_scale)
     c, d, rowptr = _i32c(c), _i32c(d), _i32c(rowptr)
     dense = a_val.shape[1]
-    for name, t in (("out", out), ("add_src", add_src), ("copy_src", copy_src), ("copy_dst", copy_dst)):
+    for name, t in (("out", out), ("add_src", add_src), ("copy_src", copy_src), ("copy_dst", copy_dst),
+                    ("add_src2", add_src2)):
         if not _row_view_ok(t, n_rows, dense):
             raise ValueError(f"seg_gmr_fused: {name} must be a float32 (n_rows, dense) row-contiguous view")
     if n_rows == 0:
@@ -149,7 +150,7 @@ def _seg_gmr_fused_cuda(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, add_s
     call("pgh_seg_gmr_fused_f32", ptr(a_val), a_val.stride(0), ptr(c), ptr(a_scale), ptr(b_val),
          b_val.stride(0) if b_val is not None else dense, ptr(d), ptr(rowptr), n_rows, n_entries,
          dense, aggr, ptr(add_src), add_src.stride(0) if add_src is not None else 0,
-         ptr(copy_src), copy_src.stride(0) if copy_src is not None else 0, ptr(copy_dst),
+         ptr(add_src2), add_src2.stride(0) if add_src2 is not None else 0, ptr(copy_src), copy_src.stride(0) if copy_src is not None else 0, ptr(copy_dst),
          copy_dst.stride(0) if copy_dst is not None else 0, ptr(out), out.stride(0),
          stream_ptr(a_val.device))
     _lib.count_launch()
@@ -160,7 +161,7 @@ _LIB.impl("seg_gmr_fused", _seg_gmr_fused_cuda, "CUDA")
 
 @torch.library.register_fake("pygho_b200::seg_gmr_fused")
 def _seg_gmr_fused_fake(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, add_src, copy_src,
-                        copy_dst, out):
+                        copy_dst, out, add_src2=None):
     return None
 
 
@@ -443,8 +444,9 @@ def linear_stats_ok(x: Tensor, weight: Tensor) -> bool:
     """The TMA / tcgen05 GEMM with the BatchNorm statistics in its epilogue (csrc/linear_stats.cu)
     computes in TF32: it replaces cuBLAS only where cuBLAS would use TF32 too (the reference sets
     float32_matmul_precision('high'), example/zinc.py:30) and for the shapes it supports."""
+    # below a few thousand rows the pipeline set-up and the ticketed tail outweigh the saved pass
     return (torch.backends.cuda.matmul.allow_tf32 and x.dtype == torch.float32 and x.ndim == 2
-            and x.is_cuda and weight.dtype == torch.float32 and x.shape[0] > 0
+            and x.is_cuda and weight.dtype == torch.float32 and x.shape[0] >= _FUSED_GEMM_MIN_ROWS
             and bool(_lib.load().pgh_linear_stats_supported(x.shape[0], x.shape[1], weight.shape[0])))
 
 
@@ -877,10 +879,15 @@ class SswlAggregate(torch.autograd.Function):
     """``cat([X, X (x) A, A (x) X], -1)`` of one SSWL layer (reference Conv.py:97-103) built in
     ONE buffer: the two spspmm launches write their column slice directly, and the three
     gradient contributions to X (two to A) are accumulated by the kernels themselves instead of
-    materialising temporaries and adding them.  sum / mean aggregation."""
+    materialising temporaries and adding them.  sum / mean aggregation.
+
+    With ``tap_residual`` the function also returns ``Xv`` itself as a second output: feeding
+    THAT tensor to the residual connection (``X + conv(X)``, example/zinc.py:286) routes the
+    residual's gradient into this backward, where it is added to dX inside the same kernel --
+    X then has a single consumer and autograd needs no separate add pass over all tuples."""
 
     @staticmethod
-    def forward(ctx, Xv, Av, plan_xa, plan_ax, aggr):
+    def forward(ctx, Xv, Av, plan_xa, plan_ax, aggr, tap_residual=False):
         n, d = Xv.shape
         cat = torch.empty((n, 3 * d), dtype=torch.float32, device=Xv.device)
         g1, g2 = plan_xa.group("a"), plan_ax.group("a")
@@ -894,11 +901,13 @@ class SswlAggregate(torch.autograd.Function):
         _ops.seg_gmr_out(Av, g2.first, None, Xv, g2.second, g2.rowptr, n, aggr, cat[:, 2 * d:], False)
         ctx.save_for_backward(Xv, Av)
         ctx.cfg = (plan_xa, plan_ax, aggr)
+        if tap_residual:
+            return cat, Xv.view_as(Xv)
         return cat
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, g):
+    def backward(ctx, g, g_res=None):
         Xv, Av = ctx.saved_tensors
         plan_xa, plan_ax, aggr = ctx.cfg
         n, d = Xv.shape
@@ -909,12 +918,15 @@ class SswlAggregate(torch.autograd.Function):
         gX = gA = None
         if ctx.needs_input_grad[0]:
             c = plan_xa.group("c")       # X is operand A of X (x) A
-            if n and nA and fused_epilogue_ok(d, g, Av):
-                # gX = g0 + sum(...) in one launch: no clone of the gradient slice
+            if n and nA and fused_epilogue_ok(d, g, Av, g_res):
+                # gX = g0 + sum(...) (+ residual gradient) in one launch: no clone, no add pass
                 gX = torch.empty((n, d), dtype=torch.float32, device=g.device)
-                _ops.seg_gmr_fused(g1, c.first, s1, Av, c.second, c.rowptr, n, 0, g0, None, None, gX)
+                _ops.seg_gmr_fused(g1, c.first, s1, Av, c.second, c.rowptr, n, 0, g0, None, None, gX,
+                                   g_res)
             else:
                 gX = g0.contiguous() if not g0.is_contiguous() else g0.clone()
+                if g_res is not None:
+                    gX.add_(g_res)
                 _ops.seg_gmr_out(g1, c.first, s1, Av, c.second, c.rowptr, n, 0, gX, True)
             dd = plan_ax.group("d")      # X is operand B of A (x) X
             _ops.seg_gmr_out(g2, dd.first, s2, Av, dd.second, dd.rowptr, n, 0, gX, True)
@@ -923,7 +935,7 @@ class SswlAggregate(torch.autograd.Function):
             gA = _ops.seg_gmr(g1, dd.first, s1, Xv, dd.second, dd.rowptr, nA, 0)
             c = plan_ax.group("c")       # A is operand A of A (x) X
             _ops.seg_gmr_out(g2, c.first, s2, Xv, c.second, c.rowptr, nA, 0, gA, True)
-        return gX, gA, None, None, None
+        return gX, gA, None, None, None, None
 
 
 class EmbeddingGather(torch.autograd.Function):
@@ -992,6 +1004,7 @@ def _tall_skinny_tn(a: Tensor, b: Tensor, chunks: int = 64, acc: Optional[Tensor
 
 _DIRECT_GRADS = True
 _FUSED_GEMM = os.environ.get("PYGHO_B200_FUSED_GEMM", "1") != "0"
+_FUSED_GEMM_MIN_ROWS = 4096
 
 
 def set_fused_linear_stats(flag: bool) -> None:

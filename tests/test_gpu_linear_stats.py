@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import torch
 
+import pygho_b200.ops  # noqa: F401  (registers torch.ops.pygho_b200.*)
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TF32_TOL = 2e-3          # relative to the largest |y|: 10-bit mantissa products, fp32 accumulation
