@@ -201,11 +201,6 @@ int mamamm_tc_launch(const float* A, int trans_a, const float* B, int trans_b,
                      int64_t n_j, int64_t n_k, int64_t dense, int pipelined, float* out,
                      cudaStream_t s);
 
-int mamamm_tma_supported(int64_t n_i, int64_t n_j, int64_t n_k, int64_t dense);
-int mamamm_tma_launch(const float* A, int trans_a, const float* B, int trans_b,
-                      const unsigned char* mask, const int* ext, int64_t b, int64_t n_i, int64_t n_j,
-                      int64_t n_k, int64_t dense, float* out, cudaStream_t s);
-
 // ext[b] = (1 + last row with a valid entry, 1 + last column with a valid entry) of a
 // (b, n1, n2) mask; one CTA per graph
 __global__ void mask_extents_kernel(const unsigned char* __restrict__ mask, int n1, int n2,
@@ -243,9 +238,6 @@ extern "C" int pgh_mamamm_f32(const float* A, int trans_a, const float* B, int t
   if (b < 0 || n_i <= 0 || n_j <= 0 || n_k <= 0 || dense <= 0) return arg_error("mamamm: sizes");
   if (b == 0) return 0;
   cudaStream_t s = as_stream(stream);
-  // 3 = tcgen05 fed by TMA boxes that ARE the (MN-major) UMMA operands (mamamm_tma.cu)
-  if (algo == 3)
-    return mamamm_tma_launch(A, trans_a, B, trans_b, mask, ext, b, n_i, n_j, n_k, dense, out, s);
   // 1 = tcgen05, one CTA per (graph, slab); 2 = tcgen05, persistent warp-specialised pipeline
   // (falls back to 1 when two tile stages do not fit in shared memory)
   if (algo == 1 || algo == 2)

@@ -780,11 +780,9 @@ def _ext3(eX: Optional[Tensor], tx: bool, eY: Optional[Tensor], ty: bool, eM: Op
 
 def mamamm_algo_for(algo: int, n_i: int, n_j: int, n_k: int, dense: int) -> int:
     """The tensor-core kernels (algo 1 / 2) hold one (n_i x n_j) and one (n_j x n_k) tile per
-    channel: n_i, n_j <= 128, n_k <= 64, dense % 8 == 0; the TMA-staged kernel (algo 3) takes
-    n_j, n_k <= 64, dense % 4 == 0.  Anything else runs on the exact-fp32 kernel (algo 0).  Decided per CALL: the gradient contractions of a forward that fits may
+    channel: n_i, n_j <= 128, n_k <= 64, dense % 8 == 0.  Anything else runs on the exact-fp32 kernel
+    (algo 0).  Decided per CALL: the gradient contractions of a forward that fits may
     not fit themselves (their (n_i, n_j, n_k) roles are permuted)."""
-    if algo == 3 and (dense % 4 != 0 or n_j > 64 or n_k > 64):
-        algo = 2          # TMA-staged kernel: box menu up to 64 rows
     if algo in (1, 2) and (dense % 8 != 0 or n_i > 128 or n_k > 64 or n_j > 128):
         return 0
     return algo

@@ -397,7 +397,7 @@ def test_full_size_properties(B):
 
 
 # -------------------------------------------------------------------------------- masked
-@pytest.mark.parametrize("algo,tol", [(0, 1e-5), (1, 1e-2), (2, 1e-2), (3, 1e-2)])
+@pytest.mark.parametrize("algo,tol", [(0, 1e-5), (1, 1e-2), (2, 1e-2)])
 def test_masked_golden(B, golden, monkeypatch, algo, tol):
     monkeypatch.setenv("PYGHO_B200_MAMAMM_ALGO", str(algo))
     g = golden("masked")
@@ -427,7 +427,7 @@ def test_masked_constructor_fills_pads(B):
     assert float(mt.fill_masked(5.0).sum()) == 16.0 + 5.0 * (72 - 16)
 
 
-@pytest.mark.parametrize("algo,tol", [(0, 2e-5), (1, 1e-2), (2, 1e-2), (3, 1e-2)])
+@pytest.mark.parametrize("algo,tol", [(0, 2e-5), (1, 1e-2), (2, 1e-2)])
 @pytest.mark.parametrize("d1,d2", [(2, 1), (1, 1), (1, 2), (2, 2)])
 def test_mamamm_forward_backward(B, monkeypatch, d1, d2, algo, tol):
     monkeypatch.setenv("PYGHO_B200_MAMAMM_ALGO", str(algo))
@@ -498,11 +498,6 @@ def test_mamamm_tcgen05_matches_fp32_kernel(n, d, ta, tb):
         assert torch.equal(pipe, got)
         # the fp32 kernel with extents is bit-identical to the one without
         assert torch.equal(torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, e, 0), ref)
-        # TMA-staged kernel (algo 3): the TMA boxes are the MN-major UMMA operands; same TF32
-        # products, summed by the tensor core in one K = 8 step per 8 j like algo 1 / 2
-        tma = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, e, 3)
-        assert float((tma - ref).abs().max()) <= 1e-2 * scale
-        assert float(tma[~mask].abs().max()) == 0.0
     from pygho_b200.ops import mask_extents
     assert torch.equal(mask_extents(mask).cpu(), torch.stack((sizes, sizes), 1).to(torch.int32))
     torch.cuda.synchronize()
@@ -533,29 +528,6 @@ def test_mamamm_pipeline_many_items():
         assert torch.equal(pipe, one)
         assert float(pipe[~holes].abs().max()) == 0.0
         assert float((pipe - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
-        torch.full((b, n, n, d), float("nan"), device=DEV)
-        tma = torch.ops.pygho_b200.mamamm(A, False, Bm, False, holes, e, 3)
-        assert float(tma[~holes].abs().max()) == 0.0
-        assert float((tma - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
-    torch.cuda.synchronize()
-
-
-@pytest.mark.parametrize("b,ni,nj,nk,d", [(3, 70, 33, 12, 16), (2, 9, 64, 64, 8), (4, 33, 20, 40, 132),
-                                          (1, 128, 5, 7, 4)])
-def test_mamamm_tma_rectangular_shapes(b, ni, nj, nk, d):
-    """algo 3 on non-square operands: several 32-row tiles of i, n_j / n_k up to the box-menu
-    limit, widths that are only multiples of 4, every transposition."""
-    import pygho_b200.ops  # noqa: F401
-    gen = torch.Generator().manual_seed(ni * 7 + nk)
-    mask = (torch.rand((b, ni, nk), generator=gen) < 0.85).to(DEV)
-    for ta in (False, True):
-        for tb in (False, True):
-            A = torch.randn((b, nj, ni, d) if ta else (b, ni, nj, d), generator=gen).to(DEV)
-            Bm = torch.randn((b, nk, nj, d) if tb else (b, nj, nk, d), generator=gen).to(DEV)
-            ref = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, None, 0)
-            got = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, None, 3)
-            assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
-            assert float(got[~mask].abs().max()) == 0.0
     torch.cuda.synchronize()
 
 
