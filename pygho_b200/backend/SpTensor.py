@@ -252,13 +252,25 @@ class SparseTensor:
 
     def _diag_to_dense(self, dims: List[int]) -> Tensor:
         if len(dims) != self._sd:
-            raise NotImplementedError(
-                "diag over a subset of the sparse dims is used by GNNAK/SUN only "
-                "(out of scope, SURVEY.md 8f)")
+            return self._diag_subset_to_dense(dims)
         pos, n = self._diag_lookup(dims)
         plan = _gather_plan(pos, self.nnz)
         flat, dshape = _flatten_dense(self._values)
         return seg_gmr(flat, None, plan, "sum").reshape((n,) + dshape)
+
+    def _diag_subset_to_dense(self, dims: List[int]) -> Tensor:
+        """Diagonal over a SUBSET of the sparse dims (reference SpTensor.py:336-352): the result
+        keeps ``dims[0]`` and every non-diagonal dim, ``ret[i, k, ...] = X[i, i, k, ...]``.
+        The reference looks each diagonal coordinate up with ONE searchsorted on the hash of the
+        diagonal dims only, so it finds a single tuple per diagonal value and fills one ``k``;
+        this implements the documented meaning (all tuples whose diagonal dims coincide).  Rarely
+        used (3-D tensors only), plain torch indexing: gradients flow through ``index_put``."""
+        idx = [i for i in range(self._sd) if i not in dims[1:]]
+        on_diag = (self._indices[dims] == self._indices[dims[0]].unsqueeze(0)).all(dim=0)
+        out = torch.zeros(tuple(self._shape[i] for i in idx) + self.denseshape,
+                          dtype=self._values.dtype, device=self._values.device)
+        coords = tuple(self._indices[i][on_diag] for i in idx)
+        return out.index_put(coords, self._values[on_diag])
 
     def _diag_to_sparse(self, dims: List[int]) -> "SparseTensor":
         raise NotImplementedError(

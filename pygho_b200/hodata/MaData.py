@@ -83,3 +83,74 @@ def to_dense_adj(edge_index: LongTensor, edge_batch: LongTensor, edge_attr: Opti
              _raw(filled_value, attr.dtype), ptr(out), ptr(mask), stream_ptr(dev))
         _lib.count_launch(2)
     return MaskedTensor(out, mask, filled_value, True)
+
+
+def to_sparse_adj(edge_index: LongTensor, edge_batch: LongTensor, edge_attr: Optional[Tensor] = None,
+                  max_num_nodes: Optional[int] = None, batch_size: Optional[int] = None):
+    """(b, n, n) SparseTensor of a batch's edges with LOCAL node ids (reference
+    ``hodata/MaData.py:74-106``): indices = (edge_batch, row, col), not assumed coalesced."""
+    from ..backend.SpTensor import SparseTensor
+    if max_num_nodes is None:
+        max_num_nodes = int(edge_index.max().item()) + 1
+    if batch_size is None:
+        batch_size = int(torch.max(edge_batch).item()) + 1
+    size = [batch_size, max_num_nodes, max_num_nodes]
+    if edge_attr is not None:
+        size += list(edge_attr.shape[1:])
+    ind = torch.cat((edge_batch.unsqueeze(0), edge_index), dim=0)
+    return SparseTensor(ind, edge_attr, shape=size, is_coalesced=False)
+
+
+def to_dense_tuplefeat(tuplefeat: Tensor, tupleshape: LongTensor, tuplefeatptr: LongTensor,
+                       max_tupleshape: Optional[LongTensor] = None, batch_size: Optional[int] = None,
+                       feat2mask=None) -> MaskedTensor:
+    """Pad the row-major tuple features of every subgraph to ``(b, n1, n2, ..., *dense)``
+    (reference ``hodata/MaData.py:152-212``): graph g's block of shape ``tupleshape[g]`` starts
+    at ``tuplefeat[tuplefeatptr[g]]``.  Built on the device with index arithmetic; positions
+    outside a graph's own shape are masked and hold 0 (the reference gathers clamped garbage
+    there and relies on the mask)."""
+    dev = _lib.require_cuda(tuplefeat, tupleshape, tuplefeatptr)
+    if batch_size is None:
+        batch_size = tupleshape.shape[0]
+    if max_tupleshape is None:
+        max_tupleshape = torch.amax(tupleshape, dim=0)
+    dims = [int(v) for v in (max_tupleshape.tolist() if isinstance(max_tupleshape, Tensor)
+                             else max_tupleshape)]
+    ndim = len(dims)
+    shape = tupleshape.to(dev)
+    src = tuplefeatptr[:-1].to(dev).reshape([batch_size] + [1] * ndim)
+    valid = torch.ones([batch_size] + dims, dtype=torch.bool, device=dev)
+    stride = torch.ones((batch_size,), dtype=torch.long, device=dev)
+    for k in range(ndim - 1, -1, -1):                    # row-major: last dim is contiguous
+        view = [1] * (ndim + 1)
+        view[k + 1] = dims[k]
+        ar = torch.arange(dims[k], device=dev).reshape(view)
+        bview = [batch_size] + [1] * ndim
+        src = src + ar * stride.reshape(bview)
+        valid = valid & (ar < shape[:, k].reshape(bview))
+        stride = stride * shape[:, k]
+    src = torch.where(valid, src, torch.zeros_like(src)).clamp_(0, max(tuplefeat.shape[0] - 1, 0))
+    data = tuplefeat[src] if tuplefeat.shape[0] else tuplefeat.new_zeros(tuple(src.shape) + tuple(tuplefeat.shape[1:]))
+    mask = valid if feat2mask is None else (valid & feat2mask(data))
+    return MaskedTensor(data, mask, 0, False)
+
+
+def batch2dense(batch, batch_size: Optional[int] = None, max_num_nodes: Optional[int] = None,
+                denseadj: bool = False, keys=("",)):
+    """Convert and pad the per-graph arrays of a collated batch object to dense forms, in place
+    (reference ``hodata/MaData.py:215-255``).  ``batch`` is any object with the reference's
+    attribute names: ``x``, ``ptr``, ``edge_index`` (local ids), ``edge_index_batch``,
+    ``edge_attr`` and, per key, ``tuplefeat<key>``, ``tupleshape<key>``, ``tuplefeat<key>_ptr``."""
+    batch.x = to_dense_x(batch.x, batch.ptr, max_num_nodes, batch_size)
+    batch_size, max_num_nodes = batch.x.shape[0], batch.x.shape[1]
+    if denseadj:
+        batch.A = to_dense_adj(batch.edge_index, batch.edge_index_batch, batch.edge_attr,
+                               max_num_nodes, batch_size)
+    else:
+        batch.A = to_sparse_adj(batch.edge_index, batch.edge_index_batch, batch.edge_attr,
+                                max_num_nodes, batch_size)
+    for key in keys:
+        X = to_dense_tuplefeat(getattr(batch, f"tuplefeat{key}"), getattr(batch, f"tupleshape{key}"),
+                               getattr(batch, f"tuplefeat{key}_ptr"), None, batch_size, None)
+        setattr(batch, f"X{key}", X)
+    return batch

@@ -174,3 +174,71 @@ def test_ma_datadict_device_padding_matches_host(dev):
     spd = ma_datadict(hb, dev, max_dist=3, tuples="spd")["X"].data.cpu().numpy()
     g0 = H.spd_matrix(hb.edge_index[:, hb.batch[hb.edge_index[0]] == 0], int(sizes[0]), 3)
     assert np.array_equal(spd[0, :sizes[0], :sizes[0]], g0)
+
+
+def test_to_dense_tuplefeat_batch2dense_and_batch2sparse(dev, golden):
+    """``to_dense_tuplefeat`` against the reference's golden output (hodata/MaData.py:152-212);
+    ``batch2dense`` / ``batch2sparse`` / ``collate_sparse`` build the reference's batch
+    attributes (MaData.py:215-255, SpData.py:56-112) from per-graph arrays."""
+    from types import SimpleNamespace
+    from pygho_b200.hodata import MaData, SpData
+    from pygho_b200.hodata.synthetic import make_graphs, collate
+    g = golden("hodata")
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    mt = MaData.to_dense_tuplefeat(T(g["dt_feat"]), T(g["dt_shape"]), T(g["dt_ptr"]))
+    assert np.array_equal(mt.mask.cpu().numpy(), g["dt_mask"])
+    assert np.array_equal(mt.data.cpu().numpy(), g["dt_data"])
+    # batch2dense on the same arrays + the dense-x / adjacency goldens
+    batch = SimpleNamespace(x=T(g["dx_x"]), ptr=T(g["dx_ptr"]), edge_index=T(g["da_ei"]),
+                            edge_index_batch=T(g["da_eb"]), edge_attr=T(g["da_ea"]),
+                            tuplefeat=T(g["dt_feat"]), tupleshape=T(g["dt_shape"]),
+                            tuplefeat_ptr=T(g["dt_ptr"]))
+    MaData.batch2dense(batch, denseadj=True)
+    assert np.array_equal(batch.x.data.cpu().numpy(), g["dx_data"])
+    assert np.array_equal(batch.A.data.cpu().numpy(), g["da_data"])
+    assert np.array_equal(batch.X.data.cpu().numpy(), g["dt_data"])
+    batch2 = SimpleNamespace(x=T(g["dx_x"]), ptr=T(g["dx_ptr"]), edge_index=T(g["da_ei"]),
+                             edge_index_batch=T(g["da_eb"]), edge_attr=T(g["da_ea"]),
+                             tuplefeat=T(g["dt_feat"]), tupleshape=T(g["dt_shape"]),
+                             tuplefeat_ptr=T(g["dt_ptr"]))
+    MaData.batch2dense(batch2, denseadj=False)
+    A = batch2.A
+    assert A.sparse_dim == 3 and tuple(A.shape[:3]) == (4, 6, 6)
+    dense = torch.zeros(4, 6, 6, dtype=A.values.dtype, device=dev)
+    dense[A.indices[0], A.indices[1], A.indices[2]] = A.values
+    assert np.array_equal(dense.cpu().numpy(), g["da_data"])
+    # sparse collate: per-graph dicts -> the block-diagonal batch of synthetic.collate
+    graphs = make_graphs(4, seed=7)
+    hb = collate(graphs)
+    dicts = [dict(x=torch.from_numpy(gr.x), edge_index=torch.from_numpy(gr.edge_index),
+                  edge_attr=torch.from_numpy(gr.edge_attr), tupleid=torch.from_numpy(gr.tupleid),
+                  tuplefeat=torch.from_numpy(gr.tuplefeat),
+                  tupleshape=torch.tensor([gr.num_nodes, gr.num_nodes]), y=gr.y) for gr in graphs]
+    b = SpData.collate_sparse(dicts)
+    assert np.array_equal(b.tupleid.numpy(), hb.tupleid) and np.array_equal(b.edge_index.numpy(), hb.edge_index)
+    assert np.array_equal(b.batch.numpy(), hb.batch)
+    for k, v in vars(b).items():
+        if isinstance(v, torch.Tensor):
+            setattr(b, k, v.to(dev))
+    SpData.batch2sparse(b)
+    assert tuple(b.X.shape) == (hb.num_nodes, hb.num_nodes) and b.X.nnz == hb.tupleid.shape[1]
+    assert tuple(b.A.shape) == (hb.num_nodes, hb.num_nodes)
+
+
+def test_diag_over_a_subset_of_dims(dev):
+    """3-D tuples, diagonal over dims (0, 1): ret[i, k] = X[i, i, k] for every k."""
+    from pygho_b200 import SparseTensor
+    gen = torch.Generator().manual_seed(3)
+    n, d = 7, 5
+    full = (torch.rand((n, n, n), generator=gen) < 0.4)
+    ind = full.nonzero().t().contiguous().to(dev)
+    val = torch.randn((ind.shape[1], d), generator=gen).to(dev).requires_grad_(True)
+    X = SparseTensor(ind, val, (n, n, n, d), True)
+    got = X.diag([0, 1])
+    dense = torch.zeros(n, n, n, d, device=dev)
+    dense[ind[0], ind[1], ind[2]] = val.detach()
+    want = torch.stack([dense[i, i] for i in range(n)])
+    assert torch.equal(got, want)
+    got.sum().backward()
+    on = (ind[0] == ind[1]).float().unsqueeze(1).expand(-1, d)
+    assert torch.equal(val.grad, on)
