@@ -20,8 +20,11 @@
 //
 // TF32 like the reference on a GPU (example/zinc.py:30 set_float32_matmul_precision('high')).
 // HBM-bound by design: per 128-row tile 128 x K x 4 B in, 64 KB out; W stays in L2.
-// Shapes: N == 128, K % 32 == 0 (every large Linear of the SSWL+/NGNN/DSSGNN/PPGN/I2 models);
-// anything else is left to cuBLAS by the caller.
+// Shapes: N in {128, 256, 384}, K % 32 == 0 (every large Linear of the SSWL+/NGNN/DSSGNN/PPGN/I2
+// models: 128 -> 128, 384 -> 128, 384 -> 384, 256 -> 128); anything else is left to cuBLAS by the
+// caller.  N = 128 * NT: the W box is loaded as NT sub-tiles of 128 rows, the accumulator is
+// 128 x N (double-buffered in TMEM while 2 N <= 512 columns, single-buffered for N = 384: the
+// TMA ring keeps filling during the epilogue), N = 384 is issued as a 256- and a 128-column MMA.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -29,13 +32,20 @@
 
 namespace pgh {
 
-constexpr int kLsBM = 128, kLsBN = 128, kLsBK = 32;
-constexpr int kLsStages = 5;
-constexpr int kLsTileBytes = kLsBM * kLsBK * 4;            // 16 KB per operand per stage
-constexpr int kLsStageBytes = 2 * kLsTileBytes;
+constexpr int kLsBM = 128, kLsBK = 32;
+constexpr int kLsTileBytes = kLsBM * kLsBK * 4;            // 16 KB: 128 rows x 32 K-elements
 constexpr int kLsThreads = 256;
-constexpr int kLsTmemCols = 256;                           // 2 accumulators x 128 columns
-constexpr size_t kLsSmemBytes = (size_t)kLsStages * kLsStageBytes + 1024;   // + alignment slack
+constexpr int kLsMaxStages = 5;
+
+template <int NT>
+struct LsCfg {
+  static constexpr int N = 128 * NT;
+  static constexpr int kStages = NT == 1 ? 5 : 3;
+  static constexpr int kStageBytes = (1 + NT) * kLsTileBytes;
+  static constexpr int kAccBufs = (2 * N <= 512) ? 2 : 1;
+  static constexpr int kTmemCols = NT == 1 ? 256 : 512;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024;   // + alignment slack
+};
 
 __device__ __forceinline__ uint32_t ls_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -153,9 +163,10 @@ __device__ __forceinline__ float ls_transpose_reduce(float (&v)[32], int lane) {
 }
 
 struct LsBars {
-  unsigned long long full[kLsStages], empty[kLsStages], tfull[2], tempty[2];
+  unsigned long long full[kLsMaxStages], empty[kLsMaxStages], tfull[2], tempty[2];
 };
 
+template <int NT>
 __global__ void __launch_bounds__(kLsThreads, 1)
 linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const float* __restrict__ bias, long long M, int K, const int* __restrict__ rows_dev,
@@ -167,6 +178,9 @@ linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   extern __shared__ unsigned char ls_smem_raw[];
   __shared__ LsBars bars;
   __shared__ uint32_t tmem_holder;
+  using Cfg = LsCfg<NT>;
+  constexpr int kLsBN = Cfg::N, kLsStages = Cfg::kStages, kLsStageBytes = Cfg::kStageBytes;
+  constexpr int kLsTmemCols = Cfg::kTmemCols, kBufs = Cfg::kAccBufs;
   __shared__ float s_part[4][2][kLsBN];            // per epilogue warp: column sums / sums of squares
   __shared__ double s_fin[2 * kLsBN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -211,7 +225,9 @@ linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           const uint32_t dst = ring + (uint32_t)stage * kLsStageBytes;
           ls_mbar_expect_tx(full, kLsStageBytes);
           ls_tma_load_2d(dst, &map_x, full, kb * kLsBK, row0);
-          ls_tma_load_2d(dst + kLsTileBytes, &map_w, full, kb * kLsBK, 0);
+#pragma unroll
+          for (int t = 0; t < NT; ++t)
+            ls_tma_load_2d(dst + (1 + t) * kLsTileBytes, &map_w, full, kb * kLsBK, t * 128);
           if (++stage == kLsStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -219,13 +235,14 @@ linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t idesc = ls_idesc_tf32(kLsBM, kLsBN);
+      const uint32_t idesc = ls_idesc_tf32(kLsBM, NT == 3 ? 256 : kLsBN);
+      const uint32_t idesc_tail = ls_idesc_tf32(kLsBM, 128);          // NT == 3: columns 256..383
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        const int buf = kBufs == 2 ? (it & 1) : 0;
+        const uint32_t aphase = (uint32_t)(kBufs == 2 ? (it >> 1) : it) & 1u;
         ls_mbar_wait(ls_smem_u32(&bars.tempty[buf]), aphase ^ 1u);   // epilogue drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_base + (uint32_t)buf * kLsBN;
@@ -235,9 +252,14 @@ linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           const uint32_t a_addr = ring + (uint32_t)stage * kLsStageBytes;
           const uint32_t b_addr = a_addr + kLsTileBytes;
 #pragma unroll
-          for (int k = 0; k < kLsBK / 8; ++k)
+          for (int k = 0; k < kLsBK / 8; ++k) {
             ls_umma_tf32(acc, ls_desc_sw128(a_addr + k * 32), ls_desc_sw128(b_addr + k * 32), idesc,
                          (uint32_t)((kb | k) != 0));
+            if (NT == 3)      // W rows 256..383 = third 16 KB sub-tile, accumulator columns 256..
+              ls_umma_tf32(acc + 256, ls_desc_sw128(a_addr + k * 32),
+                           ls_desc_sw128(b_addr + 2 * kLsTileBytes + k * 32), idesc_tail,
+                           (uint32_t)((kb | k) != 0));
+          }
           ls_umma_commit(ls_smem_u32(&bars.empty[stage]));           // slot free once the MMAs retire
           if (++stage == kLsStages) { stage = 0; phase ^= 1u; }
         }
@@ -247,18 +269,20 @@ linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global, column statistics =====
     const int q = warp - 4;                       // TMEM lane quarter this warp may access
-    double acc_s[4] = {0.0, 0.0, 0.0, 0.0}, acc_q[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc_s[4 * NT], acc_q[4 * NT];
+#pragma unroll
+    for (int i = 0; i < 4 * NT; ++i) acc_s[i] = acc_q[i] = 0.0;
     int it = 0;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const int buf = kBufs == 2 ? (it & 1) : 0;
+      const uint32_t aphase = (uint32_t)(kBufs == 2 ? (it >> 1) : it) & 1u;
       ls_mbar_wait(ls_smem_u32(&bars.tfull[buf]), aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const long long row = (long long)tile * kLsBM + q * 32 + lane;
       const bool row_ok = row < M, row_valid = row < rows_valid;
       float* yrow = y + (size_t)row * kLsBN;
-#pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
+#pragma unroll
+      for (int cb = 0; cb < 4 * NT; ++cb) {
         float v[32];
         ls_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kLsBN + cb * 32), v);
         if (row_ok) {
@@ -282,7 +306,7 @@ linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       if (lane == 0) ls_mbar_arrive(ls_smem_u32(&bars.tempty[buf]));
     }
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
+    for (int cb = 0; cb < 4 * NT; ++cb) {
       s_part[q][0][cb * 32 + lane] = (float)acc_s[cb];
       s_part[q][1][cb * 32 + lane] = (float)acc_q[cb];
     }
@@ -295,11 +319,10 @@ linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   if (warp == 2)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kLsTmemCols)
                  : "memory");
-  {
-    const int t = threadIdx.x;                    // 256 threads = 2 x 128 values
-    const int which = t >> 7, c = t & 127;
+  for (int t = threadIdx.x; t < 2 * kLsBN; t += kLsThreads) {
+    const int which = t / kLsBN, c = t - which * kLsBN;
     const float tot = ((s_part[0][which][c] + s_part[1][which][c]) + s_part[2][which][c]) + s_part[3][which][c];
-    part[(size_t)blockIdx.x * 2 * kLsBN + which * kLsBN + c] = tot;
+    part[(size_t)blockIdx.x * 2 * kLsBN + t] = tot;
   }
   if (!ticketed_combine(part, part2, 2 * kLsBN, gridDim.x, grp, ngroups, tickets, s_fin)) return;
   // statistics of (y - bias): shift = bias
@@ -358,14 +381,37 @@ static LsGeom ls_geom(int64_t M) {
 using namespace pgh;
 
 extern "C" int pgh_linear_stats_supported(int64_t M, int64_t K, int64_t N) {
-  return M > 0 && N == kLsBN && K >= kLsBK && K % kLsBK == 0 && K <= 4096;
+  return M > 0 && (N == 128 || N == 256 || N == 384) && K >= kLsBK && K % kLsBK == 0 && K <= 4096;
 }
 
 extern "C" size_t pgh_linear_stats_ws_bytes(int64_t M) {
   if (M <= 0) return 256;
   const LsGeom g = ls_geom(M);
-  return ((size_t)g.grid * 2 * kLsBN * sizeof(float) + 255) / 256 * 256 +
-         (size_t)g.ngroups * 2 * kLsBN * sizeof(float) + 256;
+  constexpr int kMaxN = 384;
+  return ((size_t)g.grid * 2 * kMaxN * sizeof(float) + 255) / 256 * 256 +
+         (size_t)g.ngroups * 2 * kMaxN * sizeof(float) + 256;
+}
+
+template <int NT>
+static int ls_launch(const CUtensorMap& map_x, const CUtensorMap& map_w, const float* bias, int64_t M,
+                     int64_t K, const int32_t* rows_dev, float* y, const LsGeom& g, void* ws,
+                     int32_t* tickets, float eps, float momentum, float* mean, float* rstd,
+                     float* running_mean, float* running_var, float* local_out, int64_t* nbt,
+                     cudaStream_t s) {
+  using Cfg = LsCfg<NT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PGH_CUDA(cudaFuncSetAttribute(linear_stats_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  float* part = reinterpret_cast<float*>(ws);
+  float* part2 = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) +
+                                          ((size_t)g.grid * 2 * Cfg::N * sizeof(float) + 255) / 256 * 256);
+  linear_stats_kernel<NT><<<g.grid, kLsThreads, Cfg::kSmemBytes, s>>>(
+      map_x, map_w, bias, M, (int)K, rows_dev, y, part, part2, g.grp, g.ngroups, tickets, eps, momentum,
+      mean, rstd, running_mean, running_var, local_out, reinterpret_cast<long long*>(nbt));
+  return check_launch("linear_stats");
 }
 
 extern "C" int pgh_linear_stats_f32(const float* x, int64_t M, int64_t K, const float* w, int64_t N,
@@ -375,7 +421,7 @@ extern "C" int pgh_linear_stats_f32(const float* x, int64_t M, int64_t K, const 
                                     void* ws, size_t ws_bytes, int32_t* tickets, void* stream) {
   if (!x || !w || !y || !ws || !tickets || (!local_out && (!mean || !rstd)))
     return arg_error("linear_stats: null pointer");
-  if (!pgh_linear_stats_supported(M, K, N)) return arg_error("linear_stats: need N == 128, K % 32 == 0");
+  if (!pgh_linear_stats_supported(M, K, N)) return arg_error("linear_stats: need N in {128, 256, 384}, K % 32 == 0");
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15)
     return arg_error("linear_stats: x and w must be 16-byte aligned");
   if (reinterpret_cast<uintptr_t>(y) & 31) return arg_error("linear_stats: y must be 32-byte aligned");
@@ -383,19 +429,12 @@ extern "C" int pgh_linear_stats_f32(const float* x, int64_t M, int64_t K, const 
   CUtensorMap map_x, map_w;
   if (!make_map(&map_x, x, M, K) || !make_map(&map_w, w, N, K))
     return arg_error("linear_stats: cuTensorMapEncodeTiled failed");
-  static bool attr_set = false;
-  if (!attr_set) {
-    PGH_CUDA(cudaFuncSetAttribute(linear_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kLsSmemBytes));
-    attr_set = true;
-  }
   const LsGeom g = ls_geom(M);
-  float* part = reinterpret_cast<float*>(ws);
-  float* part2 = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) +
-                                          ((size_t)g.grid * 2 * kLsBN * sizeof(float) + 255) / 256 * 256);
-  linear_stats_kernel<<<g.grid, kLsThreads, kLsSmemBytes, as_stream(stream)>>>(
-      map_x, map_w, bias, M, (int)K, rows_dev, y, part, part2, g.grp, g.ngroups, tickets, eps, momentum,
-      mean, rstd, running_mean, running_var, local_out,
-      reinterpret_cast<long long*>(num_batches_tracked));
-  return check_launch("linear_stats");
+  cudaStream_t s = as_stream(stream);
+#define PGH_LS(NT_) ls_launch<NT_>(map_x, map_w, bias, M, K, rows_dev, y, g, ws, tickets, eps, momentum, \
+                                   mean, rstd, running_mean, running_var, local_out, num_batches_tracked, s)
+  if (N == 128) return PGH_LS(1);
+  if (N == 256) return PGH_LS(2);
+  return PGH_LS(3);
+#undef PGH_LS
 }

@@ -31,16 +31,18 @@ def _tf32():
     torch.backends.cuda.matmul.allow_tf32 = old
 
 
-@pytest.mark.parametrize("M,K", [(1, 32), (127, 128), (128, 128), (129, 384), (4097, 128),
-                                 (70001, 384), (300000, 128), (20000, 64)])
+@pytest.mark.parametrize("M,K,N", [(1, 32, 128), (127, 128, 128), (128, 128, 128), (129, 384, 128),
+                                   (4097, 128, 128), (70001, 384, 128), (300000, 128, 128),
+                                   (20000, 64, 128), (70001, 384, 384), (4097, 384, 384),
+                                   (33333, 256, 256), (257, 128, 384), (9000, 256, 128)])
 @pytest.mark.parametrize("has_bias", [True, False])
-def test_linear_stats_matches_torch_and_its_own_output(M, K, has_bias):
+def test_linear_stats_matches_torch_and_its_own_output(M, K, N, has_bias):
     ops = torch.ops.pygho_b200
-    g = torch.Generator(device=DEV).manual_seed(M + K)
+    g = torch.Generator(device=DEV).manual_seed(M + K + N)
     x = torch.randn(M, K, device=DEV, generator=g) * 1.5 + 0.3
-    w = torch.randn(128, K, device=DEV, generator=g) / K ** 0.5
-    b = torch.randn(128, device=DEV, generator=g) if has_bias else None
-    rm, rv = torch.zeros(128, device=DEV), torch.ones(128, device=DEV)
+    w = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g) if has_bias else None
+    rm, rv = torch.zeros(N, device=DEV), torch.ones(N, device=DEV)
     nbt = torch.zeros((), dtype=torch.int64, device=DEV)
     y, mean, rstd = ops.linear_stats(x, w, b, 1e-5, 0.1, rm, rv, None, nbt, False)
     want = torch.nn.functional.linear(x.double(), w.double(), None if b is None else b.double())
@@ -90,7 +92,7 @@ def test_linear_stats_pad_rows_and_syncbn_triples():
     assert abs(float(inv_n) * M - 1.0) < 1e-6
 
 
-@pytest.mark.parametrize("rows,cin", [(6000, 128), (33333, 384)])
+@pytest.mark.parametrize("rows,cin", [(6000, 128), (33333, 384), (20000, 256)])
 def test_mlp_block_on_fused_gemm_equals_cublas_path(rows, cin):
     """MLP (Linear -> BN -> SiLU) x 2 with the fused GEMM + statistics against the same block on
     cuBLAS TF32 + separate statistics pass: outputs and all gradients within TF32 tolerance."""
@@ -98,7 +100,7 @@ def test_mlp_block_on_fused_gemm_equals_cublas_path(rows, cin):
     from pygho_b200.honn.utils import MLP
     torch.manual_seed(rows)
     mlp = MLP(cin, 128, 2, True, norm="bn", act="silu", normparam=0.3).to(DEV)
-    # hidden blocks are cin -> cin; only the 128-wide outputs run on the fused GEMM
+    # hidden block cin -> cin and output block cin -> 128: both on the fused GEMM
     ref = copy.deepcopy(mlp)
     x = torch.randn(rows, cin, device=DEV)
     w = torch.randn(rows, 128, device=DEV)
