@@ -444,7 +444,13 @@ def linear_stats_ok(x: Tensor, weight: Tensor) -> bool:
     """The TMA / tcgen05 GEMM with the BatchNorm statistics in its epilogue (csrc/linear_stats.cu)
     computes in TF32: it replaces cuBLAS only where cuBLAS would use TF32 too (the reference sets
     float32_matmul_precision('high'), example/zinc.py:30) and for the shapes it supports."""
-    # below a few thousand rows the pipeline set-up and the ticketed tail outweigh the saved pass
+    # below a few thousand rows the pipeline set-up and the ticketed tail outweigh the saved pass.
+    # N = 256 / 384 are correct but re-read W (N x K) from L2 once per 128-row tile: at ~54 GB/s
+    # of L2->SM traffic per SM that costs more than the statistics pass saves (384 -> 384 at
+    # 230 k rows: 308 us against cuBLAS 140 us + 68 us, profiles/r2_linear_stats.md) -- they
+    # stay opt-in (PYGHO_B200_FUSED_GEMM_WIDE=1) until the tile is shared by a CTA pair
+    if weight.shape[0] != 128 and not _FUSED_GEMM_WIDE:
+        return False
     return (torch.backends.cuda.matmul.allow_tf32 and x.dtype == torch.float32 and x.ndim == 2
             and x.is_cuda and weight.dtype == torch.float32 and x.shape[0] >= _FUSED_GEMM_MIN_ROWS
             and bool(_lib.load().pgh_linear_stats_supported(x.shape[0], x.shape[1], weight.shape[0])))
@@ -1005,6 +1011,7 @@ def _tall_skinny_tn(a: Tensor, b: Tensor, chunks: int = 64, acc: Optional[Tensor
 _DIRECT_GRADS = True
 _FUSED_GEMM = os.environ.get("PYGHO_B200_FUSED_GEMM", "1") != "0"
 _FUSED_GEMM_MIN_ROWS = 4096
+_FUSED_GEMM_WIDE = os.environ.get("PYGHO_B200_FUSED_GEMM_WIDE", "0") == "1"
 
 
 def set_fused_linear_stats(flag: bool) -> None:
