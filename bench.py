@@ -146,6 +146,8 @@ class ClockSampler:
         self.index, self.lines, self.proc = index, [], None
 
     def __enter__(self):
+        if self.index < 0:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -601,7 +603,9 @@ def run_b200(args):
         run_step = lambda i: train_step(dds[i % len(dds)])  # noqa: E731
     for i in range(warm):
         run_step(i)
-    with ClockSampler(local) as clocks:
+    # clocks / throttle reasons are sampled by rank 0 only (its own GPU): eight nvidia-smi pollers
+    # contend for the driver lock and slow the graph launches of every rank
+    with ClockSampler(local if rank == 0 else -1) as clocks:
         ms_total, launches = timed(run_step, args.steps)
     if graphs is not None:                                # replays do not pass through Python
         launches = sum(graphs[i % len(graphs)].launches for i in range(args.steps))

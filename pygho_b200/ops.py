@@ -881,6 +881,48 @@ class MaskedFill(torch.autograd.Function):
         return _ops.masked_fill_rows(g.contiguous(), mask, 0.0), None, None
 
 
+_FORK = os.environ.get("PYGHO_B200_FORK", "1") != "0"
+_FORK_STREAMS = {}
+
+
+class _Fork:
+    """Run a few independent kernel launches on a second stream (fork / join with stream waits;
+    inside a CUDA-graph capture this becomes a parallel branch of the graph).  At the 8-GPU
+    strong-scaling point (128 graphs per GPU) single kernels no longer fill the 148 SMs, and the
+    tails of independent launches -- the two halves of an SSWL aggregation, dX and dA, the dx and
+    dW GEMMs of a Linear -- overlap instead of queueing.  Rules: every tensor the branch WRITES
+    that is used afterwards is allocated before the fork (on the main stream); temporaries
+    allocated inside the branch are only ever touched by the branch."""
+
+    def __init__(self, device):
+        self.on = _FORK and device.type == "cuda"
+        if self.on:
+            self.main = torch.cuda.current_stream(device)
+            side = _FORK_STREAMS.get(device)
+            if side is None:
+                side = torch.cuda.Stream(device)
+                _FORK_STREAMS[device] = side
+            self.side = side
+            if self.side == self.main:
+                self.on = False
+
+    def __enter__(self):
+        if self.on:
+            self.side.wait_stream(self.main)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.on:
+            self.main.wait_stream(self.side)
+
+
 class SswlAggregate(torch.autograd.Function):
     """``cat([X, X (x) A, A (x) X], -1)`` of one SSWL layer (reference Conv.py:97-103) built in
     ONE buffer: the two spspmm launches write their column slice directly, and the three
@@ -897,6 +939,8 @@ class SswlAggregate(torch.autograd.Function):
         n, d = Xv.shape
         cat = torch.empty((n, 3 * d), dtype=torch.float32, device=Xv.device)
         g1, g2 = plan_xa.group("a"), plan_ax.group("a")
+        with _Fork(Xv.device) as fork:           # A (x) X writes its own column slice: independent
+            _ops.seg_gmr_out(Av, g2.first, None, Xv, g2.second, g2.rowptr, n, aggr, cat[:, 2 * d:], False)
         if n and Av.shape[0] and fused_epilogue_ok(d, Xv, Av, cat):
             # the X (x) A launch also copies X into the first third of the buffer
             _ops.seg_gmr_fused(Xv, g1.first, None, Av, g1.second, g1.rowptr, n, aggr, None, Xv,
@@ -904,7 +948,7 @@ class SswlAggregate(torch.autograd.Function):
         else:
             cat[:, :d].copy_(Xv)
             _ops.seg_gmr_out(Xv, g1.first, None, Av, g1.second, g1.rowptr, n, aggr, cat[:, d:2 * d], False)
-        _ops.seg_gmr_out(Av, g2.first, None, Xv, g2.second, g2.rowptr, n, aggr, cat[:, 2 * d:], False)
+        fork.join()
         ctx.save_for_backward(Xv, Av)
         ctx.cfg = (plan_xa, plan_ax, aggr)
         if tap_residual:
@@ -922,6 +966,14 @@ class SswlAggregate(torch.autograd.Function):
         s1 = plan_xa.inv_count() if aggr == 1 else None
         s2 = plan_ax.inv_count() if aggr == 1 else None
         gX = gA = None
+        fork = None
+        if ctx.needs_input_grad[1]:      # dA on the forked stream, dX on this one
+            gA = torch.empty((nA, d), dtype=torch.float32, device=g.device)
+            with _Fork(g.device) as fork:
+                dd = plan_xa.group("d")      # A is operand B of X (x) A
+                _ops.seg_gmr_out(g1, dd.first, s1, Xv, dd.second, dd.rowptr, nA, 0, gA, False)
+                c = plan_ax.group("c")       # A is operand A of A (x) X
+                _ops.seg_gmr_out(g2, c.first, s2, Xv, c.second, c.rowptr, nA, 0, gA, True)
         if ctx.needs_input_grad[0]:
             c = plan_xa.group("c")       # X is operand A of X (x) A
             if n and nA and fused_epilogue_ok(d, g, Av, g_res):
@@ -936,11 +988,8 @@ class SswlAggregate(torch.autograd.Function):
                 _ops.seg_gmr_out(g1, c.first, s1, Av, c.second, c.rowptr, n, 0, gX, True)
             dd = plan_ax.group("d")      # X is operand B of A (x) X
             _ops.seg_gmr_out(g2, dd.first, s2, Av, dd.second, dd.rowptr, n, 0, gX, True)
-        if ctx.needs_input_grad[1]:
-            dd = plan_xa.group("d")      # A is operand B of X (x) A
-            gA = _ops.seg_gmr(g1, dd.first, s1, Xv, dd.second, dd.rowptr, nA, 0)
-            c = plan_ax.group("c")       # A is operand A of A (x) X
-            _ops.seg_gmr_out(g2, c.first, s2, Xv, c.second, c.rowptr, nA, 0, gA, True)
+        if fork is not None:
+            fork.join()
         return gX, gA, None, None, None, None
 
 
@@ -1105,8 +1154,15 @@ class LinearBNAct(torch.autograd.Function):
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
         dy, dbias = _ops.bn_act_bwd_apply(dz, y, mean, rstd, gamma, beta, sums, inv_n, ctx.act,
                                           rows_dev, need_bias, acc_b)
-        dx = dy.mm(weight) if need[0] else None
-        dw = _tall_skinny_tn(dy, x, acc=acc_w) if need[1] else None
+        if need[0] and need[1] and acc_w is not None:
+            # dW (accumulated into the gradient buffer) on the forked stream, dx on this one
+            with _Fork(dy.device) as fork:
+                _tall_skinny_tn(dy, x, acc=acc_w)
+            dx, dw = dy.mm(weight), None
+            fork.join()
+        else:
+            dx = dy.mm(weight) if need[0] else None
+            dw = _tall_skinny_tn(dy, x, acc=acc_w) if need[1] else None
         return (dx, dw, dbias if (need_bias and acc_b is None) else None,
                 dgamma if (gamma is not None and need[3] and acc_g is None) else None,
                 dbeta if (beta is not None and need[4] and acc_be is None) else None,
