@@ -74,6 +74,21 @@ int pgh_seg_gmr_ld_f32(const float* a_val, int64_t lda, const int32_t* c, const 
                        int64_t n_rows, int64_t n_entries, int64_t dense, int aggr, int accumulate,
                        float* out, int64_t ldo, void* stream);
 
+/* Shared-memory staging of a tile's first-operand row range (dense == 128, two operands, sum or
+ * mean; BASELINE north_star "staging of each row's key range").  pgh_tile_ranges finds, for every
+ * tile of `rows_per_tile` consecutive output rows, the range [lo, lo + cnt) of first-operand rows
+ * its plan entries reference (once per batch, cached with the plan); pgh_seg_gmr_staged_f32 copies
+ * that range to shared memory once per tile when cnt <= max_stage_rows (<= 256) and reduces the
+ * tile's rows from it -- same arguments, reduction order and results as pgh_seg_gmr_ld_f32. */
+int pgh_tile_ranges(const int32_t* rowptr, const int32_t* first, int64_t n_rows,
+                    int64_t rows_per_tile, int32_t* tile_lo, int32_t* tile_cnt, void* stream);
+int pgh_seg_gmr_staged_f32(const float* a_val, int64_t lda, const int32_t* c, const float* a_scale,
+                           const float* b_val, int64_t ldb, const int32_t* d,
+                           const int32_t* rowptr, int64_t n_rows, int64_t dense, int aggr,
+                           int accumulate, const int32_t* tile_lo, const int32_t* tile_cnt,
+                           int64_t rows_per_tile, int64_t max_stage_rows, float* out, int64_t ldo,
+                           void* stream);
+
 /* pgh_seg_gmr_ld_f32 with a fused row epilogue (dense % 128 == 0, 16-byte aligned rows, sum or
  * mean):  out[r,:] = add_src[r,:] + reduction(r) (+ add_src2[r,:])   and, if copy_src != NULL,
  * copy_dst[r,:] = copy_src[r,:]; add_src / add_src2 may be NULL (add_src2 needs add_src).  One

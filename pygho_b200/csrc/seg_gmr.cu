@@ -612,6 +612,125 @@ seg_gmr_ring_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Staged variant (dense == 128, two operands, sum / mean): "shared-memory staging of each row's
+// key range" (BASELINE.json north_star).  For plans with many entries per output row -- the
+// 2-FWL key X___X___1___X___0, the sr25-shaped keys with ~12 entries per row, the I2 key -- the
+// lean kernel is bound by L1/L2 gather traffic: every operand row is fetched ~8-12 times.  Because
+// the tuple arrays are sorted by (root, node), the FIRST-operand rows that a tile of R consecutive
+// output rows touches lie in one short contiguous row range [lo, lo + cnt) (the tuples of the
+// roots the tile covers); that range is found once per batch (tile_range_kernel) and cached with
+// the plan.  A CTA copies the range into shared memory with coalesced 128-bit loads (each
+// first-operand row leaves L2 once per tile instead of once per entry) and its four warps then
+// reduce the tile's rows: first operand from shared memory, second operand gathered as before,
+// 4 entries = 4 independent 128-bit global loads in flight per lane.  Tiles whose range does not
+// fit (cnt > smax: e.g. groupings by the second operand, whose rows come from all over the batch)
+// read the first operand from global memory like the lean kernel.  Same sequential reduction
+// order per row as every other variant: deterministic, bit-identical results.
+constexpr int kStageThreads = 128;
+template <int AGGR, bool HAS_SCALE>
+__global__ void __launch_bounds__(kStageThreads)
+seg_gmr_staged_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
+                      const float* __restrict__ a_scale, const float* __restrict__ b_val,
+                      const int* __restrict__ d, const int* __restrict__ rowptr, long long n_rows,
+                      int lda, int ldb, int ldo, int R, const int* __restrict__ tile_lo,
+                      const int* __restrict__ tile_cnt, int smax, int accum,
+                      float* __restrict__ out) {
+  extern __shared__ float4 stage[];                       // smax rows x 32 float4
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tile = blockIdx.x;
+  const int lo = __ldg(tile_lo + tile), cnt = __ldg(tile_cnt + tile);
+  const bool staged = cnt > 0 && cnt <= smax;
+  if (staged) {
+    const float* src = a_val + (size_t)lo * lda;
+    for (int idx = threadIdx.x; idx < cnt * 32; idx += kStageThreads)
+      stage[idx] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(idx >> 5) * lda) + (idx & 31));
+    __syncthreads();
+  }
+  const long long r_end = min(n_rows, (tile + 1) * (long long)R);
+  const float* __restrict__ b_col = b_val + lane * 4;
+  const float* __restrict__ a_col = a_val + lane * 4;
+  for (long long r = tile * R + warp; r < r_end; r += kStageThreads / 32) {
+    const int e0 = __ldg(rowptr + r), e1 = __ldg(rowptr + r + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = e0; base < e1; base += 32) {
+      const int t = base + lane;
+      int ci = 0, di = 0;
+      float sc = 1.f;
+      if (t < e1) {
+        ci = c ? __ldg(c + t) : t;
+        di = d ? __ldg(d + t) : t;
+        if (HAS_SCALE) sc = __ldg(a_scale + ci);
+      }
+      const int chunk = min(32, e1 - base);
+      for (int k = 0; k < chunk; k += 4) {
+        float4 av[4], bv[4];
+        float ss[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int kk = min(k + u, chunk - 1);            // clamped: loads stay unconditional
+          const int cc = __shfl_sync(kFull, ci, kk);
+          const int dd = __shfl_sync(kFull, di, kk);
+          bv[u] = __ldg(reinterpret_cast<const float4*>(b_col + (size_t)dd * ldb));
+          av[u] = staged ? stage[(cc - lo) * 32 + lane]
+                         : __ldg(reinterpret_cast<const float4*>(a_col + (size_t)cc * lda));
+          if (HAS_SCALE) ss[u] = __shfl_sync(kFull, sc, kk);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k + u < chunk) {
+            float4 m = av[u];
+            if (HAS_SCALE)
+              m = make_float4(__fmul_rn(m.x, ss[u]), __fmul_rn(m.y, ss[u]), __fmul_rn(m.z, ss[u]),
+                              __fmul_rn(m.w, ss[u]));
+            acc = make_float4(__fmaf_rn(m.x, bv[u].x, acc.x), __fmaf_rn(m.y, bv[u].y, acc.y),
+                              __fmaf_rn(m.z, bv[u].z, acc.z), __fmaf_rn(m.w, bv[u].w, acc.w));
+          }
+        }
+      }
+    }
+    if (AGGR == PGH_MEAN && e1 > e0) {
+      const float n_ = (float)(e1 - e0);
+      acc = make_float4(acc.x / n_, acc.y / n_, acc.z / n_, acc.w / n_);
+    }
+    float4* o = reinterpret_cast<float4*>(out + (size_t)r * ldo) + lane;
+    if (accum) {
+      const float4 p = *o;
+      acc = make_float4(__fadd_rn(p.x, acc.x), __fadd_rn(p.y, acc.y), __fadd_rn(p.z, acc.z),
+                        __fadd_rn(p.w, acc.w));
+    }
+    *o = acc;
+  }
+}
+
+// [lo, lo + cnt) = range of first-operand rows referenced by the entries of output rows
+// [tile * R, (tile + 1) * R); one warp per tile.  first == NULL: identity index.
+__global__ void tile_range_kernel(const int* __restrict__ rowptr, const int* __restrict__ first,
+                                  long long n_rows, int R, long long n_tiles,
+                                  int* __restrict__ lo, int* __restrict__ cnt) {
+  const long long tile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  const int e0 = __ldg(rowptr + tile * R);
+  const int e1 = __ldg(rowptr + min(n_rows, (tile + 1) * (long long)R));
+  int mn = 0x7fffffff, mx = -1;
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const int v = first ? __ldg(first + e) : e;
+    mn = min(mn, v);
+    mx = max(mx, v);
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  }
+  if (lane == 0) {
+    lo[tile] = e1 > e0 ? mn : 0;
+    cnt[tile] = e1 > e0 ? mx - mn + 1 : 0;
+  }
+}
+
 // gscaled[r,:] = grad[r,:] / (#entries of seg(r) whose product equals out[r,:])
 template <int VEC, bool HAS_B>
 __global__ void __launch_bounds__(kThreads)
@@ -1058,6 +1177,57 @@ extern "C" int pgh_seg_gmr_fused_f32(const float* a_val, int64_t lda, const int3
                                  n_entries, (int)dense, la, lb, lo, 0, out, &x);
   if (rc) return rc;
   return check_launch("seg_gmr_fused");
+}
+
+extern "C" int pgh_tile_ranges(const int32_t* rowptr, const int32_t* first, int64_t n_rows,
+                               int64_t rows_per_tile, int32_t* tile_lo, int32_t* tile_cnt,
+                               void* stream) {
+  if (!rowptr || !tile_lo || !tile_cnt || n_rows < 0 || rows_per_tile < 1 || rows_per_tile > (1 << 20))
+    return arg_error("tile_ranges: arguments");
+  if (n_rows == 0) return 0;
+  const long long n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
+  tile_range_kernel<<<blocks_for(n_tiles * 32, 256), 256, 0, as_stream(stream)>>>(
+      rowptr, first, n_rows, (int)rows_per_tile, n_tiles, tile_lo, tile_cnt);
+  return check_launch("tile_ranges");
+}
+
+extern "C" int pgh_seg_gmr_staged_f32(const float* a_val, int64_t lda, const int32_t* c,
+                                      const float* a_scale, const float* b_val, int64_t ldb,
+                                      const int32_t* d, const int32_t* rowptr, int64_t n_rows,
+                                      int64_t dense, int aggr, int accumulate,
+                                      const int32_t* tile_lo, const int32_t* tile_cnt,
+                                      int64_t rows_per_tile, int64_t max_stage_rows, float* out,
+                                      int64_t ldo, void* stream) {
+  if (!a_val || !b_val || !rowptr || !tile_lo || !tile_cnt || !out)
+    return arg_error("seg_gmr_staged: null pointer (two operands and a CSR grouping are required)");
+  if (dense != 128) return arg_error("seg_gmr_staged: dense must be 128");
+  if (aggr < 0 || aggr > 1) return arg_error("seg_gmr_staged: sum or mean only");
+  if (rows_per_tile < 1 || max_stage_rows < 1 || max_stage_rows > 256)
+    return arg_error("seg_gmr_staged: tile geometry");
+  const int64_t lim = 0x7fffffff;
+  if (lda < dense || ldb < dense || ldo < dense || lda > lim || ldb > lim || ldo > lim || lda % 4 ||
+      ldb % 4 || ldo % 4 || !aligned16(a_val) || !aligned16(b_val) || !aligned16(out))
+    return arg_error("seg_gmr_staged: rows must be 16-byte aligned");
+  if (n_rows <= 0) return 0;
+  const long long n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
+  const size_t smem = (size_t)max_stage_rows * 512;
+  cudaStream_t s = as_stream(stream);
+#define PGH_STAGED(AG, SC)                                                                          \
+  do {                                                                                              \
+    static size_t set_ = 0;                                                                         \
+    if (smem > set_) {                                                                              \
+      PGH_CUDA(cudaFuncSetAttribute(seg_gmr_staged_kernel<AG, SC>,                                  \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+      set_ = smem;                                                                                  \
+    }                                                                                               \
+    seg_gmr_staged_kernel<AG, SC><<<(unsigned)n_tiles, kStageThreads, smem, s>>>(                   \
+        a_val, c, a_scale, b_val, d, rowptr, n_rows, (int)lda, (int)ldb, (int)ldo,                  \
+        (int)rows_per_tile, tile_lo, tile_cnt, (int)max_stage_rows, accumulate, out);               \
+  } while (0)
+  if (aggr == PGH_SUM) { if (a_scale) PGH_STAGED(PGH_SUM, true); else PGH_STAGED(PGH_SUM, false); }
+  else { if (a_scale) PGH_STAGED(PGH_MEAN, true); else PGH_STAGED(PGH_MEAN, false); }
+#undef PGH_STAGED
+  return check_launch("seg_gmr_staged");
 }
 
 extern "C" int pgh_seg_gmr_f32(const float* a_val, const int32_t* c, const float* a_scale,

@@ -165,6 +165,36 @@ def _seg_gmr_fused_fake(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, add_s
     return None
 
 
+_LIB.define("seg_gmr_staged(Tensor a_val, Tensor? c, Tensor? a_scale, Tensor b_val, Tensor? d, "
+            "Tensor rowptr, int n_rows, int aggr, Tensor tile_lo, Tensor tile_cnt, int rows_per_tile, "
+            "int max_stage_rows) -> Tensor")
+
+
+def _seg_gmr_staged_cuda(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, tile_lo, tile_cnt,
+                         rows_per_tile, max_stage_rows):
+    """seg_gmr with the first operand's row range of every tile staged in shared memory
+    (dense == 128, two operands, sum / mean); results equal ``seg_gmr`` bit for bit."""
+    a_val, b_val, a_scale = _rows2d(a_val), _rows2d(b_val), _f32c(a_scale)
+    c, d, rowptr = _i32c(c), _i32c(d), _i32c(rowptr)
+    out = torch.empty((n_rows, a_val.shape[1]), dtype=torch.float32, device=a_val.device)
+    if n_rows:
+        call("pgh_seg_gmr_staged_f32", ptr(a_val), a_val.stride(0), ptr(c), ptr(a_scale), ptr(b_val),
+             b_val.stride(0), ptr(d), ptr(rowptr), n_rows, a_val.shape[1], aggr, 0, ptr(_i32c(tile_lo)),
+             ptr(_i32c(tile_cnt)), rows_per_tile, max_stage_rows, ptr(out), out.stride(0),
+             stream_ptr(a_val.device))
+        _lib.count_launch()
+    return out
+
+
+_LIB.impl("seg_gmr_staged", _seg_gmr_staged_cuda, "CUDA")
+
+
+@torch.library.register_fake("pygho_b200::seg_gmr_staged")
+def _seg_gmr_staged_fake(a_val, c, a_scale, b_val, d, rowptr, n_rows, aggr, tile_lo, tile_cnt,
+                         rows_per_tile, max_stage_rows):
+    return a_val.new_empty((n_rows, a_val.shape[1]))
+
+
 _LIB.define("seg_tie_scale(Tensor a_val, Tensor? c, Tensor? b_val, Tensor? d, Tensor? rowptr, "
             "Tensor out, Tensor grad) -> Tensor")
 
@@ -674,6 +704,26 @@ _ops = torch.ops.pygho_b200
 
 
 # ------------------------------------------------------------------------- autograd
+_STAGED = os.environ.get("PYGHO_B200_STAGED", "1") != "0"
+
+
+def _gmr(plan, which: str, first_val: Tensor, scale: Optional[Tensor], second_val: Optional[Tensor],
+         n_rows: int, aggr: int) -> Tensor:
+    """One segmented reduce over grouping ``which`` of ``plan``: the staged kernel when the plan
+    has enough reuse of the first operand's rows (plans.TriplePlan.tiles), else the streaming
+    kernels."""
+    g = plan.group(which)
+    if (_STAGED and second_val is not None and aggr <= 1 and first_val.ndim == 2
+            and first_val.shape[1] == 128 and second_val.shape[0] > 0 and first_val.shape[0] > 0):
+        t = plan.tiles(which)
+        if t is not None:
+            return _ops.seg_gmr_staged(first_val, g.first, scale, second_val, g.second, g.rowptr,
+                                       n_rows, aggr, t[0], t[1], plan.STAGE_ROWS_PER_TILE,
+                                       plan.STAGE_MAX_ROWS)
+    return _ops.seg_gmr(first_val, g.first, scale, second_val,
+                        g.second if second_val is not None else None, g.rowptr, n_rows, aggr)
+
+
 class SegGmr(torch.autograd.Function):
     """out[r] = aggr_{t in seg(r)} A[c_t] * B[d_t] with the three CSR groupings of a
     :class:`pygho_b200.plans.TriplePlan`.  Gradients flow to the value operands only
@@ -682,9 +732,7 @@ class SegGmr(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a_val: Tensor, b_val: Optional[Tensor], plan, aggr: int):
-        ga = plan.group("a")
-        out = _ops.seg_gmr(a_val, ga.first, None, b_val, ga.second if b_val is not None else None,
-                           ga.rowptr, plan.n_out, aggr)
+        out = _gmr(plan, "a", a_val, None, b_val, plan.n_out, aggr)
         ctx.plan, ctx.aggr = plan, aggr
         ctx.has_b = b_val is not None
         if aggr >= 2:
@@ -716,12 +764,9 @@ class SegGmr(torch.autograd.Function):
         a_val, b_val = ctx.saved_tensors
         scale = plan.inv_count() if aggr == 1 else None
         if need_a:
-            gc = plan.group("c")
-            g_a = _ops.seg_gmr(g, gc.first, scale, b_val, gc.second if ctx.has_b else None,
-                               gc.rowptr, plan.n_a, 0)
+            g_a = _gmr(plan, "c", g, scale, b_val if ctx.has_b else None, plan.n_a, 0)
         if need_b:
-            gd = plan.group("d")
-            g_b = _ops.seg_gmr(g, gd.first, scale, a_val, gd.second, gd.rowptr, plan.n_b, 0)
+            g_b = _gmr(plan, "d", g, scale, a_val, plan.n_b, 0)
         return g_a, g_b, None, None
 
 
