@@ -704,7 +704,12 @@ _ops = torch.ops.pygho_b200
 
 
 # ------------------------------------------------------------------------- autograd
-_STAGED = os.environ.get("PYGHO_B200_STAGED", "1") != "0"
+# The staged kernel is correct (bit-identical) but measured SLOWER than the streaming kernels on a
+# B200 -- 248 vs 127 us on the ZINC 2-FWL key, 64 vs 34 us on sr25 X.A, 529 vs 318 us on the I2 key
+# (profiles/r2_staged_kernel.md): L1 already serves half of the repeated first-operand rows, and
+# the staging phase + 48 KB of shared memory per CTA cost more latency hiding than the saved L2
+# requests return.  Opt-in (PYGHO_B200_STAGED=1) until it overlaps staging with the reduction.
+_STAGED = os.environ.get("PYGHO_B200_STAGED", "0") == "1"
 
 
 def _gmr(plan, which: str, first_val: Tensor, scale: Optional[Tensor], second_val: Optional[Tensor],

@@ -794,6 +794,8 @@ def test_staged_kernel_is_bit_identical_to_streaming_kernel(B, shape, tuples, ke
     av, bv = torch.randn((n1, 128), generator=gen), torch.randn((n2, 128), generator=gen)
     w = torch.randn((n_out, 128), generator=gen).to(DEV)
 
+    default = OPS._STAGED
+
     def run(staged):
         OPS._STAGED = staged
         try:
@@ -804,7 +806,7 @@ def test_staged_kernel_is_bit_identical_to_streaming_kernel(B, shape, tuples, ke
             used = {k: v is not None for k, v in plan._tiles.items()}
             return out.detach(), a.grad, b.grad, used
         finally:
-            OPS._STAGED = True
+            OPS._STAGED = default
 
     o1_, ga1, gb1, used = run(True)
     o0_, ga0, gb0, _ = run(False)
