@@ -128,7 +128,8 @@ def config_of(args, world, stats):
         "global_batch": glob, "per_gpu_batch": per_gpu, "n_gpus": world,
         "matmul": "tf32 on the GPU (reference: set_float32_matmul_precision('high')), fp32 on the CPU",
         "l2": "step working set >> L2 at 1024 graphs/GPU; distinct batches rotated",
-        "parallelism": f"dp{world}: graphs sharded {per_gpu}/GPU, flat-bucket NCCL all-reduce"
+        "parallelism": f"dp{world}: graphs sharded {per_gpu}/GPU (balanced by tuple count), "
+                       "flat-bucket NCCL all-reduce"
                        + (", SyncBN" if getattr(args, "syncbn", False) else ""),
     }
     cfg.update(stats)
@@ -137,7 +138,7 @@ def config_of(args, world, stats):
 
 # ------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms while the timed region runs."""
+    """nvidia-smi sampled every 50 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -151,7 +152,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200", "-i", str(self.index)],
+                 "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -194,13 +195,31 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------- host batches
-def host_batches(args, per_gpu, rank, count):
-    """`count` distinct host batches of `per_gpu` graphs for this rank.  Rank r's batch i is
-    graphs [r * per_gpu, (r + 1) * per_gpu) of global batch i (every graph of global batch i
-    comes from one seed stream, so the N-GPU job sees the same kind of data as the 1-GPU job)."""
-    from pygho_b200.hodata.synthetic import make_batch
-    return [make_batch(per_gpu, seed=1000 * rank + i, tuples=args.tuples, shape=args.shape)
-            for i in range(count)]
+def host_batches(args, per_gpu, rank, count, world=1):
+    """`count` distinct host batches of `per_gpu` graphs for this rank.
+
+    Strong scaling (world > 1): every rank generates the SAME global batch i (one seed stream, so
+    the N-GPU job trains on exactly the graphs the 1-GPU job would see) and takes its shard.  The
+    shard is balanced by cost: graphs sorted by tuple count and dealt to the ranks in snake order
+    (equal graph counts, near-equal tuple / triple counts), because the step ends with an
+    all-reduce and therefore runs at the pace of the largest shard (SURVEY.md 8e "greedy balance
+    by sum of T per graph")."""
+    from pygho_b200.hodata.synthetic import collate, make_batch, make_graphs
+    if world == 1 or args.scaling == "weak":
+        return [make_batch(per_gpu, seed=1000 * rank + i, tuples=args.tuples, shape=args.shape)
+                for i in range(count)]
+    out = []
+    for i in range(count):
+        graphs = make_graphs(per_gpu * world, seed=i, tuples=args.tuples, shape=args.shape)
+        order = sorted(range(len(graphs)), key=lambda g: (-graphs[g].tupleid.shape[1], g))
+        mine = []
+        for pos, g in enumerate(order):
+            rnd, k = divmod(pos, world)
+            owner = k if rnd % 2 == 0 else world - 1 - k
+            if owner == rank:
+                mine.append(g)
+        out.append(collate([graphs[g] for g in sorted(mine)]))
+    return out
 
 
 def batch_stats(args, hb, keys):
@@ -525,7 +544,7 @@ def run_b200(args):
     # capturable: the step counter lives on the device, so the optimizer can be graph-captured
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True, capturable=True)
 
-    hbs = host_batches(args, per_gpu, rank, args.num_batches)
+    hbs = host_batches(args, per_gpu, rank, args.num_batches, world)
     pinned = {}
     dds = []
     for hb in hbs:

@@ -41,6 +41,7 @@ from pygho.honn.TensorOp import OpPoolingSubg2D, OpPoolingSubg3D  # noqa: E402
 from pygho_b200.hodata.synthetic import make_batch  # noqa: E402
 
 T = torch.from_numpy
+torch.set_num_threads(1)      # bit-reproducible reference outputs whichever entry point is used
 
 
 def npy(x):

@@ -55,3 +55,30 @@ def test_reference_arm_other_workloads():
         assert r.returncode == 0, r.stderr[-2000:]
         d = json.loads(r.stdout.strip().splitlines()[-1])
         assert d["value"] > 0 and d["config"]["global_batch"] == 2 and wl.split("_")[0] in d["metric"]
+
+
+def test_strong_scaling_shards_cover_the_global_batch_and_are_balanced():
+    """bench.py --gpus N (strong scaling): the ranks' shards are a disjoint cover of the 1-GPU
+    job's global batch, equal in graph count and within 3 % in tuple count."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(b)
+        args = b.parse()
+    finally:
+        sys.argv = argv
+    world, per = 4, 12
+    shards = [b.host_batches(args, per, r, 1, world)[0] for r in range(world)]
+    whole = b.host_batches(args, per * world, 0, 1, 1)
+    from pygho_b200.hodata.synthetic import make_batch
+    ref = make_batch(per * world, seed=0)
+    assert sum(s.num_graphs for s in shards) == ref.num_graphs
+    assert sum(s.num_nodes for s in shards) == ref.num_nodes
+    assert sum(s.tupleid.shape[1] for s in shards) == ref.tupleid.shape[1]
+    assert sorted(np.concatenate([s.y for s in shards]).tolist()) == sorted(ref.y.tolist())
+    t = [s.tupleid.shape[1] for s in shards]
+    assert all(s.num_graphs == per for s in shards) and max(t) <= 1.03 * min(t), t
+    assert whole[0].num_graphs == per * world
