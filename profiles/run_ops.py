@@ -213,6 +213,29 @@ for C in (384, 128):
     report(f"BN(train)+SiLU bwd ({nX}x{C})", t, tr, 4 * C * nX * 5, "5 passes by design; ref = fwd+bwd minus fwd")
     del ys, dz, yr
 
+# ------------------------------------------ Linear + BatchNorm statistics in one pass (TMA + tcgen05)
+torch.backends.cuda.matmul.allow_tf32 = True
+for K in (384, 128):
+    xl = [torch.randn(nX, K, device=dev, generator=gen) for _ in range(3)]
+    wl = torch.randn(128, K, device=dev, generator=gen) / K ** 0.5
+    bl = torch.randn(128, device=dev, generator=gen)
+    ops = torch.ops.pygho_b200
+    t = timeit(lambda i: ops.linear_stats(xl[i % 3], wl, bl, 1e-5, 0.1, None, None, None, None, False))
+
+    def ref_lin(i):
+        y = torch.nn.functional.linear(xl[i % 3], wl, bl)
+        return y, y.mean(0), y.var(0, unbiased=False)
+
+    def cublas_plus_stats(i):
+        y = torch.nn.functional.linear(xl[i % 3], wl, bl)
+        return y, ops.bn_stats(y, 1e-5, 0.1, None, None, None, None)
+
+    tr = timeit(ref_lin, 5)
+    t2 = timeit(cublas_plus_stats)
+    report(f"Linear+BN stats ({nX}x{K}->128), one pass", t, tr, 4 * (nX * K + 128 * K + nX * 128),
+           f"TF32; cuBLAS TF32 + bn_stats kernel: {t2:.1f} us")
+    del xl
+
 # ------------------------------------------------------------------ masked path (cfg3)
 b, n = 128, 40
 rng = np.random.default_rng(0)
