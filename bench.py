@@ -88,6 +88,8 @@ def parse():
                     help="the reference arm trims its step count to finish within this time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stock-gpu", action="store_true")
+    ap.add_argument("--torch-adamw", action="store_true",
+                    help="torch.optim.AdamW(fused, capturable) instead of the one-launch FlatAdamW")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-static", action="store_true",
@@ -541,8 +543,14 @@ def run_b200(args):
         from pygho_b200.dist import enable_sync_batchnorm
         enable_sync_batchnorm(model)
     bucket = FlatGradBucket(model.parameters())
-    # capturable: the step counter lives on the device, so the optimizer can be graph-captured
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True, capturable=True)
+    # both keep the step counter on the device, so the optimizer can be graph-captured.
+    # FlatAdamW: the whole AdamW update (torch.optim.AdamW's rule, 1 / world of the gradient
+    # average folded in) as ONE launch over flat parameter / gradient / moment buffers
+    if args.torch_adamw:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True, capturable=True)
+    else:
+        from pygho_b200.dist import FlatAdamW
+        opt = FlatAdamW(bucket, lr=1e-3)
 
     hbs = host_batches(args, per_gpu, rank, args.num_batches, world)
     pinned = {}
@@ -567,8 +575,11 @@ def run_b200(args):
             pred, y = pred[:nv], y[:nv]
         loss = torch.nn.functional.l1_loss(y, pred)
         loss.backward()
-        bucket.allreduce_mean()
-        opt.step()
+        if args.torch_adamw:
+            bucket.allreduce_mean()
+            opt.step()
+        else:
+            opt.step(1.0 / bucket.allreduce_sum())
         return loss
 
     def barrier():

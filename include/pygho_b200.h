@@ -281,6 +281,14 @@ int pgh_linear_stats_f32(const float* x, int64_t M, int64_t K, const float* w, i
                          float momentum, float* mean, float* rstd, float* running_mean,
                          float* running_var, float* local_out, int64_t* num_batches_tracked,
                          void* ws, size_t ws_bytes, int32_t* tickets, void* stream);
+/* AdamW (torch.optim.AdamW semantics: decoupled decay, bias correction) over ONE flat buffer of
+ * all parameters / gradients / moments of the model (the optimisation step of example/zinc.py:
+ * 368-383 as a single launch instead of one multi-tensor launch per dtype/device group).
+ * step: device float = updates done so far (the caller increments it afterwards: graph
+ * capturable); grad_scale folds the 1 / world_size of the data-parallel gradient average in. */
+int pgh_adamw_flat_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       int64_t n, const float* step, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, float grad_scale, void* stream);
 /* out[e] (+)= sum_k part[k * n + e], k < slabs, n % 4 == 0: reduction over the row slabs of a
  * split-K weight-gradient GEMM (dW = dy^T x over all tuples, honn/utils.py:85-142 backward),
  * optionally accumulating into the parameter's gradient buffer; fixed order */

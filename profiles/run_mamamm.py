@@ -63,6 +63,13 @@ for algo in ALGOS:
         nbytes = alg_bytes if e is None else valid_bytes
         print(f"algo {algo} {tag}: {us:8.1f} us  {nbytes / us / 1e3:7.1f} GB/s ({nbytes / 1e6:.0f} MB moved by design)  "
               f"{padded_flops / us / 1e6:6.2f} TFLOP/s padded, {useful_flops / us / 1e6:6.2f} useful  rel.err {err:.2e}")
+# the gradient contractions' layouts (g @ B^T, A^T @ g) on the shipped kernels
+for algo in ALGOS:
+    if algo not in (2, 4):
+        continue
+    for ta, tb in ((False, True), (True, False), (True, True)):
+        us = timeit(lambda A, B: torch.ops.pygho_b200.mamamm(A, ta, B, tb, mask, ext, algo))
+        print(f"algo {algo} ext  trans_a={int(ta)} trans_b={int(tb)}: {us:8.1f} us  {valid_bytes / us / 1e3:7.1f} GB/s")
 us = timeit(ref_path)
 out = ref_path(*sets[0])
 err = float((out.double() - want).abs().max() / want.abs().max())

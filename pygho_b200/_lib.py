@@ -65,6 +65,7 @@ SIGNATURES = {
     "pgh_bn_ws_bytes": (_sz, [_i64, _i64]),
     "pgh_bn_stats_f32": (_i, [_p, _i64, _i64, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "pgh_sum_slabs_f32": (_i, [_p, _i64, _i64, _p, _i, _p]),
+    "pgh_adamw_flat_f32": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _f, _p]),
     "pgh_linear_stats_supported": (_i, [_i64, _i64, _i64]),
     "pgh_linear_stats_ws_bytes": (_sz, [_i64]),
     "pgh_linear_stats_f32": (_i, [_p, _i64, _i64, _p, _i64, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p,

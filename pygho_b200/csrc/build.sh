@@ -8,7 +8,7 @@ FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompil
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC"
 mkdir -p build
 objs=()
-for f in seg_gmr plan masked mamamm_tc fused_mlp linear_stats hodata; do
+for f in seg_gmr plan masked mamamm_tc mamamm_smem fused_mlp linear_stats hodata; do
   if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ common.cuh -nt build/$f.o ] || [ ticket.cuh -nt build/$f.o ] || [ ../../include/pygho_b200.h -nt build/$f.o ]; then
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f.cu -o build/$f.o &
   fi

@@ -388,6 +388,34 @@ __global__ void sum_slabs_kernel(const float4* __restrict__ part, int slabs, lon
   }
 }
 
+// AdamW over ONE flat parameter / gradient / moment buffer (decoupled weight decay, bias
+// correction, torch.optim.AdamW's update order).  `step` is a device scalar holding the number of
+// updates done so far (float); the caller increments it after the launch, so the step can be
+// captured in a CUDA graph.  grad_scale folds the 1 / world_size of the gradient average in.
+__global__ void adamw_flat_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                  float4* __restrict__ m, float4* __restrict__ v, long long n4,
+                                  const float* __restrict__ step, float lr, float b1, float b2,
+                                  float eps, float wd, float grad_scale) {
+  const float t = __ldg(step) + 1.f;
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+#define PGH_ADAM(X)                                                            \
+    {                                                                          \
+      const float gr = gg.X * grad_scale;                                      \
+      mm.X = b1 * mm.X + (1.f - b1) * gr;                                      \
+      vv.X = b2 * vv.X + (1.f - b2) * gr * gr;                                 \
+      const float denom = sqrtf(vv.X) * inv_sqrt_bc2 + eps;                    \
+      pp.X = pp.X * decay - step_size * (mm.X / denom);                        \
+    }
+    PGH_ADAM(x) PGH_ADAM(y) PGH_ADAM(z) PGH_ADAM(w)
+#undef PGH_ADAM
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
 static bool bn_ok(int64_t rows, int64_t C) {
   return rows > 0 && C >= 4 && C % 4 == 0 && C / 4 <= kBnThreads;
 }
@@ -422,6 +450,25 @@ extern "C" int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, const i
       g.blocks, g.grp, g.ngroups, tickets, eps, momentum, mean, rstd, running_mean, running_var,
       local_out, reinterpret_cast<long long*>(num_batches_tracked));
   return check_launch("bn_stats");
+}
+
+extern "C" int pgh_adamw_flat_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                  int64_t n, const float* step, float lr, float beta1, float beta2,
+                                  float eps, float weight_decay, float grad_scale, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step || n < 0 || (n & 3))
+    return arg_error("adamw_flat: arguments (n % 4 == 0)");
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+       reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+    return arg_error("adamw_flat: buffers must be 16-byte aligned");
+  if (n == 0) return 0;
+  const long long n4 = n / 4;
+  long long nb = (n4 + 255) / 256;
+  if (nb > kSMs * 8) nb = kSMs * 8;
+  adamw_flat_kernel<<<(unsigned)nb, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad),
+      reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq), n4, step, lr, beta1,
+      beta2, eps, weight_decay, grad_scale);
+  return check_launch("adamw_flat");
 }
 
 extern "C" int pgh_sum_slabs_f32(const float* part, int64_t slabs, int64_t n, float* out,

@@ -230,6 +230,12 @@ extern "C" int pgh_mask_extents(const uint8_t* mask, int64_t b, int64_t n1, int6
   return check_launch("mask_extents");
 }
 
+namespace pgh {
+int mamamm_smem_launch(const float* A, int trans_a, const float* B, int trans_b,
+                       const unsigned char* mask, const int* ext, int64_t b, int64_t n_i, int64_t n_j,
+                       int64_t n_k, int64_t dense, float* out, cudaStream_t s);
+}
+
 extern "C" int pgh_mamamm_f32(const float* A, int trans_a, const float* B, int trans_b,
                               const uint8_t* mask, const int32_t* ext, int64_t b, int64_t n_i,
                               int64_t n_j, int64_t n_k, int64_t dense, int algo, float* out,
@@ -238,6 +244,13 @@ extern "C" int pgh_mamamm_f32(const float* A, int trans_a, const float* B, int t
   if (b < 0 || n_i <= 0 || n_j <= 0 || n_k <= 0 || dense <= 0) return arg_error("mamamm: sizes");
   if (b == 0) return 0;
   cudaStream_t s = as_stream(stream);
+  // 4 = exact fp32 from a TMA-fed shared-memory ring (csrc/mamamm_smem.cu); shapes it does not
+  // take (dense % 16, more than 512 columns, a stage that does not fit twice) run on algo 0
+  if (algo == 4) {
+    const int rc = mamamm_smem_launch(A, trans_a, B, trans_b, mask, ext, b, n_i, n_j, n_k, dense, out, s);
+    if (rc >= 0) return rc;
+    algo = 0;
+  }
   // 1 = tcgen05, one CTA per (graph, slab); 2 = tcgen05, persistent warp-specialised pipeline
   // (falls back to 1 when two tile stages do not fit in shared memory)
   if (algo == 1 || algo == 2)

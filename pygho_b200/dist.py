@@ -42,29 +42,78 @@ class FlatGradBucket:
         if not self.params:
             raise ValueError("no trainable parameters")
         dev, dtype = self.params[0].device, self.params[0].dtype
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, dtype=dtype, device=dev)
-        off = 0
+        # every parameter starts at a multiple of 4 elements (16 bytes): the fused kernels add
+        # into these views with 128-bit accesses, and the flat optimizer walks the buffer as float4
+        self.offsets = []
+        total = 0
         for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=dtype, device=dev)
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
 
     def zero(self) -> None:
         self.flat.zero_()
 
     def allreduce_mean(self, group=None) -> None:
         """Average gradients over the ranks (no-op without an initialised group)."""
+        if self.allreduce_sum(group) > 1:
+            self.flat.div_(dist.get_world_size(group))
+
+    def allreduce_sum(self, group=None) -> int:
+        """Sum gradients over the ranks; returns the world size (the caller folds the 1 / world
+        of the average into its optimizer step, see :class:`FlatAdamW`)."""
         if not (dist.is_available() and dist.is_initialized()):
-            return
+            return 1
         world = dist.get_world_size(group)
-        if world == 1:
-            return
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        self.flat.div_(world)
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return world
 
     def nbytes(self) -> int:
         return self.flat.numel() * self.flat.element_size()
+
+
+class FlatAdamW:
+    """AdamW whose parameters, gradients and moments each live in ONE flat buffer: the whole
+    optimisation step is a single kernel launch (``pgh_adamw_flat_f32``) instead of torch's
+    multi-tensor launches (3 launches / 85 us per SSWL+ step for 5 MB of parameters -- 3 % of a
+    128-graph step at the 8-GPU strong-scaling point).  Same update rule as
+    ``torch.optim.AdamW`` (decoupled weight decay, bias correction); the step counter is a device
+    scalar, so the step is CUDA-graph capturable.  ``bucket`` is the model's
+    :class:`FlatGradBucket`; the parameters are re-pointed to views of a flat buffer laid out
+    like the bucket (``p.data`` keeps its values)."""
+
+    def __init__(self, bucket: "FlatGradBucket", lr: float = 1e-3, betas=(0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 1e-2):
+        self.bucket, self.lr, self.betas, self.eps, self.weight_decay = bucket, lr, betas, eps, weight_decay
+        flat = bucket.flat
+        if flat.dtype != torch.float32 or not flat.is_cuda:
+            raise TypeError("FlatAdamW needs float32 CUDA parameters")
+        self.param = torch.zeros_like(flat)
+        with torch.no_grad():
+            for p, off in zip(bucket.params, bucket.offsets):
+                view = self.param[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.steps = torch.zeros((1,), dtype=torch.float32, device=flat.device)
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0) -> None:
+        from . import _lib
+        flat = self.bucket.flat
+        _lib.call("pgh_adamw_flat_f32", self.param.data_ptr(), flat.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), flat.numel(), self.steps.data_ptr(), float(self.lr),
+                  float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                  float(grad_scale), _lib.stream_ptr(flat.device))
+        _lib.count_launch()
+        self.steps.add_(1.0)
+
+    def zero_grad(self) -> None:
+        self.bucket.zero()
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:

@@ -481,6 +481,10 @@ def linear_stats_ok(x: Tensor, weight: Tensor) -> bool:
     # stay opt-in (PYGHO_B200_FUSED_GEMM_WIDE=1) until the tile is shared by a CTA pair
     if weight.shape[0] != 128 and not _FUSED_GEMM_WIDE:
         return False
+    # K = 128: the epilogue (TMEM load, statistics, stores: ~5.8 us per 128-row tile) is longer than
+    # the loads, 70.9 us against cuBLAS 61.7 us + statistics at 230 k rows (profiles/r2_op_rooflines.md)
+    if weight.shape[1] < 256 and not _FUSED_GEMM_WIDE:
+        return False
     return (torch.backends.cuda.matmul.allow_tf32 and x.dtype == torch.float32 and x.ndim == 2
             and x.is_cuda and weight.dtype == torch.float32 and x.shape[0] >= _FUSED_GEMM_MIN_ROWS
             and bool(_lib.load().pgh_linear_stats_supported(x.shape[0], x.shape[1], weight.shape[0])))
@@ -838,7 +842,9 @@ def mamamm_algo_for(algo: int, n_i: int, n_j: int, n_k: int, dense: int) -> int:
     """The tensor-core kernels (algo 1 / 2) hold one (n_i x n_j) and one (n_j x n_k) tile per
     channel: n_i, n_j <= 128, n_k <= 64, dense % 8 == 0.  Anything else runs on the exact-fp32 kernel
     (algo 0).  Decided per CALL: the gradient contractions of a forward that fits may
-    not fit themselves (their (n_i, n_j, n_k) roles are permuted)."""
+    not fit themselves (their (n_i, n_j, n_k) roles are permuted).  algo 4 (exact fp32 from a
+    TMA-fed shared-memory ring, csrc/mamamm_smem.cu) takes any shape: the library itself runs the
+    shapes its ring cannot hold on algo 0."""
     if algo in (1, 2) and (dense % 8 != 0 or n_i > 128 or n_k > 64 or n_j > 128):
         return 0
     return algo

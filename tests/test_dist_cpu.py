@@ -27,7 +27,10 @@ def test_flat_bucket_views():
     m = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Linear(4, 2))
     b = FlatGradBucket(m.parameters())
     m(torch.ones(5, 3)).sum().backward()
-    assert b.flat.numel() == sum(p.numel() for p in m.parameters())
+    # every parameter starts on a 16-byte boundary of the flat buffer
+    assert b.flat.numel() == sum((p.numel() + 3) // 4 * 4 for p in m.parameters())
+    assert all(o % 4 == 0 for o in b.offsets)
+    assert m[1].bias.grad.data_ptr() == b.flat.data_ptr() + 4 * b.offsets[3]
     assert float(b.flat.abs().sum()) > 0
     assert m[0].weight.grad.data_ptr() == b.flat.data_ptr()
     b.zero()

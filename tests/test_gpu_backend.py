@@ -427,7 +427,7 @@ def test_masked_constructor_fills_pads(B):
     assert float(mt.fill_masked(5.0).sum()) == 16.0 + 5.0 * (72 - 16)
 
 
-@pytest.mark.parametrize("algo,tol", [(0, 2e-5), (1, 1e-2), (2, 1e-2)])
+@pytest.mark.parametrize("algo,tol", [(0, 2e-5), (1, 1e-2), (2, 1e-2), (4, 2e-5)])
 @pytest.mark.parametrize("d1,d2", [(2, 1), (1, 1), (1, 2), (2, 2)])
 def test_mamamm_forward_backward(B, monkeypatch, d1, d2, algo, tol):
     monkeypatch.setenv("PYGHO_B200_MAMAMM_ALGO", str(algo))
@@ -500,6 +500,46 @@ def test_mamamm_tcgen05_matches_fp32_kernel(n, d, ta, tb):
         assert torch.equal(torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, mask, e, 0), ref)
     from pygho_b200.ops import mask_extents
     assert torch.equal(mask_extents(mask).cpu(), torch.stack((sizes, sizes), 1).to(torch.int32))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("shape", [(6, 40, 40, 40, 128), (5, 37, 23, 29, 64), (7, 9, 9, 9, 16),
+                                   (3, 100, 70, 100, 32), (2, 20, 300, 12, 16), (4, 16, 16, 16, 40)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_mamamm_smem_ring_is_bit_identical_to_fp32_kernel(shape, ta, tb):
+    """algo 4 (TMA-fed shared-memory ring, exact fp32, csrc/mamamm_smem.cu) against algo 0: the
+    same j-ascending fmaf chains -> identical bits; rectangular extents, graphs of every size
+    incl. empty ones, a mask with holes, several row passes (n = 100), dense = 40 (not a
+    multiple of 16: runs on algo 0 inside the library), pads exactly zero."""
+    import pygho_b200.ops  # noqa: F401
+    b, n_i, n_j, n_k, d = shape
+    gen = torch.Generator().manual_seed(n_i * 7 + n_j * 3 + d + 2 * ta + tb)
+    si = torch.randint(0, n_i + 1, (b,), generator=gen)
+    sj = torch.randint(0, n_j + 1, (b,), generator=gen)
+    sk = torch.randint(0, n_k + 1, (b,), generator=gen)
+    si[0], sj[0], sk[0] = n_i, n_j, n_k
+    if b > 2:
+        si[1] = 0
+        sj[2] = 0
+    def band(s1, n1, s2, n2):
+        return (torch.arange(n1)[None, :, None] < s1[:, None, None]) & (torch.arange(n2)[None, None, :] < s2[:, None, None])
+    mA, mB, mO = band(si, n_i, sj, n_j), band(sj, n_j, sk, n_k), band(si, n_i, sk, n_k)
+    holes = (mO & (torch.rand((b, n_i, n_k), generator=gen) < 0.8)).to(DEV)
+    A = torch.randn((b, n_i, n_j, d), generator=gen) * mA.unsqueeze(-1)
+    Bm = torch.randn((b, n_j, n_k, d), generator=gen) * mB.unsqueeze(-1)
+    A = (A.transpose(1, 2) if ta else A).contiguous().to(DEV)
+    Bm = (Bm.transpose(1, 2) if tb else Bm).contiguous().to(DEV)
+    ext = torch.stack((si, sj, sk), 1).to(torch.int32).to(DEV)
+    ref = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, holes, None, 0)
+    for e in (None, ext):
+        torch.full((b, n_i, n_k, d), float("nan"), device=DEV)     # poison the next allocation
+        got = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, holes, e, 4)
+        assert torch.equal(got, ref), float((got - ref).abs().max())
+        assert float(got[~holes].abs().max()) == 0.0
+    # back-to-back launches re-arm their work queues (64 rotating, self-resetting)
+    for _ in range(70):
+        got = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, holes, ext, 4)
+    assert torch.equal(got, ref)
     torch.cuda.synchronize()
 
 

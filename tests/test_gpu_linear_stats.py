@@ -106,9 +106,9 @@ def test_mlp_block_on_fused_gemm_equals_cublas_path(rows, cin):
     w = torch.randn(rows, 128, device=DEV)
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
     last = [m for m in mlp.modules() if isinstance(m, torch.nn.Linear)][-1]
-    assert ops.linear_stats_ok(torch.empty(rows, last.in_features, device=DEV), last.weight)
-    wide, ops._FUSED_GEMM_WIDE = ops._FUSED_GEMM_WIDE, True    # cover the N = 256 / 384 kernels too
+    wide, ops._FUSED_GEMM_WIDE = ops._FUSED_GEMM_WIDE, True    # cover N = 256 / 384 and K = 128 too
     try:
+        assert ops.linear_stats_ok(torch.empty(rows, last.in_features, device=DEV), last.weight)
         (mlp(xa) * w).sum().backward()
     finally:
         ops._FUSED_GEMM_WIDE = wide

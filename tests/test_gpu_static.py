@@ -307,3 +307,31 @@ def test_syncbn_sharded_training_equals_single_process(tmp_path):
             raise
         outs.append(out)
     assert all(p.returncode == 0 for p in procs), "\n".join(o[-3000:] for o in outs)
+
+
+@pytest.mark.parametrize("world", [1, 4])
+def test_flat_adamw_equals_torch_adamw(world):
+    """FlatAdamW (one launch over flat parameter / gradient / moment buffers, the 1 / world of the
+    gradient average folded in) follows torch.optim.AdamW step for step."""
+    import copy
+    from pygho_b200.dist import FlatAdamW, FlatGradBucket
+    torch.manual_seed(5)
+    a = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.SiLU(), torch.nn.Linear(53, 3)).to(DEV)
+    b = copy.deepcopy(a)
+    bucket = FlatGradBucket(a.parameters())
+    flat = FlatAdamW(bucket, lr=3e-3, weight_decay=0.05)
+    ref = torch.optim.AdamW(b.parameters(), lr=3e-3, weight_decay=0.05)
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert torch.equal(p, q)                     # re-pointing the parameters kept their values
+        assert p.data_ptr() % 16 == 0
+    for it in range(6):
+        x = torch.randn(64, 37, device=DEV)
+        bucket.zero()
+        (a(x).square().sum() * world).backward()     # "sum over ranks" of identical shards
+        flat.step(1.0 / world)
+        ref.zero_grad()
+        b(x).square().sum().backward()
+        ref.step()
+        for p, q in zip(a.parameters(), b.parameters()):
+            assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), (it, float((p - q).abs().max()))
+    assert float(flat.steps) == 6.0
