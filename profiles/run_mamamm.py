@@ -63,6 +63,22 @@ for algo in ALGOS:
         nbytes = alg_bytes if e is None else valid_bytes
         print(f"algo {algo} {tag}: {us:8.1f} us  {nbytes / us / 1e3:7.1f} GB/s ({nbytes / 1e6:.0f} MB moved by design)  "
               f"{padded_flops / us / 1e6:6.2f} TFLOP/s padded, {useful_flops / us / 1e6:6.2f} useful  rel.err {err:.2e}")
+if os.environ.get("ABLATE") and 4 in ALGOS:
+    from pygho_b200 import _lib
+    names = {0: "all", 1: "no FMAs", 2: "no loads", 3: "no loads, no FMAs", 4: "no stores", 8: "no pad fill",
+             12: "no stores, no pad fill", 13: "loads only", 14: "FMAs only", 15: "queue + barriers only",
+             16: "four channels per lane only", 30: "FMAs only, four channels per lane"}
+    for dbg, name in names.items():
+        _lib.load().pgh_set_tuning(7, dbg)
+        for tag, e in (("full", None), ("ext ", ext)):
+            us = timeit(lambda A, B: torch.ops.pygho_b200.mamamm(A, False, B, False, mask, e, 4))
+            print(f"algo 4 {tag} ablation {dbg:2d} ({name}): {us:8.1f} us")
+    for hint in (0, 1000000):
+        for dbg in (0, 14, 15):
+            _lib.load().pgh_set_tuning(7, dbg | (hint << 8))
+            us = timeit(lambda A, B: torch.ops.pygho_b200.mamamm(A, False, B, False, mask, ext, 4))
+            print(f"algo 4 ext  wait hint {hint:7d} ns, ablation {dbg:2d}: {us:8.1f} us")
+    _lib.load().pgh_set_tuning(7, 0)
 # the gradient contractions' layouts (g @ B^T, A^T @ g) on the shipped kernels
 for algo in ALGOS:
     if algo not in (2, 4):

@@ -1,0 +1,6 @@
+#!/usr/bin/env bash
+# Round 2, GPU call 23: mamamm algo 4 v4 (two channels per lane for small graphs): tests + ablation.
+set -x
+O=gpurun_out; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_backend.py -m gpu -x -q -k "mamamm" > $O/r2c23_tests.log 2>&1; tail -5 $O/r2c23_tests.log
+ABLATE=1 ALGOS=4 ITERS=20 timeout 600 python profiles/run_mamamm.py > $O/r2c23_mamamm_ablate.txt 2>&1; cat $O/r2c23_mamamm_ablate.txt

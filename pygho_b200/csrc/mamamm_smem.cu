@@ -12,13 +12,16 @@
 //              cp.async.bulk.tensor boxes (16 channels x JC x 8 rows / columns) of A' and B' into a
 //              shared-memory ring -- only boxes that intersect the graph's valid extents are
 //              fetched, the ring keeps filling across unit boundaries
-//   warps 0-14 consumers: a thread owns a 4 (rows) x 4 (columns) x 4 (channels) register tile;
+//   warps 0-13 consumers: a thread owns a 4 (rows) x 4 (columns) x 4 (channels) register tile;
 //              four lanes cover the 16 channels of a cell, the two lane groups of a quarter
 //              warp share the A' rows (broadcast) and take the even / odd columns of an 8-column
 //              block, whose cells are an odd number of 64-byte cells apart in both operand
 //              layouts (JC = 9 when B' is contraction-major): all LDS.128 are conflict free
-//   epilogue   mask select + 128-bit stores of the valid region; the pad region of the output is
-//              zero-filled in whole 512-byte rows, dealt over the units of the graph
+//   epilogue   mask select (bytes prefetched towards L1 at the unit's first chunk) + 128-bit stores
+//              of the valid region
+//   warp 14    pad filler: one thread follows the ring's unit descriptors and has the bulk-copy
+//              engine write the pad region of the output from a block of zeros in shared memory
+//              (cp.async.bulk shared -> global, one run per output row), while the FMA warps work
 //
 // Sum order is j ascending with fmaf, the same as the CUDA-core kernel (algo 0): bit-identical.
 // Operand pads must be zero (MaskedTensor keeps them at padvalue 0), as for the other kernels.
@@ -31,12 +34,14 @@ namespace pgh {
 constexpr int kMsCH = 16;                    // channels per slab: one 64-byte cell per (row, col)
 constexpr int kMsCell = kMsCH * 4;           // bytes
 constexpr int kMsRB = 8;                     // rows / columns per TMA box
-constexpr int kMsConsumerWarps = 15;          // + 1 producer warp = 16 warps: 128 registers per thread
+constexpr int kMsConsumerWarps = 14;          // + pad-fill warp + producer warp = 16 warps: 128 registers per thread
+constexpr int kMsFillWarp = kMsConsumerWarps, kMsProducerWarp = kMsConsumerWarps + 1;
 constexpr int kMsConsumers = kMsConsumerWarps * 32;
-constexpr int kMsThreads = kMsConsumers + 32;
+constexpr int kMsThreads = kMsConsumers + 64;
 constexpr int kMsMaxPairs = kMsConsumers / 8;   // a pair = 4 rows x 8 columns of output
 constexpr int kMsMaxStages = 8;
 constexpr size_t kMsSmemCap = 227 * 1024;
+constexpr int kMsZeroBytes = 4096;            // source of the pad-fill bulk stores
 
 struct MsParams {
   int n_i, n_j, n_k, dense;       // tensor extents of A' (n_i x n_j) and B' (n_j x n_k)
@@ -44,6 +49,9 @@ struct MsParams {
   int nab_max, nkb_max;           // boxes of A' / B' per stage
   int stages, stage_bytes;
   long long units;                // b * nslab * npass
+  unsigned long long* trace;      // profiling hook (pgh_debug_trace): [count, (tag, clock) ...] of CTA 0
+  long long trace_words;
+  int dbg;                        // profiling only (pgh_set_tuning key 7): 1 no FMAs, 2 no loads, 4 no stores, 8 no pad fill, 16 never two channels per lane, 32 no mask loads, 64 no tile stores
 };
 
 struct MsMeta {
@@ -57,18 +65,30 @@ __device__ __forceinline__ void ms_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 // bounded wait: a lost arrival traps (reported as a launch error) instead of hanging the GPU
-__device__ __forceinline__ void ms_mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t spin = 0; spin < (1u << 14); ++spin) {
+__device__ __forceinline__ void ms_mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     uint32_t done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(1000000u)
-        : "memory");
+    if (hint_ns) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}\n"
+          : "=r"(done)
+          : "r"(bar), "r"(parity), "r"(hint_ns)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}\n"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
     if (done) return;
   }
   __trap();
@@ -88,18 +108,142 @@ __device__ __forceinline__ void ms_tma_load_4d(uint32_t dst, const CUtensorMap* 
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ float4 ms_lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(addr));
-  return v;
+// profiling hook: CTA 0 appends (tag, clock64) pairs; tag = role << 56 | unit-local info
+__device__ __forceinline__ void ms_trace(const MsParams& P, unsigned long long tag) {
+  if (P.trace && blockIdx.x == 0) {
+    const unsigned long long i = atomicAdd(P.trace, 2ull);
+    if ((long long)i + 3 < P.trace_words) {
+      P.trace[1 + i] = tag;
+      P.trace[2 + i] = (unsigned long long)clock64();
+    }
+  }
 }
-__device__ __forceinline__ void ms_fma4(float4& acc, const float4& a, const float4& b) {
-  acc.x = fmaf(a.x, b.x, acc.x);
-  acc.y = fmaf(a.y, b.y, acc.y);
-  acc.z = fmaf(a.z, b.z, acc.z);
-  acc.w = fmaf(a.w, b.w, acc.w);
+
+struct MsRing {
+  uint32_t ring, full, empty;     // shared-memory addresses: stage 0, full_bar[0], empty_bar[0]
+  int s;
+  uint32_t ph, hint;
+};
+
+template <int V> struct MsVec;
+template <> struct MsVec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(uint32_t addr) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+  }
+};
+template <> struct MsVec<2> {
+  float v[2];
+  __device__ __forceinline__ void load(uint32_t addr) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
+  }
+};
+
+// One unit (graph, 16-channel slab, row pass) on the consumer warps: all its chunks, then the
+// epilogue.  L lanes cover the 16 channels of a cell (L = 4: float4 per lane, L = 8: float2); the
+// caller has already waited for the unit's first chunk.
+template <bool AK, bool BK, int L>
+__device__ __forceinline__ void ms_unit(const MsMeta& m, MsRing& R, const MsParams& P,
+                                        const unsigned char* __restrict__ mask, float* __restrict__ out) {
+  constexpr int JC = BK ? 9 : 8;
+  constexpr int kBoxBytes = kMsRB * JC * kMsCell;
+  constexpr int V = kMsCH / L;                          // channels per lane
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid / L, l = tid % L, pair = grp >> 1, par = grp & 1;
+  const int nkb = (m.ek + kMsRB - 1) / kMsRB;
+  const int it = nkb > 0 ? pair / nkb : 0;
+  const int kb = nkb > 0 ? pair - it * nkb : 0;
+  const int i0 = it * 4;
+  const bool active = m.nchunks > 0 && i0 < m.rows;
+  const int rr0 = i0 & 7;
+  const uint32_t offA = (uint32_t)((i0 >> 3) * kBoxBytes + (AK ? rr0 * JC : rr0) * kMsCell + l * V * 4);
+  const uint32_t offB =
+      (uint32_t)(P.nab_max * kBoxBytes + kb * kBoxBytes + (BK ? par * JC : par) * kMsCell + l * V * 4);
+  const int r0 = m.pass * P.rows_per_pass;
+  // first cell of this thread's tile (row r0 + i0, column kb * 8 + par)
+  const long long cellb = ((long long)m.item * P.n_i + r0 + i0) * P.n_k + kb * kMsRB + par;
+  if (active && l == 0) {
+    // the epilogue's mask bytes: start them towards L1 now, no register held
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+      if (r0 + i0 + x < m.ei) asm volatile("prefetch.global.L1 [%0];" ::"l"(mask + cellb + (long long)x * P.n_k));
+  }
+  float acc[4][4][V];
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+#pragma unroll
+      for (int c = 0; c < V; ++c) acc[x][y][c] = 0.f;
+
+  const int nst = m.nchunks > 0 ? m.nchunks : 1;
+  const bool tr = tid == 0 && P.trace != nullptr;
+  for (int ch = 0; ch < nst; ++ch) {
+    if (ch > 0) ms_mbar_wait(R.full + 8u * R.s, R.ph, R.hint);
+    if (tr) ms_trace(P, (2ull << 56) | ((unsigned long long)m.item << 16) | (m.slab << 8) | ch);
+    if (active && !(P.dbg & 1)) {
+      const uint32_t base = R.ring + (uint32_t)R.s * (uint32_t)P.stage_bytes;
+      const uint32_t pa = base + offA, pb = base + offB;
+#pragma unroll(L == 8 ? 2 : 1)
+      for (int jj = 0; jj < JC; ++jj) {
+        MsVec<V> a[4], bv[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) a[x].load(pa + (uint32_t)((AK ? x * JC + jj : jj * kMsRB + x) * kMsCell));
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+          bv[y].load(pb + (uint32_t)((BK ? 2 * y * JC + jj : jj * kMsRB + 2 * y) * kMsCell));
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int c = 0; c < V; ++c) acc[x][y][c] = fmaf(a[x].v[c], bv[y].v[c], acc[x][y][c]);
+      }
+    }
+    __syncwarp();
+    if (tr) ms_trace(P, (3ull << 56) | ((unsigned long long)m.item << 16) | (m.slab << 8) | ch);
+    if (lane == 0) ms_mbar_arrive(R.empty + 8u * R.s);
+    if (++R.s == P.stages) { R.s = 0; R.ph ^= 1u; }
+  }
+  if (tr) ms_trace(P, (4ull << 56) | ((unsigned long long)m.item << 16) | (m.slab << 8));
+
+  if (active && !(P.dbg & 4)) {
+    // ------------------------------------------------------------------ epilogue of the unit
+    const unsigned char* mp = mask + cellb;
+    float* op = out + cellb * P.dense + m.slab * kMsCH + l * V;
+    const int ni = m.ei - (r0 + i0), nk = m.ek - (kb * kMsRB + par);    // valid rows / columns from here
+    unsigned int mk = 0;
+    if (P.dbg & 32) {
+      mk = 0xFFFFu;
+    } else {
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+          if (x < ni && 2 * y < nk && mp[(long long)x * P.n_k + 2 * y]) mk |= 1u << (x * 4 + y);
+    }
+    if (P.dbg & 64) {          // profiling: mask loads only, one store
+      if (mk == 0x12345u) *op = 1.f;
+      return;
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      float* orow = op + (long long)x * P.n_k * P.dense;
+#pragma unroll
+      for (int y = 0; y < 4; ++y) {
+        if (x < ni && 2 * y < nk) {
+          const bool on = (mk >> (x * 4 + y)) & 1u;
+          float* o = orow + (long long)(2 * y) * P.dense;
+          if (V == 4)
+            *reinterpret_cast<float4*>(o) = on ? make_float4(acc[x][y][0], acc[x][y][1], acc[x][y][V - 2], acc[x][y][V - 1])
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          else
+            *reinterpret_cast<float2*>(o) = on ? make_float2(acc[x][y][0], acc[x][y][1]) : make_float2(0.f, 0.f);
+        }
+      }
+    }
+  }
+  if (tr) ms_trace(P, (5ull << 56) | ((unsigned long long)m.item << 16) | (m.slab << 8));
 }
 
 // AK / BK: the operand's contraction index is its fast (inner) spatial dim as stored:
@@ -119,46 +263,61 @@ mamamm_smem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __shared__ __align__(8) unsigned long long full_bar[kMsMaxStages], empty_bar[kMsMaxStages];
   __shared__ MsMeta meta[kMsMaxStages];
 
-  const uint32_t ring = (ms_u32(ms_smem_raw) + 127u) & ~127u;
+  // [zeros: kMsZeroBytes][ring: stages x stage_bytes], 128-byte aligned
+  const uint32_t zeros = (ms_u32(ms_smem_raw) + 127u) & ~127u;
+  const uint32_t ring = zeros + kMsZeroBytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int o = tid * 16; o < kMsZeroBytes; o += kMsThreads * 16)
+    asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(zeros + o), "f"(0.f) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> bulk-copy reads
 
   if (tid == 0) {
     for (int s = 0; s < P.stages; ++s) {
       ms_mbar_init(ms_u32(&full_bar[s]), 1);
-      ms_mbar_init(ms_u32(&empty_bar[s]), kMsConsumerWarps);
+      ms_mbar_init(ms_u32(&empty_bar[s]), kMsConsumerWarps + 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const int upi = P.nslab * P.npass;          // units per graph
+  const uint32_t hint = (uint32_t)P.dbg >> 8;  // suspend-time hint of the barrier waits, ns (0: none)
 
-  if (warp == kMsConsumerWarps) {
+  if (warp == kMsProducerWarp) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (;;) {
-        const unsigned int u = atomicAdd(&counters[0], 1u);
-        if ((long long)u >= P.units) break;
+      // the queue is read two units ahead and the extents one unit ahead, so neither the atomic's
+      // nor the loads' round trip sits between two units' boxes
+      unsigned int u = atomicAdd(&counters[0], 1u);
+      unsigned int u1 = atomicAdd(&counters[0], 1u);
+      int e0 = P.n_i, e1 = P.n_j, e2 = P.n_k;
+      if (ext && (long long)u < P.units) {
+        const int it = (int)(u / (unsigned)upi);
+        e0 = ext[3 * it + 0]; e1 = ext[3 * it + 1]; e2 = ext[3 * it + 2];
+      }
+      while ((long long)u < P.units) {
+        const unsigned int u2 = atomicAdd(&counters[0], 1u);
+        int f0 = P.n_i, f1 = P.n_j, f2 = P.n_k;
+        if (ext && (long long)u1 < P.units) {
+          const int it = (int)(u1 / (unsigned)upi);
+          f0 = ext[3 * it + 0]; f1 = ext[3 * it + 1]; f2 = ext[3 * it + 2];
+        }
         const int item = (int)(u / (unsigned)upi), rem = (int)(u % (unsigned)upi);
         const int slab = rem / P.npass, pass = rem % P.npass;
-        int ei = P.n_i, ej = P.n_j, ek = P.n_k;
-        if (ext) {
-          ei = min(max(ext[3 * item + 0], 0), P.n_i);
-          ej = min(max(ext[3 * item + 1], 0), P.n_j);
-          ek = min(max(ext[3 * item + 2], 0), P.n_k);
-        }
+        const int ei = min(max(e0, 0), P.n_i), ej = min(max(e1, 0), P.n_j), ek = min(max(e2, 0), P.n_k);
         const int r0 = pass * P.rows_per_pass;
         const int rows = max(min(ei - r0, P.rows_per_pass), 0);
         const int nab = (rows + kMsRB - 1) / kMsRB, nkb = (ek + kMsRB - 1) / kMsRB;
         const int nch = (rows > 0 && ek > 0) ? max((ej + JC - 1) / JC, 1) : 0;
         const int c0 = slab * kMsCH;
         for (int ch = 0; ch < max(nch, 1); ++ch) {
-          ms_mbar_wait(ms_u32(&empty_bar[s]), ph ^ 1u);
+          ms_mbar_wait(ms_u32(&empty_bar[s]), ph ^ 1u, hint);
+          ms_trace(P, (1ull << 56) | ((unsigned long long)item << 16) | (slab << 8) | ch);
           meta[s] = MsMeta{item, slab, pass, ch, nch, ei, ek, rows};
           const uint32_t fb = ms_u32(&full_bar[s]);
-          if (nch == 0) {
+          if (nch == 0 || (P.dbg & 2)) {
             ms_mbar_arrive(fb);
           } else {
             ms_mbar_expect_tx(fb, (uint32_t)((nab + nkb) * kBoxBytes));
@@ -178,9 +337,11 @@ mamamm_smem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
           if (++s == P.stages) { s = 0; ph ^= 1u; }
         }
+        u = u1; u1 = u2;
+        e0 = f0; e1 = f1; e2 = f2;
       }
       // end marker for the consumers
-      ms_mbar_wait(ms_u32(&empty_bar[s]), ph ^ 1u);
+      ms_mbar_wait(ms_u32(&empty_bar[s]), ph ^ 1u, hint);
       meta[s] = MsMeta{-1, 0, 0, 0, 0, 0, 0, 0};
       ms_mbar_arrive(ms_u32(&full_bar[s]));
       // the last CTA to run dry re-arms the queue for the next launch
@@ -194,84 +355,57 @@ mamamm_smem_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     return;
   }
 
-  // -------------------------------------------------------------------- consumers
-  const int grp = tid >> 2, l4 = tid & 3, pair = grp >> 1, par = grp & 1;
-  float4 acc[4][4];
-  int s = 0;
-  uint32_t ph = 0;
-  bool active = false;
-  int i0 = 0, kb = 0;
-  uint32_t offA = 0, offB = 0;
-  for (;;) {
-    ms_mbar_wait(ms_u32(&full_bar[s]), ph);
-    const MsMeta m = meta[s];
-    if (m.item < 0) break;
-    if (m.chunk == 0) {
-      const int nkb = (m.ek + kMsRB - 1) / kMsRB;
-      const int it = nkb > 0 ? pair / nkb : 0;
-      kb = nkb > 0 ? pair - it * nkb : 0;
-      i0 = it * 4;
-      active = m.nchunks > 0 && i0 < m.rows;
-      const int rr0 = i0 & 7;
-      offA = (uint32_t)((i0 >> 3) * kBoxBytes + (AK ? rr0 * JC : rr0) * kMsCell + l4 * 16);
-      offB = (uint32_t)(P.nab_max * kBoxBytes + kb * kBoxBytes + (BK ? par * JC : par) * kMsCell + l4 * 16);
-#pragma unroll
-      for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (active) {
-      const uint32_t base = ring + (uint32_t)s * (uint32_t)P.stage_bytes;
-      const uint32_t pa = base + offA, pb = base + offB;
-#pragma unroll(1)
-      for (int jj = 0; jj < JC; ++jj) {
-        float4 a[4], bv[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-          a[x] = ms_lds128(pa + (uint32_t)((AK ? x * JC + jj : jj * kMsRB + x) * kMsCell));
-#pragma unroll
-        for (int y = 0; y < 4; ++y)
-          bv[y] = ms_lds128(pb + (uint32_t)((BK ? 2 * y * JC + jj : jj * kMsRB + 2 * y) * kMsCell));
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y) ms_fma4(acc[x][y], a[x], bv[y]);
+  if (warp == kMsFillWarp) {
+    // ------------------------------------------------------ pad filler (off the FMA warps' path)
+    // follows the ring like a consumer, but only reads the unit's extents: the pad region of the
+    // output (rows >= ei, and the columns >= ek of the rows below) is written by the bulk-copy
+    // engine from a block of zeros in shared memory (cp.async.bulk shared -> global), one run
+    // per output row, the rows dealt over the units of the graph
+    int s = 0;
+    uint32_t ph = 0;
+    const long long row_bytes = (long long)P.n_k * P.dense * 4;
+    for (;;) {
+      ms_mbar_wait(ms_u32(&full_bar[s]), ph, hint);
+      const MsMeta m = meta[s];
+      __syncwarp();
+      if (lane == 0) ms_mbar_arrive(ms_u32(&empty_bar[s]));
+      if (++s == P.stages) { s = 0; ph ^= 1u; }
+      if (m.item < 0) break;
+      if (m.chunk != 0 || (P.dbg & 8) || lane != 0) continue;
+      char* obase = reinterpret_cast<char*>(out) + (long long)m.item * P.n_i * row_bytes;
+      for (int i = m.slab * P.npass + m.pass; i < P.n_i; i += upi) {
+        const int k0 = i < m.ei ? m.ek : 0;
+        char* dst = obase + i * row_bytes + (long long)k0 * P.dense * 4;
+        long long left = (long long)(P.n_k - k0) * P.dense * 4;
+        while (left > 0) {
+          const uint32_t n = (uint32_t)(left < kMsZeroBytes ? left : kMsZeroBytes);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(zeros), "r"(n)
+                       : "memory");
+          dst += n;
+          left -= n;
+        }
       }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    __syncwarp();
-    if (lane == 0) ms_mbar_arrive(ms_u32(&empty_bar[s]));
-    if (++s == P.stages) { s = 0; ph ^= 1u; }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    return;
+  }
 
-    if (m.chunk + 1 >= m.nchunks) {
-      // ---------------------------------------------------------------- epilogue of the unit
-      const long long cell0 = (long long)m.item * P.n_i * P.n_k;
-      if (active) {
-        const int r0 = m.pass * P.rows_per_pass;
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const int i = r0 + i0 + x;
-#pragma unroll
-          for (int y = 0; y < 4; ++y) {
-            const int k = kb * kMsRB + 2 * y + par;
-            if (i < m.ei && k < m.ek) {
-              const long long cell = cell0 + (long long)i * P.n_k + k;
-              const float4 v = mask[cell] ? acc[x][y] : make_float4(0.f, 0.f, 0.f, 0.f);
-              *reinterpret_cast<float4*>(out + cell * P.dense + m.slab * kMsCH + l4 * 4) = v;
-            }
-          }
-        }
-      }
-      // pads of the output: whole rows of `dense` zeros, dealt over the units of the graph
-      const int cells = P.n_i * P.n_k, me = m.slab * P.npass + m.pass;
-      const int c4n = P.dense >> 2;
-      for (int q = me + upi * warp; q < cells; q += upi * kMsConsumerWarps) {
-        const int i = q / P.n_k, k = q - i * P.n_k;
-        if (i >= m.ei || k >= m.ek) {
-          float4* row = reinterpret_cast<float4*>(out + (cell0 + q) * P.dense);
-          for (int c4 = lane; c4 < c4n; c4 += 32) row[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    }
+  // -------------------------------------------------------------------- consumers
+  MsRing R;
+  R.ring = ring; R.full = ms_u32(&full_bar[0]); R.empty = ms_u32(&empty_bar[0]);
+  R.s = 0; R.ph = 0; R.hint = hint;
+  for (;;) {
+    ms_mbar_wait(R.full + 8u * R.s, R.ph, hint);
+    const MsMeta m = meta[R.s];
+    if (m.item < 0) break;
+    // units that need at most half of the tile slots are spread over twice the threads (two
+    // channels per lane instead of four): twice the warps to hide the shared-memory latency
+    const int need = ((m.rows + 3) >> 2) * ((m.ek + kMsRB - 1) / kMsRB);
+    if (need * 16 <= kMsConsumers && !(P.dbg & 16))
+      ms_unit<AK, BK, 8>(m, R, P, mask, out);
+    else
+      ms_unit<AK, BK, 4>(m, R, P, mask, out);
   }
 }
 
@@ -308,6 +442,9 @@ static bool ms_make_map(CUtensorMap* map, const float* base, int64_t b, int64_t 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+extern unsigned long long* g_trace_host;   // mamamm_tc.cu (pgh_debug_trace)
+extern long long g_trace_host_words;
+
 // self-resetting work queues, rotated per launch so that launches on different streams (or
 // concurrent branches of one captured graph) never share one
 constexpr int kMsQueues = 64;
@@ -329,13 +466,16 @@ static bool ms_plan(int64_t b, int64_t n_i, int64_t n_j, int64_t n_k, int64_t de
   P.nab_max = (P.rows_per_pass + kMsRB - 1) / kMsRB;
   P.nkb_max = nkb;
   P.stage_bytes = (P.nab_max + P.nkb_max) * kMsRB * JC * kMsCell;
-  const long long room = (long long)kMsSmemCap - 1024 - 128;   // static barriers / meta, alignment
+  const long long room = (long long)kMsSmemCap - 1024 - 128 - kMsZeroBytes;   // static barriers / meta, alignment
   long long st = room / P.stage_bytes;
   if (st < 2) return false;
   P.stages = (int)(st > kMsMaxStages ? kMsMaxStages : st);
   const long long units = (long long)b * P.nslab * P.npass;
   if (units <= 0 || units > 0x7fffffffLL - 4096 || (long long)n_i * n_k > 0x7fffffffLL) return false;
   P.units = units;
+  P.dbg = g_tune[7];
+  P.trace = g_trace_host;
+  P.trace_words = g_trace_host_words;
   return true;
 }
 
@@ -343,7 +483,7 @@ template <bool AK, bool BK>
 static int ms_launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const unsigned char* mask,
                        const int* ext, const MsParams& P, float* out, unsigned int* counters,
                        cudaStream_t s) {
-  const size_t smem = (size_t)P.stages * P.stage_bytes + 128;
+  const size_t smem = (size_t)P.stages * P.stage_bytes + 128 + kMsZeroBytes;
   static bool attr_set = false;
   if (!attr_set) {
     PGH_CUDA(cudaFuncSetAttribute(mamamm_smem_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,

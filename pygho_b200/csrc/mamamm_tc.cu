@@ -961,9 +961,17 @@ int mamamm_tc_launch(const float* A, int trans_a, const float* B, int trans_b,
 
 }  // namespace pgh
 
+namespace pgh {
+// the same buffer, for kernels in other translation units (passed to them as a kernel argument)
+unsigned long long* g_trace_host = nullptr;
+long long g_trace_host_words = 0;
+}
+
 extern "C" int pgh_debug_trace(void* device_buf, int64_t n_words) {
   unsigned long long* p = static_cast<unsigned long long*>(device_buf);
   long long n = device_buf ? (long long)n_words : 0;
+  pgh::g_trace_host = p;
+  pgh::g_trace_host_words = n;
   PGH_CUDA(cudaMemcpyToSymbol(pgh::g_trace, &p, sizeof(p)));
   PGH_CUDA(cudaMemcpyToSymbol(pgh::g_trace_words, &n, sizeof(n)));
   return 0;
