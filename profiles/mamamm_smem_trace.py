@@ -45,25 +45,31 @@ def graph_time(algo, e, dbg=0, reps=12):
     return e0.elapsed_time(e1) * 1e3 / (5 * reps)
 
 
-for algo in (2, 4):
+for algo in (() if os.environ.get("TRACE_ONLY") else (2, 4)):
     print(f"graph replay: algo {algo} ext {graph_time(algo, ext):7.1f} us   full {graph_time(algo, None):7.1f} us")
-for dbg, name in ((1, "no FMAs"), (4, "no stores"), (13, "loads only"), (14, "FMAs only"), (15, "queue + barriers only"),
+for dbg, name in () if os.environ.get("TRACE_ONLY") else ((1, "no FMAs"), (4, "no stores"), (13, "loads only"), (14, "FMAs only"), (15, "queue + barriers only"),
                   (16, "four channels per lane only"), (32, "no mask loads"), (64, "mask loads, no tile stores"),
                   (33, "no FMAs, no mask loads"), (65, "no FMAs, mask loads, no tile stores")):
     print(f"graph replay: algo 4 ext ablation {dbg:2d} ({name}): {graph_time(4, ext, dbg):7.1f} us")
 
 K = 4096
 buf = torch.zeros(K, dtype=torch.int64, device=dev)
+_lib.load().pgh_set_tuning(7, int(os.environ.get("TRACE_DBG", "0")))
 _lib.call("pgh_debug_trace", buf.data_ptr(), buf.numel())
 mm(sets[0][0], False, sets[0][1], False, mask, ext, 4)
 torch.cuda.synchronize()
 _lib.call("pgh_debug_trace", None, 0)
+_lib.load().pgh_set_tuning(7, 0)
 t = buf.cpu().numpy()
-cnt = int(t[0]) // 2
-ev = t[1:1 + 2 * min(cnt, (K - 1) // 2)].reshape(-1, 2)
-t0 = ev[:, 1].min()
-names = {1: "P issue", 2: "C start", 3: "C done ", 4: "C unit ", 5: "C epi  "}
-print(f"{cnt} events of CTA 0 (cycles since first stamp; 1 us = ~1900 cycles)")
-for tag, clk in sorted(ev.tolist(), key=lambda r: r[1]):
+half = (K - 2) // 2
+ev = []
+for region in (0, 1):
+    cnt = int(t[region])
+    ev += t[2 + region * half: 2 + region * half + 2 * cnt].reshape(-1, 2).tolist()
+t0 = min(e[1] for e in ev)
+names = {1: "P issue", 2: "C start", 3: "C done ", 4: "C unit ", 5: "C epi  ", 6: "P begin", 7: "P unit issued", 8: "P next unit known",
+         9: "P end marker sent", 10: "P pad fill drained"}
+print(f"{len(ev)} events of CTA 0 (cycles since first stamp; 1 us = ~1900 cycles), TRACE_DBG={os.environ.get('TRACE_DBG', '0')}")
+for tag, clk in sorted(ev, key=lambda r: r[1]):
     role, item, slab, ch = tag >> 56, (tag >> 16) & 0xFFFFFF, (tag >> 8) & 0xFF, tag & 0xFF
     print(f"{clk - t0:9d}  {names.get(role, role)}  item {item:3d} (n={int(sizes[item]):2d}) slab {slab} chunk {ch}")
