@@ -3,6 +3,7 @@
 // Layout is the reference's: (b, n, n, dense) with the dense (channel) axis contiguous
 // (backend/MaTensor.py:34-111).  Every kernel maps lanes to channels, so each warp
 // request is one contiguous 128 B line.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -126,6 +127,214 @@ __global__ void masked_pool_kernel(const float4* __restrict__ data,
   if (out_mask && ch == 0) out_mask[rest] = cnt > 0;
 }
 
+// Warp-cooperative variant for dense % 128 == 0 (all 32 lanes of a warp share one output row):
+// the mask bytes of 32 reduced positions are fetched with ONE load per lane and turned into a
+// warp-uniform bit set, so the value loads no longer wait for a mask load each and 8 of them are
+// in flight per lane.  Same ascending order of the reduction as the per-thread kernel.
+// SPLIT (few output rows, long reduced extent, e.g. pooling both tuple dims of a graph): one
+// thread-block CLUSTER of kPoolCluster CTAs x 8 warps per output row; warp s of the cluster takes
+// the 32-position chunks s, s + 64, ...; partial results are combined in warp order inside each CTA
+// and then in CTA-rank order through distributed shared memory (deterministic, no workspace).
+constexpr int kPoolCluster = 8;
+
+template <int AGGR, bool SPLIT>
+__global__ void __launch_bounds__(256)
+masked_pool_warp_kernel(const float4* __restrict__ data, const unsigned char* __restrict__ mask,
+                        PoolView v, float4* __restrict__ out, unsigned char* __restrict__ out_mask,
+                        long long warps_total) {
+  const long long w = SPLIT ? (long long)(blockIdx.x / kPoolCluster)
+                          : ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= warps_total) return;
+  const int lane = threadIdx.x & 31;
+  const int wid = (int)(threadIdx.x >> 5);
+  const int crank = SPLIT ? (int)(blockIdx.x % kPoolCluster) : 0;     // == rank in the cluster (1-D grid)
+  const int sub = SPLIT ? crank * 8 + wid : 0;
+  constexpr int kStep = SPLIT ? 256 * kPoolCluster : 32;
+  const int cg = v.c4 >> 5;
+  const int ch = (int)(w % cg) * 32 + lane;
+  const long long rest = w / cg;
+  const int in = (int)(rest % v.inner);
+  const long long o = rest / v.inner;
+  const float init = AGGR == PGH_MAX ? -INFINITY : AGGR == PGH_MIN ? INFINITY : 0.f;
+  float4 acc = make_float4(init, init, init, init);
+  int cnt = 0;
+  const long long base = o * v.red * v.inner + in;
+  const unsigned char* mp = mask + base;
+  const float4* dp = data + base * v.c4 + ch;
+  const long long pstep = v.inner, dstep = (long long)v.inner * v.c4;
+  auto take = [&](const float4& x) {
+    if (AGGR == PGH_MAX) acc = make_float4(fmaxf(acc.x, x.x), fmaxf(acc.y, x.y), fmaxf(acc.z, x.z), fmaxf(acc.w, x.w));
+    else if (AGGR == PGH_MIN) acc = make_float4(fminf(acc.x, x.x), fminf(acc.y, x.y), fminf(acc.z, x.z), fminf(acc.w, x.w));
+    else acc = make_float4(acc.x + x.x, acc.y + x.y, acc.z + x.z, acc.w + x.w);
+  };
+  for (int rc = sub * 32; rc < v.red; rc += kStep) {
+    const unsigned char m = rc + lane < v.red ? __ldg(mp + (rc + lane) * pstep) : (unsigned char)0;
+    unsigned bits = __ballot_sync(0xffffffffu, m != 0);
+    cnt += __popc(bits);
+    const float4* dq = dp + rc * dstep;
+    while (bits) {
+      float4 x[8];
+      int n = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (bits) {
+          const int r = __ffs(bits) - 1;
+          bits &= bits - 1;
+          x[u] = __ldg(dq + r * dstep);
+          n = u + 1;
+        }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (u < n) take(x[u]);
+    }
+  }
+  if (SPLIT) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float4 part[8][32];
+    __shared__ int pcnt[8];
+    __shared__ float4 cpart[kPoolCluster][32];   // used in the cluster's rank-0 CTA
+    __shared__ int ccnt[kPoolCluster];
+    part[wid][lane] = acc;
+    if (lane == 0) pcnt[wid] = cnt;
+    __syncthreads();
+    if (wid == 0) {
+      acc = part[0][lane];
+      cnt = pcnt[0];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) { take(part[q][lane]); cnt += pcnt[q]; }
+      cluster.map_shared_rank(&cpart[0][0], 0)[crank * 32 + lane] = acc;
+      if (lane == 0) cluster.map_shared_rank(&ccnt[0], 0)[crank] = cnt;
+    }
+    cluster.sync();
+    if (crank != 0 || wid != 0) return;
+    acc = cpart[0][lane];
+    cnt = ccnt[0];
+#pragma unroll
+    for (int q = 1; q < kPoolCluster; ++q) { take(cpart[q][lane]); cnt += ccnt[q]; }
+  }
+  if (cnt == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  else if (AGGR == PGH_MEAN) {
+    const float n = (float)cnt;
+    acc = make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
+  }
+  if (AGGR == PGH_MAX || AGGR == PGH_MIN) {
+    if (isinf(acc.x)) acc.x = 0.f;
+    if (isinf(acc.y)) acc.y = 0.f;
+    if (isinf(acc.z)) acc.z = 0.f;
+    if (isinf(acc.w)) acc.w = 0.f;
+  }
+  out[rest * v.c4 + ch] = acc;
+  if (out_mask && ch == 0) out_mask[rest] = cnt > 0;
+}
+
+// Backward, warp-cooperative (dense % 128 == 0): mask bits by ballot, stores never wait for a
+// mask load; the tie / valid counts of mean, max and min come from the same bit sets.
+template <int AGGR, bool SPLIT>
+__global__ void __launch_bounds__(256)
+masked_pool_bwd_warp_kernel(const float4* __restrict__ data, const unsigned char* __restrict__ mask,
+                            const float4* __restrict__ outp, const float4* __restrict__ g_out,
+                            PoolView v, float4* __restrict__ g_data, long long warps_total) {
+  const long long w = SPLIT ? (long long)(blockIdx.x / kPoolCluster)
+                          : ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= warps_total) return;
+  const int lane = threadIdx.x & 31;
+  const int wid = (int)(threadIdx.x >> 5);
+  const int crank = SPLIT ? (int)(blockIdx.x % kPoolCluster) : 0;     // == rank in the cluster (1-D grid)
+  const int sub = SPLIT ? crank * 8 + wid : 0;
+  constexpr int kStep = SPLIT ? 256 * kPoolCluster : 32;
+  const int cg = v.c4 >> 5;
+  const int ch = (int)(w % cg) * 32 + lane;
+  const long long rest = w / cg;
+  const int in = (int)(rest % v.inner);
+  const long long o = rest / v.inner;
+  const long long base = o * v.red * v.inner + in;
+  const unsigned char* mp = mask + base;
+  const float4* dp = data + base * v.c4 + ch;
+  float4* gp = g_data + base * v.c4 + ch;
+  const long long pstep = v.inner, dstep = (long long)v.inner * v.c4;
+  const float4 g = g_out[rest * v.c4 + ch];
+  constexpr bool kExt = (AGGR == PGH_MAX || AGGR == PGH_MIN);
+  const float4 ov = kExt ? outp[rest * v.c4 + ch] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 wgt = g;
+  if (AGGR != PGH_SUM) {
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int rc = sub * 32; rc < v.red; rc += kStep) {
+      const unsigned char m = rc + lane < v.red ? __ldg(mp + (rc + lane) * pstep) : (unsigned char)0;
+      unsigned bits = __ballot_sync(0xffffffffu, m != 0);
+      if (!kExt) { c0 += __popc(bits); continue; }
+      const float4* dq = dp + rc * dstep;
+      while (bits) {
+        float4 x[8];
+        int n = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (bits) {
+            const int r = __ffs(bits) - 1;
+            bits &= bits - 1;
+            x[u] = __ldg(dq + r * dstep);
+            n = u + 1;
+          }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (u < n) { c0 += x[u].x == ov.x; c1 += x[u].y == ov.y; c2 += x[u].z == ov.z; c3 += x[u].w == ov.w; }
+      }
+    }
+    if (!kExt) c1 = c2 = c3 = c0;
+    if (SPLIT) {
+      namespace cg = cooperative_groups;
+      cg::cluster_group cluster = cg::this_cluster();
+      __shared__ int4 pc[8][32];
+      __shared__ int4 cpc[32];                    // this CTA's counts, read by the whole cluster
+      pc[wid][lane] = make_int4(c0, c1, c2, c3);
+      __syncthreads();
+      if (wid == 0) {
+        int4 t = make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int4 u = pc[q][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        cpc[lane] = t;
+      }
+      cluster.sync();
+      c0 = c1 = c2 = c3 = 0;
+#pragma unroll
+      for (int q = 0; q < kPoolCluster; ++q) {
+        const int4 t = cluster.map_shared_rank(&cpc[0], q)[lane];
+        c0 += t.x; c1 += t.y; c2 += t.z; c3 += t.w;
+      }
+      cluster.sync();                              // peers may exit only after everyone has read
+    }
+    wgt = make_float4(c0 ? g.x / (float)c0 : 0.f, c1 ? g.y / (float)c1 : 0.f,
+                      c2 ? g.z / (float)c2 : 0.f, c3 ? g.w / (float)c3 : 0.f);
+  }
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int rc = sub * 32; rc < v.red; rc += kStep) {
+    const unsigned char m = rc + lane < v.red ? __ldg(mp + (rc + lane) * pstep) : (unsigned char)0;
+    const unsigned bits = __ballot_sync(0xffffffffu, m != 0);
+    const int nr = min(32, v.red - rc);
+    const float4* dq = dp + rc * dstep;
+    float4* gq = gp + rc * dstep;
+    if (kExt) {
+      for (int r0 = 0; r0 < nr; r0 += 8) {
+        float4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (r0 + u < nr && ((bits >> (r0 + u)) & 1u)) x[u] = __ldg(dq + (r0 + u) * dstep);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (r0 + u < nr) {
+            float4 val = zero;
+            if ((bits >> (r0 + u)) & 1u)
+              val = make_float4(x[u].x == ov.x ? wgt.x : 0.f, x[u].y == ov.y ? wgt.y : 0.f,
+                                x[u].z == ov.z ? wgt.z : 0.f, x[u].w == ov.w ? wgt.w : 0.f);
+            gq[(r0 + u) * dstep] = val;
+          }
+      }
+    } else {
+      for (int r = 0; r < nr; ++r) gq[r * dstep] = ((bits >> r) & 1u) ? wgt : zero;
+    }
+  }
+}
+
 template <int AGGR>
 __global__ void masked_pool_bwd_kernel(const float4* __restrict__ data,
                                        const unsigned char* __restrict__ mask,
@@ -178,6 +387,23 @@ __global__ void masked_pool_bwd_kernel(const float4* __restrict__ data,
   }
 }
 
+// SPLIT kernels: one cluster of kPoolCluster CTAs per output row
+template <typename... KArgs, typename... Args>
+static void pool_cluster_launch(void (*kern)(KArgs...), long long rows, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(rows * kPoolCluster));
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kPoolCluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static int pool_view(int64_t b, int64_t n1, int64_t n2, int64_t dense, int red_dims, PoolView& v) {
   if (dense % 4) return arg_error("masked_pool: dense % 4 != 0");
   v.c4 = (int)(dense / 4);
@@ -194,6 +420,15 @@ __global__ void masked_fill_kernel(const float* __restrict__ data,
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * dense) return;
   out[idx] = mask[idx / dense] ? data[idx] : value;
+}
+
+// dense % 4 == 0, 16-byte aligned: 128 bits per thread, masked-out rows are not read
+__global__ void masked_fill4_kernel(const float4* __restrict__ data,
+                                    const unsigned char* __restrict__ mask, long long total4,
+                                    int c4, float value, float4* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  out[idx] = __ldg(mask + idx / c4) ? __ldg(data + idx) : make_float4(value, value, value, value);
 }
 
 int mamamm_tc_launch(const float* A, int trans_a, const float* B, int trans_b,
@@ -278,7 +513,17 @@ extern "C" int pgh_masked_pool_f32(const float* data, const uint8_t* mask, int64
   if (total <= 0) return 0;
   cudaStream_t s = as_stream(stream);
   const unsigned nb = blocks_for(total, 256);
-#define PGH_POOL(AG) masked_pool_kernel<AG><<<nb, 256, 0, s>>>((const float4*)data, mask, v, (float4*)out, out_mask, total)
+  const bool warp_path = v.c4 % 32 == 0;
+  const long long warps = v.outer * v.inner * (v.c4 / 32);
+  const unsigned nbw = blocks_for(warps * 32, 256);
+  // few output rows with a long reduced extent: one CTA of 8 warps per output row
+  const bool split = v.red >= 128 && warps < 8LL * kSMs;
+#define PGH_POOL(AG)                                                                                         \
+  do {                                                                                                       \
+    if (warp_path && split) pool_cluster_launch(masked_pool_warp_kernel<AG, true>, warps, s, (const float4*)data, mask, v, (float4*)out, out_mask, warps); \
+    else if (warp_path) masked_pool_warp_kernel<AG, false><<<nbw, 256, 0, s>>>((const float4*)data, mask, v, (float4*)out, out_mask, warps); \
+    else masked_pool_kernel<AG><<<nb, 256, 0, s>>>((const float4*)data, mask, v, (float4*)out, out_mask, total);   \
+  } while (0)
   switch (aggr) {
     case PGH_SUM: PGH_POOL(PGH_SUM); break;
     case PGH_MEAN: PGH_POOL(PGH_MEAN); break;
@@ -305,7 +550,17 @@ extern "C" int pgh_masked_pool_bwd_f32(const float* data, const uint8_t* mask, c
   if (total <= 0) return 0;
   cudaStream_t s = as_stream(stream);
   const unsigned nb = blocks_for(total, 256);
-#define PGH_POOLB(AG) masked_pool_bwd_kernel<AG><<<nb, 256, 0, s>>>((const float4*)data, mask, (const float4*)out, (const float4*)g_out, v, (float4*)g_data, total)
+  const bool warp_path = v.c4 % 32 == 0;
+  const long long warps = v.outer * v.inner * (v.c4 / 32);
+  const unsigned nbw = blocks_for(warps * 32, 256);
+  // few output rows with a long reduced extent: one CTA of 8 warps per output row
+  const bool split = v.red >= 128 && warps < 8LL * kSMs;
+#define PGH_POOLB(AG)                                                                                        \
+  do {                                                                                                       \
+    if (warp_path && split) pool_cluster_launch(masked_pool_bwd_warp_kernel<AG, true>, warps, s, (const float4*)data, mask, (const float4*)out, (const float4*)g_out, v, (float4*)g_data, warps); \
+    else if (warp_path) masked_pool_bwd_warp_kernel<AG, false><<<nbw, 256, 0, s>>>((const float4*)data, mask, (const float4*)out, (const float4*)g_out, v, (float4*)g_data, warps); \
+    else masked_pool_bwd_kernel<AG><<<nb, 256, 0, s>>>((const float4*)data, mask, (const float4*)out, (const float4*)g_out, v, (float4*)g_data, total); \
+  } while (0)
   switch (aggr) {
     case PGH_SUM: PGH_POOLB(PGH_SUM); break;
     case PGH_MEAN: PGH_POOLB(PGH_MEAN); break;
@@ -321,7 +576,11 @@ extern "C" int pgh_masked_fill_f32(const float* data, const uint8_t* mask, int64
                                    int64_t dense, float value, float* out, void* stream) {
   if (!data || !mask || !out) return arg_error("masked_fill: null pointer");
   if (rows * dense <= 0) return 0;
-  masked_fill_kernel<<<blocks_for(rows * dense, 256), 256, 0, as_stream(stream)>>>(
-      data, mask, rows, (int)dense, value, out);
+  if (dense % 4 == 0 && !((reinterpret_cast<uintptr_t>(data) | reinterpret_cast<uintptr_t>(out)) & 15))
+    masked_fill4_kernel<<<blocks_for(rows * dense / 4, 256), 256, 0, as_stream(stream)>>>(
+        (const float4*)data, mask, rows * dense / 4, (int)(dense / 4), value, (float4*)out);
+  else
+    masked_fill_kernel<<<blocks_for(rows * dense, 256), 256, 0, as_stream(stream)>>>(
+        data, mask, rows, (int)dense, value, out);
   return check_launch("masked_fill");
 }

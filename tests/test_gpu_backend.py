@@ -453,9 +453,11 @@ def test_mamamm_forward_backward(B, monkeypatch, d1, d2, algo, tol):
 
 @pytest.mark.parametrize("aggr", AGGRS)
 @pytest.mark.parametrize("dims", [(1,), (2,), (1, 2)])
-def test_masked_pool_forward_backward(B, aggr, dims):
+@pytest.mark.parametrize("b,n,d", [(4, 9, 24), (3, 37, 128), (2, 10, 256)])
+def test_masked_pool_forward_backward(B, aggr, dims, b, n, d):
+    """d = 24: thread-per-4-channels kernels; d % 128 == 0: warp-cooperative kernels (mask bits by
+    ballot), n = 37 walks more than one 32-position chunk of the reduced extent."""
     gen = torch.Generator().manual_seed(5)
-    b, n, d = 4, 9, 24
     mask = torch.rand((b, n, n), generator=gen) < 0.6
     mask[0] = False                                          # a fully masked graph
     data = torch.randn((b, n, n, d), generator=gen)
