@@ -443,7 +443,8 @@ def roofline_spspmm(dd, hidden, device, peaks, key="X___X___1___A___0"):
 
 
 def roofline_mamamm(dd, hidden, device, peaks):
-    """The dense 2-FWL contraction (PPGNConv DD) alone: tcgen05 TF32 pipeline kernel."""
+    """The dense 2-FWL contraction (PPGNConv DD) alone: the default kernel (algo 4, exact fp32 from
+    a TMA-fed shared-memory ring) and, beside it, the tcgen05 TF32 pipeline (algo 2)."""
     from pygho_b200.backend.Mamamm import default_algo, mamamm
     from pygho_b200 import MaskedTensor
     X = dd["X"]
@@ -465,17 +466,33 @@ def roofline_mamamm(dd, hidden, device, peaks):
     for i in range(3):
         launch(i)
     us, timing = _time_launches(launch, 5 * nsets, device)
+    import os
+    keep = os.environ.get("PYGHO_B200_MAMAMM_ALGO")
+    os.environ["PYGHO_B200_MAMAMM_ALGO"] = "2"
+    try:
+        for i in range(3):
+            launch(i)
+        us_tc, _ = _time_launches(launch, 5 * nsets, device)
+    finally:
+        if keep is None:
+            del os.environ["PYGHO_B200_MAMAMM_ALGO"]
+        else:
+            os.environ["PYGHO_B200_MAMAMM_ALGO"] = keep
     sizes = mask[:, :, 0].sum(1).double()
     alg_bytes = 4 * hidden * b * 3 * n * n + b * n * n            # SURVEY 8d (padded tensors)
     moved = int(4 * hidden * float((2 * sizes * sizes).sum() + b * n * n) + b * n * n)
     useful = 2.0 * hidden * float((sizes ** 3).sum())
-    return _roofline_obj(f"mamamm_tc_pipe_kernel (algo {default_algo()}; tcgen05 kind::tf32, TMEM accumulators)",
+    names = {4: "mamamm_smem_kernel (algo 4; exact fp32 FMAs from a TMA-fed shared-memory ring, largest graph first)",
+             2: "mamamm_tc_pipe_kernel (algo 2; tcgen05 kind::tf32, TMEM accumulators)"}
+    return _roofline_obj(names.get(default_algo(), f"mamamm algo {default_algo()}"),
                          alg_bytes, us, timing, peaks, "mamamm",
                          {"graphs": b, "padded_n": n, "operand_sets": nsets, "l2_bytes": l2,
                           "moved_bytes_valid_extents": moved,
                           "moved_frac_of_peak": moved / (us * 1e-6) / 1e9 / (peaks.get("hbm_gbs") or 6650.0),
                           "useful_tflops": useful / (us * 1e-6) / 1e12,
-                          "tensor_pipe_util_vs_tf32_dense_1100": useful / (us * 1e-6) / 1e12 / 1100.0})
+                          "tcgen05_algo2_us_per_launch": us_tc,
+                          "tcgen05_algo2_useful_tflops": useful / (us_tc * 1e-6) / 1e12,
+                          "tcgen05_algo2_tensor_pipe_util_vs_tf32_dense_1100": useful / (us_tc * 1e-6) / 1e12 / 1100.0})
 
 
 def roofline_pool(dd, hidden, device, peaks, three_d):

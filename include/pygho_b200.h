@@ -212,10 +212,15 @@ int pgh_check_sorted_i64(const int64_t* key, int64_t n, int strict, int32_t* inf
  * algo 0 = CUDA-core tiled kernel (exact fp32), 1 = tcgen05 TF32 tensor-core kernel with one
  * CTA per (graph, 8-channel slab), 2 = the same tiles and MMAs in a persistent
  * warp-specialised pipeline (same bits as 1; falls back to 1 when two tile stages do not fit
- * in shared memory).                                                                      */
+ * in shared memory), 4 = exact fp32 FMAs from a TMA-fed shared-memory ring (same bits as 0;
+ * shapes its ring cannot hold run on 0).
+ * order (optional, (b) int32, a permutation of 0..b-1) = the order in which algo 4's work queue
+ * hands out the graphs; largest first keeps the tail of the launch short.  Never changes the
+ * result.                                                                                 */
 int pgh_mamamm_f32(const float* A, int trans_a, const float* B, int trans_b,
-                   const uint8_t* mask, const int32_t* ext, int64_t b, int64_t n_i, int64_t n_j,
-                   int64_t n_k, int64_t dense, int algo, float* out, void* stream);
+                   const uint8_t* mask, const int32_t* ext, const int32_t* order, int64_t b,
+                   int64_t n_i, int64_t n_j, int64_t n_k, int64_t dense, int algo, float* out,
+                   void* stream);
 /* ext2[g] = (1 + last valid row, 1 + last valid column) of a (b, n1, n2) mask */
 int pgh_mask_extents(const uint8_t* mask, int64_t b, int64_t n1, int64_t n2, int32_t* ext2,
                      void* stream);

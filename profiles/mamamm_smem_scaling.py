@@ -14,15 +14,15 @@ dev = torch.device("cuda", 0)
 mm = torch.ops.pygho_b200.mamamm
 
 
-def graph_time(A, B, mask, e, algo, dbg=0, reps=12):
+def graph_time(A, B, mask, e, algo, dbg=0, reps=12, order=None):
     _lib.load().pgh_set_tuning(7, dbg)
     for i in range(3):
-        mm(A[i], False, B[i], False, mask, e, algo)
+        mm(A[i], False, B[i], False, mask, e, algo, order)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for i in range(reps):
-            mm(A[i % 3], False, B[i % 3], False, mask, e, algo)
+            mm(A[i % 3], False, B[i % 3], False, mask, e, algo, order)
     g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -46,8 +46,10 @@ for b in (1, 8, 32, 64, 128, 256, 512):
     ext = torch.stack((sizes, sizes, sizes), 1).to(torch.int32).to(dev)
     valid = 4 * d * float((2 * sizes.double() ** 2).sum() + b * n * n) + b * n * n
     row = [f"b={b:4d} ({valid / 1e6:6.1f} MB)"]
-    for algo, dbg, name in ((2, 0, "algo 2"), (4, 0, "algo 4"), (4, 15, "skeleton"), (4, 13, "loads"), (4, 14, "FMAs"),
-                            (4, 1, "no FMAs")):
-        row.append(f"{name} {graph_time(A, B, mask, ext, algo, dbg):7.1f}")
+    lpt = torch.argsort(sizes, descending=True, stable=True).to(torch.int32).to(dev)
+    row.append(f"algo 2 {graph_time(A, B, mask, ext, 2):6.1f}")
+    row.append(f"algo 4 {graph_time(A, B, mask, ext, 4):6.1f}")
+    for dbg, name in ((0, "LPT"), (4, "no epi"), (1, "no FMA"), (13, "loads"), (14, "FMAs"), (15, "skel")):
+        row.append(f"{name} {graph_time(A, B, mask, ext, 4, dbg, order=lpt):6.1f}")
     print("  ".join(row), flush=True)
     del A, B

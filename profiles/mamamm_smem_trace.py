@@ -56,7 +56,8 @@ K = 4096
 buf = torch.zeros(K, dtype=torch.int64, device=dev)
 _lib.load().pgh_set_tuning(7, int(os.environ.get("TRACE_DBG", "0")))
 _lib.call("pgh_debug_trace", buf.data_ptr(), buf.numel())
-mm(sets[0][0], False, sets[0][1], False, mask, ext, 4)
+mm(sets[0][0], False, sets[0][1], False, mask, ext, 4,
+   torch.argsort(sizes, descending=True, stable=True).to(torch.int32).to(dev) if os.environ.get('TRACE_LPT') else None)
 torch.cuda.synchronize()
 _lib.call("pgh_debug_trace", None, 0)
 _lib.load().pgh_set_tuning(7, 0)

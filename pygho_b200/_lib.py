@@ -57,7 +57,7 @@ SIGNATURES = {
     "pgh_gather_i32": (_i, [_p, _p, _i64, _p, _p]),
     "pgh_gather_i64_as_i32": (_i, [_p, _p, _i64, _p, _p]),
     "pgh_check_sorted_i64": (_i, [_p, _i64, _i, _p, _p]),
-    "pgh_mamamm_f32": (_i, [_p, _i, _p, _i, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _p, _p]),
+    "pgh_mamamm_f32": (_i, [_p, _i, _p, _i, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i, _p, _p]),
     "pgh_mask_extents": (_i, [_p, _i64, _i64, _i64, _p, _p]),
     "pgh_masked_pool_f32": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i, _i, _p, _p, _p]),
     "pgh_masked_pool_bwd_f32": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i, _p, _p]),

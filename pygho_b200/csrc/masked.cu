@@ -467,14 +467,14 @@ extern "C" int pgh_mask_extents(const uint8_t* mask, int64_t b, int64_t n1, int6
 
 namespace pgh {
 int mamamm_smem_launch(const float* A, int trans_a, const float* B, int trans_b,
-                       const unsigned char* mask, const int* ext, int64_t b, int64_t n_i, int64_t n_j,
-                       int64_t n_k, int64_t dense, float* out, cudaStream_t s);
+                       const unsigned char* mask, const int* ext, const int* order, int64_t b,
+                       int64_t n_i, int64_t n_j, int64_t n_k, int64_t dense, float* out, cudaStream_t s);
 }
 
 extern "C" int pgh_mamamm_f32(const float* A, int trans_a, const float* B, int trans_b,
-                              const uint8_t* mask, const int32_t* ext, int64_t b, int64_t n_i,
-                              int64_t n_j, int64_t n_k, int64_t dense, int algo, float* out,
-                              void* stream) {
+                              const uint8_t* mask, const int32_t* ext, const int32_t* order,
+                              int64_t b, int64_t n_i, int64_t n_j, int64_t n_k, int64_t dense,
+                              int algo, float* out, void* stream) {
   if (!A || !B || !mask || !out) return arg_error("mamamm: null pointer");
   if (b < 0 || n_i <= 0 || n_j <= 0 || n_k <= 0 || dense <= 0) return arg_error("mamamm: sizes");
   if (b == 0) return 0;
@@ -482,7 +482,7 @@ extern "C" int pgh_mamamm_f32(const float* A, int trans_a, const float* B, int t
   // 4 = exact fp32 from a TMA-fed shared-memory ring (csrc/mamamm_smem.cu); shapes it does not
   // take (dense % 16, more than 512 columns, a stage that does not fit twice) run on algo 0
   if (algo == 4) {
-    const int rc = mamamm_smem_launch(A, trans_a, B, trans_b, mask, ext, b, n_i, n_j, n_k, dense, out, s);
+    const int rc = mamamm_smem_launch(A, trans_a, B, trans_b, mask, ext, order, b, n_i, n_j, n_k, dense, out, s);
     if (rc >= 0) return rc;
     algo = 0;
   }

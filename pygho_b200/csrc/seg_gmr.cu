@@ -1076,7 +1076,7 @@ static int launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, con
 using namespace pgh;
 
 extern "C" const char* pgh_last_error(void) { return pgh::g_err; }
-extern "C" int pgh_abi_version(void) { return 2; }
+extern "C" int pgh_abi_version(void) { return 3; }
 
 extern "C" int pgh_set_tuning(int key, int value) {
   if (key < 0 || key >= 8) return arg_error("set_tuning: key");

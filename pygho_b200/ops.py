@@ -267,10 +267,10 @@ def _inv_count_fake(rowptr):
 
 # -------------------------------------------------------------------------- masked
 _LIB.define("mamamm(Tensor A, bool trans_a, Tensor B, bool trans_b, Tensor mask, Tensor? ext, "
-            "int algo) -> Tensor")
+            "int algo, Tensor? order=None) -> Tensor")
 
 
-def _mamamm_cuda(A, trans_a, B, trans_b, mask, ext, algo):
+def _mamamm_cuda(A, trans_a, B, trans_b, mask, ext, algo, order=None):
     A, B = _f32c(A), _f32c(B)
     mask = mask.contiguous()
     b = A.shape[0]
@@ -282,11 +282,14 @@ def _mamamm_cuda(A, trans_a, B, trans_b, mask, ext, algo):
         raise ValueError(f"mamamm: mask shape {tuple(mask.shape)} != {(b, n_i, n_k)}")
     if ext is not None and (ext.dtype != torch.int32 or tuple(ext.shape) != (b, 3)):
         raise ValueError("mamamm: ext must be an int32 tensor of shape (batch, 3)")
+    if order is not None and (order.dtype != torch.int32 or tuple(order.shape) != (b,)):
+        raise ValueError("mamamm: order must be an int32 permutation of shape (batch,)")
     dense = A.shape[3]
     out = torch.empty((b, n_i, n_k, dense), dtype=torch.float32, device=A.device)
     if out.numel():
         call("pgh_mamamm_f32", ptr(A), int(trans_a), ptr(B), int(trans_b),
              ptr(mask.view(torch.uint8)), ptr(ext.contiguous() if ext is not None else None),
+             ptr(order.contiguous() if order is not None else None),
              b, n_i, n_j, n_k, dense, algo, ptr(out), stream_ptr(A.device))
         _lib.count_launch()
     return out
@@ -296,7 +299,7 @@ _LIB.impl("mamamm", _mamamm_cuda, "CUDA")
 
 
 @torch.library.register_fake("pygho_b200::mamamm")
-def _mamamm_fake(A, trans_a, B, trans_b, mask, ext, algo):
+def _mamamm_fake(A, trans_a, B, trans_b, mask, ext, algo, order=None):
     n_i = A.shape[2] if trans_a else A.shape[1]
     n_k = B.shape[1] if trans_b else B.shape[2]
     return A.new_empty((A.shape[0], n_i, n_k, A.shape[3]))
@@ -812,9 +815,10 @@ _EXT3_CACHE = {}
 def _ext3(eX: Optional[Tensor], tx: bool, eY: Optional[Tensor], ty: bool, eM: Optional[Tensor],
           shape) -> Optional[Tensor]:
     """Per-graph (n_i, n_j, n_k) of X' @ Y' masked by M from the (rows, cols) extents of the
-    stored operands; ``None`` extents mean "full"."""
+    stored operands, and the graphs in descending order of their work (the queue order of the
+    algo-4 kernel); ``None`` extents mean "full" -> (None, None)."""
     if eX is None and eY is None and eM is None:
-        return None
+        return None, None
     key = (id(eX), tx, id(eY), ty, id(eM), shape)
     hit = _EXT3_CACHE.get(key)
     if hit is not None:
@@ -832,10 +836,12 @@ def _ext3(eX: Optional[Tensor], tx: bool, eY: Optional[Tensor], ty: bool, eM: Op
     rM, cM = oriented(eM, False, n_i, n_k)
     ext = torch.stack((torch.minimum(rX, rM), torch.minimum(cX, rY), torch.minimum(cY, cM)),
                       dim=1).contiguous()
+    work = ext[:, 0].to(torch.int64) * ext[:, 1] * ext[:, 2]
+    order = torch.argsort(work, descending=True, stable=True).to(torch.int32)
     if len(_EXT3_CACHE) > 64:
         _EXT3_CACHE.clear()
-    _EXT3_CACHE[key] = (ext, eX, eY, eM)      # keep the keyed tensors alive
-    return ext
+    _EXT3_CACHE[key] = ((ext, order), eX, eY, eM)      # keep the keyed tensors alive
+    return ext, order
 
 
 def mamamm_algo_for(algo: int, n_i: int, n_j: int, n_k: int, dense: int) -> int:
@@ -855,7 +861,8 @@ def _mm(X, tx, eX, Y, ty, eY, mask, eM, algo):
     n_i, n_j = (X.shape[2], X.shape[1]) if tx else (X.shape[1], X.shape[2])
     n_k = Y.shape[1] if ty else Y.shape[2]
     algo = mamamm_algo_for(algo, n_i, n_j, n_k, X.shape[3])
-    return _ops.mamamm(X, tx, Y, ty, mask, _ext3(eX, tx, eY, ty, eM, (b, n_i, n_j, n_k)), algo)
+    ext, order = _ext3(eX, tx, eY, ty, eM, (b, n_i, n_j, n_k))
+    return _ops.mamamm(X, tx, Y, ty, mask, ext, algo, order)
 
 
 class MaMaMM(torch.autograd.Function):

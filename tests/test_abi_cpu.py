@@ -32,7 +32,7 @@ def test_binding_table_matches_header():
     from pygho_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _declared()
     lib = _lib.load()
-    assert lib.pgh_abi_version() == 2
+    assert lib.pgh_abi_version() == 3
     assert lib.pgh_last_error() is not None
 
 

@@ -538,6 +538,11 @@ def test_mamamm_smem_ring_is_bit_identical_to_fp32_kernel(shape, ta, tb):
         got = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, holes, e, 4)
         assert torch.equal(got, ref), float((got - ref).abs().max())
         assert float(got[~holes].abs().max()) == 0.0
+    # the queue order (largest graph first, or any permutation) never changes the result
+    lpt = torch.argsort((si * sj * sk), descending=True, stable=True).to(torch.int32).to(DEV)
+    for order in (lpt, torch.randperm(b, generator=gen).to(torch.int32).to(DEV)):
+        got = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, holes, ext, 4, order)
+        assert torch.equal(got, ref), float((got - ref).abs().max())
     # back-to-back launches re-arm their work queues (64 rotating, self-resetting)
     for _ in range(70):
         got = torch.ops.pygho_b200.mamamm(A, ta, Bm, tb, holes, ext, 4)
