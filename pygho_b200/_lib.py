@@ -107,6 +107,8 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get("PYGHO_B200_NO_PDL"):
+            lib.pgh_set_tuning(8, 0)     # launch every kernel fully serialised (A/B measurements)
         _lib = lib
     return _lib
 

@@ -41,6 +41,36 @@ inline unsigned blocks_for(int64_t n, int per_block) {
 
 constexpr int kSMs = 148;  // B200
 
-extern int g_tune[8];  // run-time tuning knobs (pgh_set_tuning), defined in seg_gmr.cu
+extern int g_tune[16];  // run-time tuning knobs (pgh_set_tuning), defined in seg_gmr.cu
+
+// Programmatic dependent launch (key 8, on by default): the grid may be scheduled while its
+// predecessor in the stream is still draining, so that its launch latency and ramp-up hide under
+// the predecessor's tail.  EVERY kernel launched through launch_pdl starts with pdl_enter():
+// griddepcontrol.wait returns once the predecessor grids have completed and their writes are
+// visible, i.e. before the kernel's first access to global memory; launch_dependents lets the
+// successor be scheduled as soon as all CTAs of this grid are running.  Kernels of other libraries
+// (cuBLAS, ATen) in between serialise as usual.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_tune[8] ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
 
 }  // namespace pgh

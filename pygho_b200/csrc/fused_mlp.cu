@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_stats_kernel(const float* __
                                 float momentum, float* __restrict__ mean, float* __restrict__ rstd,
                                 float* __restrict__ running_mean, float* __restrict__ running_var,
                                 float* __restrict__ local_out, long long* __restrict__ nbt) {
+  pdl_enter();
   extern __shared__ float4 sm[];
   const long long rows = valid_rows(rows_cap, rows_dev);
   const int tx = threadIdx.x, c4 = blockDim.x, ty_n = blockDim.y;
@@ -159,6 +160,7 @@ __global__ void bn_sync_finalize_kernel(const float* __restrict__ gathered, int 
                                         float eps, float momentum, float* __restrict__ mean,
                                         float* __restrict__ rstd, float* __restrict__ running_mean,
                                         float* __restrict__ running_var, float* __restrict__ inv_n) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double n = 0.0, m = 0.0, m2 = 0.0;
@@ -190,6 +192,7 @@ __global__ void bn_act_fwd_kernel(const float4* __restrict__ y, const float4* __
                                   const float4* __restrict__ beta, long long n4_cap, int c4,
                                   const int* __restrict__ rows_dev,
                                   const float4* __restrict__ residual, float4* __restrict__ z) {
+  pdl_enter();
   const long long n4 = valid_rows(n4_cap / c4, rows_dev) * c4;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UN) {
@@ -233,6 +236,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(const 
                                          int* __restrict__ tickets, float* __restrict__ sums,
                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                          int accumulate) {
+  pdl_enter();
   extern __shared__ float4 sm[];
   const long long rows = valid_rows(rows_cap, rows_dev);
   const int tx = threadIdx.x, c4 = blockDim.x, ty_n = blockDim.y;
@@ -295,6 +299,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(const f
                                         float* __restrict__ part, float* __restrict__ part2,
                                         int blocks, int grp, int ngroups, int* __restrict__ tickets,
                                         float* __restrict__ dbias, int accumulate) {
+  pdl_enter();
   extern __shared__ float4 sm[];
   const long long rows = valid_rows(rows_cap, rows_dev);
   const int tx = threadIdx.x, c4 = blockDim.x, ty_n = blockDim.y;
@@ -360,6 +365,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(const f
 constexpr int kSlabLanes = 8, kSlabMax = 8;    // <= 64 slabs per call
 __global__ void sum_slabs_kernel(const float4* __restrict__ part, int slabs, long long n4,
                                  float4* __restrict__ out, int accumulate) {
+  pdl_enter();
   __shared__ float4 sm[kSlabLanes][32];
   const long long e = (long long)blockIdx.x * 32 + threadIdx.x;
   const int y = threadIdx.y;
@@ -396,6 +402,7 @@ __global__ void adamw_flat_kernel(float4* __restrict__ p, const float4* __restri
                                   float4* __restrict__ m, float4* __restrict__ v, long long n4,
                                   const float* __restrict__ step, float lr, float b1, float b2,
                                   float eps, float wd, float grad_scale) {
+  pdl_enter();
   const float t = __ldg(step) + 1.f;
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
@@ -445,7 +452,7 @@ extern "C" int pgh_bn_stats_f32(const float* y, int64_t rows, int64_t C, const i
   if ((reinterpret_cast<uintptr_t>(y) & 15)) return arg_error("bn_stats: y must be 16-byte aligned");
   const BnGeom g = bn_geom(rows, C);
   if (ws_bytes < pgh_bn_ws_bytes(rows, C)) return arg_error("bn_stats: workspace too small");
-  bn_stats_kernel<<<g.blocks, dim3(g.c4, g.ty), g.smem, as_stream(stream)>>>(
+  launch_pdl(bn_stats_kernel, dim3(g.blocks), dim3(dim3(g.c4, g.ty)), g.smem, as_stream(stream), 
       y, rows, (int)C, rows_dev, g.rows_per_block, reinterpret_cast<float*>(ws), bn_part2(ws, g, C),
       g.blocks, g.grp, g.ngroups, tickets, eps, momentum, mean, rstd, running_mean, running_var,
       local_out, reinterpret_cast<long long*>(num_batches_tracked));
@@ -464,7 +471,7 @@ extern "C" int pgh_adamw_flat_f32(float* param, const float* grad, float* exp_av
   const long long n4 = n / 4;
   long long nb = (n4 + 255) / 256;
   if (nb > kSMs * 8) nb = kSMs * 8;
-  adamw_flat_kernel<<<(unsigned)nb, 256, 0, as_stream(stream)>>>(
+  launch_pdl(adamw_flat_kernel, dim3((unsigned)nb), dim3(256), 0, as_stream(stream), 
       reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad),
       reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq), n4, step, lr, beta1,
       beta2, eps, weight_decay, grad_scale);
@@ -479,7 +486,7 @@ extern "C" int pgh_sum_slabs_f32(const float* part, int64_t slabs, int64_t n, fl
     return arg_error("sum_slabs: tensors must be 16-byte aligned");
   if (n == 0) return 0;
   const long long n4 = n / 4;
-  sum_slabs_kernel<<<blocks_for(n4, 32), dim3(32, kSlabLanes), 0, as_stream(stream)>>>(
+  launch_pdl(sum_slabs_kernel, dim3(blocks_for(n4, 32)), dim3(dim3(32, kSlabLanes)), 0, as_stream(stream), 
       reinterpret_cast<const float4*>(part), (int)slabs, n4, reinterpret_cast<float4*>(out), accumulate);
   return check_launch("sum_slabs");
 }
@@ -489,7 +496,7 @@ extern "C" int pgh_bn_sync_finalize_f32(const float* gathered, int64_t world, in
                                         float* running_mean, float* running_var, float* inv_n,
                                         void* stream) {
   if (!gathered || !mean || !rstd || world < 1 || C < 1) return arg_error("bn_sync_finalize: arguments");
-  bn_sync_finalize_kernel<<<blocks_for(C, 128), 128, 0, as_stream(stream)>>>(
+  launch_pdl(bn_sync_finalize_kernel, dim3(blocks_for(C, 128)), dim3(128), 0, as_stream(stream), 
       gathered, (int)world, (int)C, eps, momentum, mean, rstd, running_mean, running_var, inv_n);
   return check_launch("bn_sync_finalize");
 }
@@ -507,7 +514,7 @@ extern "C" int pgh_bn_act_res_fwd_f32(const float* y, const float* mean, const f
   long long nb = (n4 + 255) / 256;
   if (nb > 148 * 16) nb = 148 * 16;
   cudaStream_t s = as_stream(stream);
-#define PGH_FWD_U(A, U) bn_act_fwd_kernel<A, U><<<(unsigned)nb, 256, 0, s>>>(                        \
+#define PGH_FWD_U(A, U) launch_pdl(bn_act_fwd_kernel<A, U>, dim3((unsigned)nb), dim3(256), 0, s,                         \
       (const float4*)y, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,             \
       (const float4*)beta, n4, (int)(C / 4), rows_dev, (const float4*)residual, (float4*)z)
 #define PGH_FWD(A)                                                                                   \
@@ -537,7 +544,7 @@ extern "C" int pgh_bn_act_bwd_reduce_f32(const float* dz, const float* y, const 
   cudaStream_t s = as_stream(stream);
   const dim3 blk(g.c4, g.ty);
 #define PGH_RED_U(A, U)                                                                              \
-  bn_act_bwd_reduce_kernel<A, U><<<g.blocks, blk, g.smem, s>>>(                                      \
+  launch_pdl(bn_act_bwd_reduce_kernel<A, U>, dim3(g.blocks), dim3(blk), g.smem, s,                                       \
       dz, y, mean, rstd, gamma, beta, rows, (int)C, rows_dev, g.rows_per_block,                      \
       reinterpret_cast<float*>(ws), bn_part2(ws, g, C), g.blocks, g.grp, g.ngroups, tickets, sums,   \
       dgamma, dbeta, accumulate)
@@ -568,7 +575,7 @@ extern "C" int pgh_bn_act_bwd_apply_f32(const float* dz, const float* y, const f
   cudaStream_t s = as_stream(stream);
   const dim3 blk(g.c4, g.ty);
 #define PGH_APP_U(A, U)                                                                              \
-  bn_act_bwd_apply_kernel<A, U><<<g.blocks, blk, g.smem, s>>>(                                       \
+  launch_pdl(bn_act_bwd_apply_kernel<A, U>, dim3(g.blocks), dim3(blk), g.smem, s,                                        \
       dz, y, mean, rstd, gamma, beta, sums, inv_n, rows, (int)C, rows_dev, g.rows_per_block, dy,     \
       reinterpret_cast<float*>(ws), bn_part2(ws, g, C), g.blocks, g.grp, g.ngroups, tickets, dbias,  \
       accumulate)

@@ -185,7 +185,9 @@ linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   __shared__ double s_fin[2 * kLsBN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (ls_smem_u32(ls_smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B: 1024-B aligned
-  const long long rows_valid = rows_dev ? min(M, (long long)max(__ldg(rows_dev), 0)) : M;
+  // programmatic dependent launch: barrier set-up and the TMEM allocation below overlap the
+  // predecessor's tail; global memory is first touched after griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int m_tiles = (int)((M + kLsBM - 1) / kLsBM);
   const int kblocks = K / kLsBK;
 
@@ -211,6 +213,8 @@ linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_holder;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const long long rows_valid = rows_dev ? min(M, (long long)max(__ldg(rows_dev), 0)) : M;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -408,7 +412,7 @@ static int ls_launch(const CUtensorMap& map_x, const CUtensorMap& map_w, const f
   float* part = reinterpret_cast<float*>(ws);
   float* part2 = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) +
                                           ((size_t)g.grid * 2 * Cfg::N * sizeof(float) + 255) / 256 * 256);
-  linear_stats_kernel<NT><<<g.grid, kLsThreads, Cfg::kSmemBytes, s>>>(
+  launch_pdl(linear_stats_kernel<NT>, dim3(g.grid), dim3(kLsThreads), Cfg::kSmemBytes, s,
       map_x, map_w, bias, M, (int)K, rows_dev, y, part, part2, g.grp, g.ngroups, tickets, eps, momentum,
       mean, rstd, running_mean, running_var, local_out, reinterpret_cast<long long*>(nbt));
   return check_launch("linear_stats");

@@ -88,6 +88,7 @@ seg_gmr_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
                const int* __restrict__ d, const int* __restrict__ rowptr, long long n_rows,
                int dense, int lda, int ldb, int ldo, int lpr, int accum,
                float* __restrict__ out) {
+  pdl_enter();
   const Lane L = lane_setup(rowptr, n_rows, lpr);
   const int colstep = lpr * VEC;
   for (int col0 = 0; col0 < dense; col0 += colstep) {
@@ -178,6 +179,7 @@ seg_gmr_stream_kernel(const float* __restrict__ a_val, const int* __restrict__ c
                       const int* __restrict__ d, const int* __restrict__ rowptr,
                       long long n_rows, int dense, int lda, int ldb, int ldo, int rw, int accum,
                       float* __restrict__ out) {
+  pdl_enter();
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -298,6 +300,7 @@ seg_gmr_lean_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
                     const float* __restrict__ acc_src2, int lds2,
                     const float* __restrict__ copy_src, int ldcs, float* __restrict__ copy_dst,
                     int ldcd, float* __restrict__ out) {
+  pdl_enter();
   constexpr unsigned kFull = 0xffffffffu;
   constexpr bool kLen = (AGGR != PGH_SUM);          // row lengths matter (mean, empty max/min rows)
   const int lane = threadIdx.x & 31;
@@ -477,6 +480,7 @@ seg_gmr_ring_kernel(const float* __restrict__ a_val, const int* __restrict__ c,
                     const int* __restrict__ d, const int* __restrict__ rowptr,
                     long long n_rows, int dense, int lda, int ldb, int ldo, int rw, int accum,
                     float* __restrict__ out) {
+  pdl_enter();
   static_assert(NS % U == 0 && 32 % U == 0 && NS <= 32, "ring geometry");
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int OPS = HAS_B ? 2 : 1;
@@ -904,7 +908,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // run-time tuning knobs (pgh_set_tuning): [0] seg_gmr variant (-1 = built-in choice),
 // [1] ring kernel: target plan entries per warp, [6] profiling: no row stores
 // [2..5] fused BN kernels (fused_mlp.cu)
-int g_tune[8] = {-1, 16, 0, 0, 0, 0, 0, 0};
+int g_tune[16] = {-1, 16, 0, 0, 0, 0, 0, 0, /* [8] programmatic dependent launch */ 1, 0, 0, 0, 0, 0, 0, 0};
 
 template <int AGGR, bool HAS_B, int NS, int U, int WARPS>
 static void launch_ring_t(cudaStream_t s, const float* a_val, const int* c, const float* a_scale,
@@ -918,7 +922,7 @@ static void launch_ring_t(cudaStream_t s, const float* a_val, const int* c, cons
     configured = true;
   }
   const unsigned nb = blocks_for(n_rows, WARPS * rw);
-  kern<<<nb, WARPS * 32, smem, s>>>(a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb,
+  launch_pdl(kern, dim3(nb), dim3(WARPS * 32), smem, s, a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb,
                                     ldo, rw, accum, out);
 }
 
@@ -979,7 +983,7 @@ static void launch_lean(cudaStream_t s, const float* a_val, const int* c, const 
   const int lds = x.add_src ? x.ld_add : ldo;
   const bool acc = accum || x.add_src;
 #define PGH_LEAN(B, S, A)                                                                      \
-  seg_gmr_lean_kernel<AGGR, B, S, A, U, MINB><<<nb, kThreads, 0, s>>>(                         \
+  launch_pdl(seg_gmr_lean_kernel<AGGR, B, S, A, U, MINB>, dim3(nb), dim3(kThreads), 0, s,                          \
       a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, acc_src, lds,     \
       x.add_src2, x.ld_add2, x.copy_src, x.ld_copy_src, x.copy_dst, x.ld_copy_dst, out)
   const int sel = (b_val ? 4 : 0) | (a_scale ? 2 : 0) | (acc ? 1 : 0);
@@ -1044,29 +1048,29 @@ static int launch_gmr(const Geometry& g, cudaStream_t s, const float* a_val, con
     if (variant < 0) variant = (n_entries > 6 * n_rows) ? 3 : 2;
     if (b_val) {
       if (variant == 1)
-        seg_gmr_stream_kernel<AGGR, true, 8, 1><<<nb, kThreads, 0, s>>>(
+        launch_pdl(seg_gmr_stream_kernel<AGGR, true, 8, 1>, dim3(nb), dim3(kThreads), 0, s, 
             a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
       else if (variant == 2)
-        seg_gmr_stream_kernel<AGGR, true, 4, 4><<<nb, kThreads, 0, s>>>(
+        launch_pdl(seg_gmr_stream_kernel<AGGR, true, 4, 4>, dim3(nb), dim3(kThreads), 0, s, 
             a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
       else if (variant == 3)
-        seg_gmr_stream_kernel<AGGR, true, 2, 5><<<nb, kThreads, 0, s>>>(
+        launch_pdl(seg_gmr_stream_kernel<AGGR, true, 2, 5>, dim3(nb), dim3(kThreads), 0, s, 
             a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
       else
-        seg_gmr_stream_kernel<AGGR, true, 4, 1><<<nb, kThreads, 0, s>>>(
+        launch_pdl(seg_gmr_stream_kernel<AGGR, true, 4, 1>, dim3(nb), dim3(kThreads), 0, s, 
             a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
     } else {
-      seg_gmr_stream_kernel<AGGR, false, 8, 1><<<nb, kThreads, 0, s>>>(
+      launch_pdl(seg_gmr_stream_kernel<AGGR, false, 8, 1>, dim3(nb), dim3(kThreads), 0, s, 
           a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, rw, accum, out);
     }
     return 0;
   }
   if (extra) return arg_error("seg_gmr_fused: needs dense % 128 == 0 and 16-byte aligned rows");
   if (b_val)
-    seg_gmr_kernel<AGGR, VEC, true><<<g.blocks, kThreads, 0, s>>>(
+    launch_pdl(seg_gmr_kernel<AGGR, VEC, true>, dim3(g.blocks), dim3(kThreads), 0, s, 
         a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, g.lpr, accum, out);
   else
-    seg_gmr_kernel<AGGR, VEC, false><<<g.blocks, kThreads, 0, s>>>(
+    launch_pdl(seg_gmr_kernel<AGGR, VEC, false>, dim3(g.blocks), dim3(kThreads), 0, s, 
         a_val, c, a_scale, b_val, d, rowptr, n_rows, dense, lda, ldb, ldo, g.lpr, accum, out);
   return 0;
 }
@@ -1079,7 +1083,7 @@ extern "C" const char* pgh_last_error(void) { return pgh::g_err; }
 extern "C" int pgh_abi_version(void) { return 3; }
 
 extern "C" int pgh_set_tuning(int key, int value) {
-  if (key < 0 || key >= 8) return arg_error("set_tuning: key");
+  if (key < 0 || key >= 16) return arg_error("set_tuning: key");
   pgh::g_tune[key] = value;
   return 0;
 }
