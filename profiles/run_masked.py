@@ -81,6 +81,8 @@ report("masked fill (pads -> 0)", t, 4 * d * (s2 + rows) + rows)
 if args.mamamm:
     ext = torch.stack((sizes, sizes, sizes), 1).to(torch.int32).to(dev)
     valid = 4 * d * float(2 * s2 + b * n * n) + b * n * n
-    for algo in (2, 4):
-        t = timeit(lambda i: P.mamamm(Ms[i % NM], False, Ms[(i + 1) % NM], False, mask, ext, algo))
-        report(f"mamamm algo {algo} ext", t, valid)
+    lpt = torch.argsort(sizes, descending=True, stable=True).to(torch.int32).to(dev)
+    for algo, order, name in ((2, None, "tcgen05 tf32 pipeline"), (4, None, "fp32 smem ring, input order"),
+                              (4, lpt, "fp32 smem ring, largest first")):
+        t = timeit(lambda i: P.mamamm(Ms[i % NM], False, Ms[(i + 1) % NM], False, mask, ext, algo, order))
+        report(f"mamamm algo {algo} ({name})", t, valid)

@@ -250,12 +250,12 @@ torch.backends.cuda.matmul.allow_tf32 = True
 full_bytes = 4 * d * b * 3 * n * n + b * n * n
 valid_bytes = 4 * d * float((2 * sizes.double() ** 2).sum() + b * n * n) + b * n * n
 from pygho_b200.backend import mamamm  # noqa: E402
-for algo in (2, 1, 0):
+for algo in (4, 2, 1, 0):
     os.environ["PYGHO_B200_MAMAMM_ALGO"] = str(algo)
     t = timeit(lambda i: mamamm(MT[i % NM], 2, MT[(i + 1) % NM], 1, mask))
     tr = timeit(lambda i: torch.matmul(Ms[i % NM].permute(3, 0, 1, 2), Ms[(i + 1) % NM].permute(3, 0, 1, 2)).permute(1, 2, 3, 0) * mask.unsqueeze(-1), 5)
     flops = 2 * d * float((sizes.double() ** 3).sum())
-    report(f"mamamm algo {algo} ({ {2: 'tcgen05 tf32, persistent pipeline', 1: 'tcgen05 tf32, CTA per item', 0: 'fp32 simt'}[algo] }) b={b} n={n}", t, tr, valid_bytes,
+    report(f"mamamm algo {algo} ({ {4: 'exact fp32, TMA-fed smem ring, largest graph first', 2: 'tcgen05 tf32, persistent pipeline', 1: 'tcgen05 tf32, CTA per item', 0: 'fp32 simt'}[algo] }) b={b} n={n}", t, tr, valid_bytes,
            f"{full_bytes / 1e6:.0f} MB if pads were read; useful {flops / t / 1e6:.1f} TFLOP/s")
 for aggr in ("sum", "max"):
     code = {"sum": 0, "max": 2}[aggr]

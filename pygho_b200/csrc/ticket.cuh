@@ -21,11 +21,41 @@ __device__ inline bool ticketed_combine(const float* part, float* part2, int W, 
   const int g_n = min(grp, blocks - g_lo);
   const int W4 = W >> 2;
   constexpr int kInFlight = 8;
+  if (blocks == 1) {
+    // a single CTA (the graph-level and node-level layers of small batches): its own partial,
+    // no fence, no ticket -- the whole tail is one barrier and one L2 round trip
+    __syncthreads();
+    for (int e = tid; e < W4; e += nt) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part) + e);
+      fin[4 * e] = (double)v.x; fin[4 * e + 1] = (double)v.y; fin[4 * e + 2] = (double)v.z; fin[4 * e + 3] = (double)v.w;
+    }
+    __syncthreads();
+    return true;
+  }
   __threadfence();                       // release: this CTA's partial is visible before its ticket
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(tickets + 1 + g, 1) == g_n - 1);
   __syncthreads();
   if (!s_last) return false;
+  if (ngroups == 1) {
+    // one group: its last CTA is the last CTA -- sum the partials straight into fin
+    for (int e = tid; e < W4; e += nt) {
+      double ax = 0.0, ay = 0.0, az = 0.0, aw = 0.0;
+      const float4* p = reinterpret_cast<const float4*>(part) + e;
+      for (int b0 = 0; b0 < g_n; b0 += kInFlight) {
+        float4 v[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) v[u] = __ldcg(p + (size_t)min(b0 + u, g_n - 1) * W4);
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+          if (b0 + u < g_n) { ax += (double)v[u].x; ay += (double)v[u].y; az += (double)v[u].z; aw += (double)v[u].w; }
+      }
+      fin[4 * e] = ax; fin[4 * e + 1] = ay; fin[4 * e + 2] = az; fin[4 * e + 3] = aw;
+    }
+    if (tid == 0) tickets[1] = 0;
+    __syncthreads();
+    return true;
+  }
   // acquire side: the partials are read with ld.global.cg (L2, never a stale L1 line) after the
   // barrier that follows the ticket -- the pattern of CUDA's threadFenceReduction sample
   for (int e = tid; e < W4; e += nt) {
