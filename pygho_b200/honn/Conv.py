@@ -89,8 +89,12 @@ class SSWLConv(Module):
         plan_ax = P.plan_from_acd(acd2, X.nnz, A.nnz, X.nnz)
         if tap_residual and not xv.is_contiguous():
             tap_residual = False
+        # sum aggregation: both gradient contributions to X in one segmented reduction
+        merged = None
+        if m1.aggr == "sum" and X.nnz and A.nnz and xv.requires_grad and torch.is_grad_enabled():
+            merged = P.sswl_bwd_group(acd1, acd2, m2.precomputekey + KEYSEP + "acd", X.nnz, A.nnz)
         out = SswlAggregate.apply(xv.contiguous(), av.contiguous(), plan_xa, plan_ax,
-                                  0 if m1.aggr == "sum" else 1, tap_residual)
+                                  0 if m1.aggr == "sum" else 1, tap_residual, merged)
         return out if tap_residual else (out, None)
 
 

@@ -998,7 +998,7 @@ class SswlAggregate(torch.autograd.Function):
     X then has a single consumer and autograd needs no separate add pass over all tuples."""
 
     @staticmethod
-    def forward(ctx, Xv, Av, plan_xa, plan_ax, aggr, tap_residual=False):
+    def forward(ctx, Xv, Av, plan_xa, plan_ax, aggr, tap_residual=False, merged_bwd=None):
         n, d = Xv.shape
         cat = torch.empty((n, 3 * d), dtype=torch.float32, device=Xv.device)
         g1, g2 = plan_xa.group("a"), plan_ax.group("a")
@@ -1013,7 +1013,7 @@ class SswlAggregate(torch.autograd.Function):
             _ops.seg_gmr_out(Xv, g1.first, None, Av, g1.second, g1.rowptr, n, aggr, cat[:, d:2 * d], False)
         fork.join()
         ctx.save_for_backward(Xv, Av)
-        ctx.cfg = (plan_xa, plan_ax, aggr)
+        ctx.cfg = (plan_xa, plan_ax, aggr, merged_bwd)
         if tap_residual:
             return cat, Xv.view_as(Xv)
         return cat
@@ -1022,7 +1022,7 @@ class SswlAggregate(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g, g_res=None):
         Xv, Av = ctx.saved_tensors
-        plan_xa, plan_ax, aggr = ctx.cfg
+        plan_xa, plan_ax, aggr, merged = ctx.cfg
         n, d = Xv.shape
         nA = Av.shape[0]
         g0, g1, g2 = g[:, :d], g[:, d:2 * d], g[:, 2 * d:]
@@ -1037,7 +1037,15 @@ class SswlAggregate(torch.autograd.Function):
                 _ops.seg_gmr_out(g1, dd.first, s1, Xv, dd.second, dd.rowptr, nA, 0, gA, False)
                 c = plan_ax.group("c")       # A is operand A of A (x) X
                 _ops.seg_gmr_out(g2, c.first, s2, Xv, c.second, c.rowptr, nA, 0, gA, True)
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and merged is not None and aggr == 0 and n and nA \
+                and g.is_contiguous() and fused_epilogue_ok(d, g, Av, g_res):
+            # gX = g0 + sum over BOTH products' entries (+ residual gradient) in one launch: the
+            # gradient of the concatenation is read as (3 n, d) rows, the merged plan
+            # (plans.sswl_bwd_group) addresses its second and third column slice
+            gX = torch.empty((n, d), dtype=torch.float32, device=g.device)
+            _ops.seg_gmr_fused(g.view(3 * n, d), merged.first, None, Av, merged.second, merged.rowptr,
+                               n, 0, g0, None, None, gX, g_res)
+        elif ctx.needs_input_grad[0]:
             c = plan_xa.group("c")       # X is operand A of X (x) A
             if n and nA and fused_epilogue_ok(d, g, Av, g_res):
                 # gX = g0 + sum(...) (+ residual gradient) in one launch: no clone, no add pass
@@ -1053,7 +1061,7 @@ class SswlAggregate(torch.autograd.Function):
             _ops.seg_gmr_out(g2, dd.first, s2, Av, dd.second, dd.rowptr, n, 0, gX, True)
         if fork is not None:
             fork.join()
-        return gX, gA, None, None, None, None
+        return gX, gA, None, None, None, None, None
 
 
 class EmbeddingGather(torch.autograd.Function):

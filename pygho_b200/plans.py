@@ -293,6 +293,53 @@ def plan_from_acd(acd: Tensor, n_out: int, n_a: int, n_b: int) -> TriplePlan:
     return plan
 
 
+def merge_groups(g1: Group, g2: Group, n_rows: int, stride: int, off1: int, off2: int) -> Group:
+    """Row-wise concatenation of two CSR groupings over the same ``n_rows`` rows: row r of the
+    result holds the entries of ``g1``'s row r followed by those of ``g2``'s row r.  The first
+    index of every entry is remapped to ``stride * first + off`` (the two groupings read
+    different column slices of ONE row-major buffer viewed as (stride * rows, width / stride)).
+    Fixed-shape torch ops only (no size read-back): capacity-padded plans keep their filler
+    entries behind ``rowptr[n_rows]`` of the result."""
+    if g1.rowptr is None or g2.rowptr is None:
+        raise ValueError("merge_groups needs CSR groupings")
+    rp1, rp2 = g1.rowptr.to(torch.int64), g2.rowptr.to(torch.int64)
+    T1, T2 = g1.first.numel(), g2.first.numel()
+    dev = rp1.device
+    t1 = torch.arange(T1, device=dev)
+    t2 = torch.arange(T2, device=dev)
+    r1 = torch.searchsorted(rp1[1:].contiguous(), t1, right=True)        # row of entry t (n_rows: filler)
+    r2 = torch.searchsorted(rp2[1:].contiguous(), t2, right=True)
+    pos1 = t1 + rp2[r1]                                   # entries of g2 in earlier rows
+    pos2 = t2 + rp1[torch.clamp(r2 + 1, max=n_rows)]     # entries of g1 in rows <= r
+    first = torch.zeros((T1 + T2,), dtype=torch.int32, device=dev)
+    second = torch.zeros((T1 + T2,), dtype=torch.int32, device=dev)
+    first[pos1] = g1.first * stride + off1
+    first[pos2] = g2.first * stride + off2
+    second[pos1] = g1.second
+    second[pos2] = g2.second
+    return Group((rp1 + rp2).to(torch.int32), first, second)
+
+
+def sswl_bwd_group(acd_xa: Tensor, acd_ax: Tensor, ax_name: str, nX: int, nA: int) -> Group:
+    """The gradient of an SSWL layer's tuple features in ONE segmented reduction
+    (``ops.SswlAggregate.backward``): for tuple r, the entries of ``X (x) A`` in which r is the
+    first operand followed by the entries of ``A (x) X`` in which r is the second operand.  The
+    first index addresses the gradient of the concatenation ``[X, X(x)A, A(x)X]`` viewed as
+    (3 nX, d) rows: 3 a + 1 / 3 a + 2; the second index is the row of A.  Cached on ``acd_xa``
+    (``ax_name`` = the datadict key of ``acd_ax``: static batches rebuild it by name)."""
+    cache = _cache(acd_xa)
+    key = ("sswl_bwd", ax_name, int(nX), int(nA))
+    hit = cache.get(key)
+    if hit is None:
+        if 3 * int(nX) + 2 >= 2 ** 31:
+            raise ValueError("sswl_bwd_group: too many tuples for int32 row ids")
+        gc = plan_from_acd(acd_xa, nX, nX, nA).group("c")     # first = a, second = d (row of A)
+        gd = plan_from_acd(acd_ax, nX, nA, nX).group("d")     # first = a, second = c (row of A)
+        hit = merge_groups(gc, gd, int(nX), 3, 1, 2)
+        cache[key] = hit
+    return hit
+
+
 def plan_from_key(key: Tensor, n_rows: int, assume_sorted: bool = False) -> TriplePlan:
     """Pooling plan: value row t goes to output row ``key[t]`` (a = key, c = identity);
     its transpose is the un-pooling gather.  Cached on ``key``."""

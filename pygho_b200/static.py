@@ -158,6 +158,8 @@ def _rebuild(dd: dict, t: torch.Tensor, key):
     kind = key[0] if isinstance(key, tuple) else key
     if kind == "acd":
         return P.plan_from_acd(t, *key[1:])
+    if kind == "sswl_bwd":
+        return P.sswl_bwd_group(t, dd[key[1]], key[1], key[2], key[3])
     if kind == "key":
         return P.plan_from_key(t, key[1], key[2])
     if kind == "embedding":

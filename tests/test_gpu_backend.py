@@ -740,6 +740,41 @@ def test_seg_gmr_fused_epilogue_matches_separate_launches(mean):
                           None, None, torch.empty(n_rows, 64, device=DEV))
 
 
+@pytest.mark.parametrize("residual", [False, True])
+def test_sswl_merged_gradient_plan_matches_two_launches(residual):
+    """ops.SswlAggregate.backward with the merged plan (plans.sswl_bwd_group: both products'
+    entries per tuple, the gradient of the concatenation read as (3 n, d) rows, ONE launch)
+    against the two accumulating launches: same gradients within fp32 reassociation."""
+    from pygho_b200 import plans as P
+    from pygho_b200.hodata.device import sp_datadict
+    from pygho_b200.hodata.synthetic import make_batch
+    from pygho_b200.ops import SswlAggregate
+    k1, k2 = "X___X___1___A___0", "X___A___1___X___0"
+    dd = sp_datadict(make_batch(48, seed=5), DEV, [k1, k2])
+    nX, nA, d = dd["X"].nnz, dd["A"].nnz, 128
+    acd1, acd2 = dd[k1 + "___acd"], dd[k2 + "___acd"]
+    plan_xa, plan_ax = P.plan_from_acd(acd1, nX, nX, nA), P.plan_from_acd(acd2, nX, nA, nX)
+    merged = P.sswl_bwd_group(acd1, acd2, k2 + "___acd", nX, nA)
+    assert int(merged.rowptr[-1]) == acd1.shape[1] + acd2.shape[1]
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    Xv0 = torch.randn(nX, d, generator=gen, device=DEV)
+    Av0 = torch.randn(nA, d, generator=gen, device=DEV)
+    w = torch.randn(nX, 3 * d, generator=gen, device=DEV)
+    wr = torch.randn(nX, d, generator=gen, device=DEV)
+    grads = []
+    for m in (None, merged):
+        Xv, Av = Xv0.clone().requires_grad_(True), Av0.clone().requires_grad_(True)
+        out = SswlAggregate.apply(Xv, Av, plan_xa, plan_ax, 0, residual, m)
+        if residual:
+            cat, tap = out
+            ((cat * w).sum() + (tap * wr).sum()).backward()
+        else:
+            (out * w).sum().backward()
+        grads.append((Xv.grad, Av.grad))
+    close(grads[1][0], grads[0][0], 2e-6)
+    assert torch.equal(grads[1][1], grads[0][1])
+
+
 @pytest.mark.parametrize("n,V,D", [(5, 16, 8), (300, 16, 128), (70001, 28, 128), (4097, 3, 32)])
 def test_embedding_matches_torch(n, V, D):
     """pygho_b200.honn.utils.Embedding: forward bit-exact, deterministic weight gradient within
