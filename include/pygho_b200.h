@@ -195,6 +195,18 @@ int pgh_i32_to_i64(const int32_t* src, int64_t n, int64_t* dst, void* stream);
 int pgh_gather_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t* dst, void* stream);
 int pgh_gather_i64_as_i32(const int64_t* src, const int32_t* idx, int64_t n, int32_t* dst,
                           void* stream);
+/* Whole CSR regrouping of a reference-format plan acd (3, T) int64 (the `acd` / `bcd` tensors
+ * of backend/Spspmm.py:57-222) in one call: idx32 (3, T) = a, c, d as int32 and, for every
+ * grouping in `which` (bit 1 = by a over n_out rows, 2 = by c over n_a rows, 4 = by d over n_b
+ * rows): rowptr (rows + 1) and the two other index arrays gathered into that grouping's stable
+ * order (first/second: by a -> (c, d), by c -> (a, d), by d -> (a, c)).  A key equal to the
+ * row count sorts behind rowptr[rows] (filler entries of capacity-padded plans). */
+size_t pgh_acd_regroup_ws_bytes(int64_t T);
+int pgh_acd_regroup(const int64_t* acd, int64_t T, int64_t n_out, int64_t n_a, int64_t n_b,
+                    int which, int32_t* idx32, int32_t* rowptr_a, int32_t* first_a,
+                    int32_t* second_a, int32_t* rowptr_c, int32_t* first_c, int32_t* second_c,
+                    int32_t* rowptr_d, int32_t* first_d, int32_t* second_d, void* ws,
+                    size_t ws_bytes, void* stream);
 /* info[0] += number of descents key[i] > key[i+1] (0 <=> non-decreasing);
  * with strict != 0 equal neighbours count as well (sorted AND duplicate free) */
 int pgh_check_sorted_i64(const int64_t* key, int64_t n, int strict, int32_t* info,

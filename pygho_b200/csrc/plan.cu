@@ -340,6 +340,75 @@ extern "C" int pgh_sort_keys_perm(const int64_t* key_in, int64_t n, int end_bit,
   return check_launch("sort_keys_perm");
 }
 
+// ------------------------------------------------------------------ one-call CSR regrouping
+// Everything plans.TriplePlan needs from a reference-format plan (3, T) int64 in ONE host call:
+// int32 copies of a / c / d and, for each requested grouping (bit 1 = by a, 2 = by c, 4 = by d),
+// rowptr + the two other index arrays in that grouping's (stable) order.  ~14 launches issued from
+// C instead of ~30 Python-level operations per plan: the host side of feeding a batch is
+// launch-overhead bound (profiles/r1_host_profile.txt).
+__global__ void gather2_i32_kernel(const int* __restrict__ s1, const int* __restrict__ s2,
+                                   const int* __restrict__ idx, long long n, int* __restrict__ d1,
+                                   int* __restrict__ d2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int p = idx[i];
+  d1[i] = s1[p];
+  d2[i] = s2[p];
+}
+
+extern "C" size_t pgh_acd_regroup_ws_bytes(int64_t T) {
+  if (T <= 0) return 256;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const unsigned int*)nullptr, (unsigned int*)nullptr,
+                                  (const int*)nullptr, (int*)nullptr, (int)T, 0, 32);
+  return align_up(tmp) + 3 * align_up(sizeof(int) * (size_t)T);
+}
+
+static int bit_length(int64_t v) {
+  int b = 0;
+  while (v > 0) { ++b; v >>= 1; }
+  return b < 1 ? 1 : b;
+}
+
+extern "C" int pgh_acd_regroup(const int64_t* acd, int64_t T, int64_t n_out, int64_t n_a, int64_t n_b,
+                               int which, int32_t* idx32, int32_t* rowptr_a, int32_t* first_a,
+                               int32_t* second_a, int32_t* rowptr_c, int32_t* first_c,
+                               int32_t* second_c, int32_t* rowptr_d, int32_t* first_d,
+                               int32_t* second_d, void* ws, size_t ws_bytes, void* stream) {
+  if (T < 0 || n_out < 0 || n_a < 0 || n_b < 0) return arg_error("acd_regroup: sizes");
+  if (T > 0x7fffffff) return arg_error("acd_regroup: T too large");
+  if (T > 0 && (!acd || !idx32)) return arg_error("acd_regroup: null pointer");
+  cudaStream_t s = as_stream(stream);
+  int32_t* a32 = idx32;
+  int32_t* c32 = idx32 + T;
+  int32_t* d32 = idx32 + 2 * T;
+  if (T > 0) i64_to_i32_kernel<<<blocks_for(3 * T, kT), kT, 0, s>>>((const long long*)acd, 3 * T, idx32, nullptr);
+  const size_t arr = align_up(sizeof(int) * (size_t)(T > 0 ? T : 1));
+  if (ws_bytes < pgh_acd_regroup_ws_bytes(T)) return arg_error("acd_regroup: workspace too small");
+  int* iota = reinterpret_cast<int*>(ws);
+  int* ks = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + arr);
+  int* perm = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + 2 * arr);
+  void* tmp = reinterpret_cast<char*>(ws) + 3 * arr;
+  size_t tmp_bytes = ws_bytes - 3 * arr;
+  if (T > 0 && which) iota_kernel<<<blocks_for(T, kT), kT, 0, s>>>(iota, T);
+  struct G { int bit; const int32_t* key; int64_t n_rows; const int32_t* f; const int32_t* g; int32_t *rp, *fo, *go; };
+  const G groups[3] = {{1, a32, n_out, c32, d32, rowptr_a, first_a, second_a},
+                       {2, c32, n_a, a32, d32, rowptr_c, first_c, second_c},
+                       {4, d32, n_b, a32, c32, rowptr_d, first_d, second_d}};
+  for (const G& g : groups) {
+    if (!(which & g.bit)) continue;
+    if (!g.rp || (T > 0 && (!g.fo || !g.go))) return arg_error("acd_regroup: null output");
+    if (T > 0) {
+      size_t tb = tmp_bytes;
+      PGH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const unsigned int*)g.key, (unsigned int*)ks,
+                                               (const int*)iota, perm, (int)T, 0, bit_length(g.n_rows), s));
+    }
+    rowptr_kernel<<<blocks_for(T + 1, kT), kT, 0, s>>>(ks, T, g.n_rows, g.rp);
+    if (T > 0) gather2_i32_kernel<<<blocks_for(T, kT), kT, 0, s>>>(g.f, g.g, perm, T, g.fo, g.go);
+  }
+  return check_launch("acd_regroup");
+}
+
 extern "C" size_t pgh_unique_ws_bytes(int64_t n) {
   if (n <= 0) return 256;
   size_t tmp = 0;

@@ -105,7 +105,7 @@ def prefetch_plans(datadict: dict, keys: Iterable[str], backward: bool = True,
         _op0, op1, _d1, op2, _d2 = parse_key(key)
         n1 = nA if op1 == "A" else nX
         n2 = nA if op2 == "A" else nX
-        P.plan_from_acd(datadict[key + KEYSEP + "acd"], nX, n1, n2).prefetch(backward)
+        P.plan_from_acd(datadict[key + KEYSEP + "acd"], nX, n1, n2, build_all=backward).prefetch(backward)
     # the merged gradient plan of the SSWL layers (both products' entries per tuple)
     k_xa, k_ax = "X___X___1___A___0" + KEYSEP + "acd", "X___A___1___X___0" + KEYSEP + "acd"
     if backward and k_xa in datadict and k_ax in datadict and nX and nA:

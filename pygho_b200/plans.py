@@ -273,9 +273,13 @@ def _cache(t: Tensor) -> dict:
     return c
 
 
-def plan_from_acd(acd: Tensor, n_out: int, n_a: int, n_b: int) -> TriplePlan:
+def plan_from_acd(acd: Tensor, n_out: int, n_a: int, n_b: int, build_all: bool = False
+                  ) -> TriplePlan:
     """Plan of a reference-format ``acd``/``bcd`` LongTensor (3, T); cached on ``acd``.
-    ``acd[0]`` is not assumed sorted (a stable sort puts it in CSR order either way)."""
+    ``acd[0]`` is not assumed sorted (a stable sort puts it in CSR order either way).
+    ``build_all``: also build the three CSR groupings now, with ONE library call
+    (``pgh_acd_regroup``) instead of ~30 small operations -- what a training step needs anyway
+    (forward: by a, gradients: by c and by d); the batch feeders ask for it."""
     cache = _cache(acd)
     key = ("acd", int(n_out), int(n_a), int(n_b))
     plan = cache.get(key)
@@ -287,9 +291,37 @@ def plan_from_acd(acd: Tensor, n_out: int, n_a: int, n_b: int) -> TriplePlan:
         if _CHECK and acd.numel():
             lim = torch.tensor([[n_out], [n_a], [n_b]], device=acd.device)
             assert bool(((acd >= 0) & (acd < lim)).all()), "acd index out of range"
-        plan = TriplePlan(acd.shape[1], n_out, n_a, n_b, to_i32(acd[0]), to_i32(acd[1]),
-                          to_i32(acd[2]))
+        if build_all and acd.dtype == torch.int64:
+            plan = _regroup_all(acd, int(n_out), int(n_a), int(n_b))
+        else:
+            plan = TriplePlan(acd.shape[1], n_out, n_a, n_b, to_i32(acd[0]), to_i32(acd[1]),
+                              to_i32(acd[2]))
         cache[key] = plan
+    if build_all:
+        plan.prefetch(True)
+    return plan
+
+
+def _regroup_all(acd: Tensor, n_out: int, n_a: int, n_b: int) -> TriplePlan:
+    """TriplePlan of an int64 (3, T) plan with all three groupings, one C-ABI call."""
+    T = acd.shape[1]
+    dev = acd.device
+    idx = torch.empty((3, T), dtype=torch.int32, device=dev)
+    # one allocation for the nine outputs: [rowptr_a | rowptr_c | rowptr_d | 6 x T]
+    sizes = (n_out + 1, n_a + 1, n_b + 1) + (T,) * 6
+    buf = torch.empty((sum(sizes),), dtype=torch.int32, device=dev)
+    parts, off = [], 0
+    for sz in sizes:
+        parts.append(buf[off:off + sz])
+        off += sz
+    rp_a, rp_c, rp_d, f_a, s_a, f_c, s_c, f_d, s_d = parts
+    ws = _ws(size_query("pgh_acd_regroup_ws_bytes", T), dev)
+    _launch("pgh_acd_regroup", ptr(acd), T, n_out, n_a, n_b, 7, ptr(idx), ptr(rp_a), ptr(f_a),
+            ptr(s_a), ptr(rp_c), ptr(f_c), ptr(s_c), ptr(rp_d), ptr(f_d), ptr(s_d), ptr(ws),
+            ws.numel(), stream_ptr(dev))
+    plan = TriplePlan(T, n_out, n_a, n_b, idx[0], idx[1], idx[2])
+    plan._groups = {"a": Group(rp_a, f_a, s_a), "c": Group(rp_c, f_c, s_c),
+                    "d": Group(rp_d, f_d, s_d)}
     return plan
 
 

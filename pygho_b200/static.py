@@ -153,11 +153,13 @@ def _owner_of(dd: dict, indices: torch.Tensor) -> SparseTensor:
                               "SparseTensor of the datadict owns")
 
 
-def _rebuild(dd: dict, t: torch.Tensor, key):
+def _rebuild(dd: dict, t: torch.Tensor, key, template=None):
     """Build, on the new batch's tensor ``t``, the plan the template holds under ``key``."""
     kind = key[0] if isinstance(key, tuple) else key
     if kind == "acd":
-        return P.plan_from_acd(t, *key[1:])
+        # a template that uses all three groupings (training) gets them from one library call
+        every = isinstance(template, P.TriplePlan) and len(template._groups) == 3
+        return P.plan_from_acd(t, *key[1:], build_all=every)
     if kind == "sswl_bwd":
         return P.sswl_bwd_group(t, dd[key[1]], key[1], key[2], key[3])
     if kind == "key":
@@ -193,7 +195,7 @@ class _Mirror:
         cache = getattr(dst, "_pgh_cache", None)
         if cache:
             for key, dobj in cache.items():
-                self.obj(dobj, _rebuild(dd_src, src, key), dd_src)
+                self.obj(dobj, _rebuild(dd_src, src, key, dobj), dd_src)
 
     def obj(self, d, s, dd_src):
         if d is None:

@@ -740,6 +740,26 @@ def test_seg_gmr_fused_epilogue_matches_separate_launches(mean):
                           None, None, torch.empty(n_rows, 64, device=DEV))
 
 
+@pytest.mark.parametrize("T_,with_fillers", [(0, False), (1, False), (5000, False), (5000, True)])
+def test_acd_regroup_one_call_equals_lazy_groupings(T_, with_fillers):
+    """pgh_acd_regroup (all three CSR groupings of a (3, T) plan in one library call) against the
+    grouping-by-grouping path: identical rowptr / index arrays, incl. filler entries whose key
+    equals the row count (capacity-padded plans) and the empty plan."""
+    from pygho_b200 import plans as P
+    gen = torch.Generator().manual_seed(T_ + 7)
+    n_out, n_a, n_b = 301, 97, 1000
+    hi = (n_out + 1, n_a + 1, n_b + 1) if with_fillers else (n_out, n_a, n_b)
+    acd = torch.stack([torch.randint(0, h, (T_,), generator=gen) for h in hi]).to(DEV)
+    lazy = P.plan_from_acd(acd.clone(), n_out, n_a, n_b)
+    fused = P.plan_from_acd(acd.clone(), n_out, n_a, n_b, build_all=True)
+    assert set(fused._groups) == {"a", "c", "d"}
+    for k in "acd":
+        assert torch.equal(fused.idx[k], lazy.idx[k])
+        gl, gf = lazy.group(k), fused.group(k)
+        for x, y in zip(gl, gf):
+            assert x.dtype == y.dtype == torch.int32 and torch.equal(x, y), k
+
+
 @pytest.mark.parametrize("residual", [False, True])
 def test_sswl_merged_gradient_plan_matches_two_launches(residual):
     """ops.SswlAggregate.backward with the merged plan (plans.sswl_bwd_group: both products'
