@@ -384,6 +384,13 @@ int pgh_dense_adj(const int64_t* edge_src, const int64_t* edge_dst, const int64_
                   int64_t n_graphs, int64_t nmax, int64_t width, int elem_bytes, uint64_t fill,
                   void* out, uint8_t* mask, void* stream);
 
+/* n independent device-to-device copies in one launch (host arrays of device pointers and byte
+ * counts; sizes and addresses multiples of 4): a freshly prepared batch -> the static buffers of a
+ * captured training step (the role of `.to(device)` + batch transform of hodata/Wrapper.py:90-98
+ * for graph-replayed steps). */
+int pgh_multi_copy(const void* const* src, void* const* dst, const int64_t* bytes, int n,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -355,3 +355,67 @@ extern "C" int pgh_dense_adj(const int64_t* edge_src, const int64_t* edge_dst,
   }
   return check_launch("dense_adj");
 }
+
+// ------------------------------------------------------------------ batched device copies
+// n independent device -> device copies in ONE launch (the table travels in the kernel
+// parameters): a freshly built batch is moved into the static buffers a captured training step
+// replays on (pygho_b200/static.py mirror_into: ~60 arrays per batch, each its own copy kernel
+// before).  Sizes are multiples of 4 bytes, pointers 4-byte aligned; 16-byte vectors where both
+// sides allow it.
+namespace pgh {
+constexpr int kCopyMax = 64;
+constexpr int kCopyChunk = 16384;       // bytes per CTA
+struct CopyTable {
+  const char* src[kCopyMax];
+  char* dst[kCopyMax];
+  long long bytes[kCopyMax];
+  int first_cta[kCopyMax + 1];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__ CopyTable tab) {
+  int e = 0;
+  while (e + 1 < tab.n && (int)blockIdx.x >= tab.first_cta[e + 1]) ++e;
+  const long long off = (long long)((int)blockIdx.x - tab.first_cta[e]) * kCopyChunk;
+  const long long len = min((long long)kCopyChunk, tab.bytes[e] - off);
+  const char* s = tab.src[e] + off;
+  char* d = tab.dst[e] + off;
+  if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+    const long long n16 = len >> 4;
+    for (long long i = threadIdx.x; i < n16; i += 256)
+      reinterpret_cast<int4*>(d)[i] = reinterpret_cast<const int4*>(s)[i];
+    for (long long i = (n16 << 2) + threadIdx.x; i < (len >> 2); i += 256)
+      reinterpret_cast<int*>(d)[i] = reinterpret_cast<const int*>(s)[i];
+  } else {
+    for (long long i = threadIdx.x; i < (len >> 2); i += 256)
+      reinterpret_cast<int*>(d)[i] = reinterpret_cast<const int*>(s)[i];
+  }
+}
+}  // namespace pgh
+
+extern "C" int pgh_multi_copy(const void* const* src, void* const* dst, const int64_t* bytes, int n,
+                              void* stream) {
+  if (n < 0 || (n > 0 && (!src || !dst || !bytes))) return arg_error("multi_copy: arguments");
+  cudaStream_t s = as_stream(stream);
+  for (int base = 0; base < n; base += pgh::kCopyMax) {
+    pgh::CopyTable tab;
+    int m = 0, ctas = 0;
+    for (int i = base; i < n && m < pgh::kCopyMax; ++i) {
+      if (bytes[i] < 0 || (bytes[i] & 3) || ((reinterpret_cast<uintptr_t>(src[i]) | reinterpret_cast<uintptr_t>(dst[i])) & 3))
+        return arg_error("multi_copy: sizes and pointers must be multiples of 4 bytes");
+      if (bytes[i] == 0) continue;
+      if (!src[i] || !dst[i]) return arg_error("multi_copy: null pointer");
+      tab.src[m] = static_cast<const char*>(src[i]);
+      tab.dst[m] = static_cast<char*>(dst[i]);
+      tab.bytes[m] = bytes[i];
+      tab.first_cta[m] = ctas;
+      ctas += (int)((bytes[i] + pgh::kCopyChunk - 1) / pgh::kCopyChunk);
+      ++m;
+    }
+    if (m == 0) continue;
+    tab.first_cta[m] = ctas;
+    tab.n = m;
+    pgh::multi_copy_kernel<<<ctas, 256, 0, s>>>(tab);
+  }
+  return check_launch("multi_copy");
+}

@@ -28,6 +28,7 @@ size inside the step (3-D pooling to a sparse pattern) is rejected.
 """
 from __future__ import annotations
 
+import os
 import threading
 import time
 from contextlib import contextmanager
@@ -263,6 +264,33 @@ class _Mirror:
         self.pairs = []
 
 
+def _copy_pairs(pairs) -> None:
+    """dst <- src for every pair, stream-ordered: ONE launch of the library's batched copy for
+    the arrays it takes (contiguous, sizes and addresses multiples of 4 bytes), ``copy_`` for
+    the rest (e.g. byte masks of odd length)."""
+    import ctypes as C
+    from . import _lib
+    srcs, dsts, sizes = [], [], []
+    dev = None
+    for dst, src in pairs:
+        nb = dst.numel() * dst.element_size()
+        if (dst.is_cuda and src.is_cuda and dst.device == src.device and dst.is_contiguous()
+                and src.is_contiguous() and nb % 4 == 0 and dst.data_ptr() % 4 == 0
+                and src.data_ptr() % 4 == 0 and (dev is None or dev == dst.device)):
+            dev = dst.device
+            if nb:
+                srcs.append(src.data_ptr())
+                dsts.append(dst.data_ptr())
+                sizes.append(nb)
+        else:
+            dst.copy_(src, non_blocking=True)
+    if srcs:
+        n = len(srcs)
+        _lib.call("pgh_multi_copy", (C.c_void_p * n)(*srcs), (C.c_void_p * n)(*dsts),
+                  (C.c_int64 * n)(*sizes), n, _lib.stream_ptr(dev))
+        _lib.count_launch()
+
+
 def mirror_into(template: dict, fresh: dict) -> int:
     """Copy every device array of ``fresh`` (datadict of a batch padded to the same capacities,
     incl. all cached plans the template has built) over the template's arrays; returns the
@@ -278,8 +306,7 @@ def mirror_into(template: dict, fresh: dict) -> int:
                 m.tensor(d.values, s.values, fresh)
         elif isinstance(d, torch.Tensor):
             m.tensor(d, s, fresh)
-    for dst, src in m.pairs:
-        dst.copy_(src, non_blocking=True)
+    _copy_pairs(m.pairs)
     n = len(m.pairs)
     m.release()
     return n
@@ -380,6 +407,9 @@ class StaticFeeder:
         t0 = time.perf_counter()
         with torch.cuda.stream(self.side):
             self.side.wait_event(self.consumed[slot])      # the slot's last replay is over
+            if os.environ.get("PYGHO_B200_FEEDER_NOLOAD"):  # profiling: replay without feeding
+                self.loaded[slot].record(self.side)
+                return
             fresh = self._sp_datadict(hb, self.device, self.keys, self.pinned)
             self.copies = mirror_into(self.slots[slot], fresh)
             self.loaded[slot].record(self.side)
