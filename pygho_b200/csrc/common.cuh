@@ -43,13 +43,17 @@ constexpr int kSMs = 148;  // B200
 
 extern int g_tune[16];  // run-time tuning knobs (pgh_set_tuning), defined in seg_gmr.cu
 
-// Programmatic dependent launch (key 8, on by default): the grid may be scheduled while its
-// predecessor in the stream is still draining, so that its launch latency and ramp-up hide under
-// the predecessor's tail.  EVERY kernel launched through launch_pdl starts with pdl_enter():
+// Programmatic dependent launch (key 8, on by default): the launch is a programmatic edge of the
+// stream / captured graph instead of a full serialisation, so that its launch latency hides under
+// the predecessor's completion.  EVERY kernel launched through launch_pdl starts with pdl_enter():
 // griddepcontrol.wait returns once the predecessor grids have completed and their writes are
-// visible, i.e. before the kernel's first access to global memory; launch_dependents lets the
-// successor be scheduled as soon as all CTAs of this grid are running.  Kernels of other libraries
-// (cuBLAS, ATen) in between serialise as usual.
+// visible, i.e. before the kernel's first access to global memory.  No kernel triggers its
+// dependents early (the trigger is implicit at grid completion): with griddepcontrol.
+// launch_dependents at the top of every kernel the successor's CTAs sat on the SMs while the
+// predecessor was still running -- a 7.4 us pooling kernel took 10.7 us in back-to-back replays and
+// the training step gained less (128 graphs: 2.691 ms serialised, 2.623 ms early trigger, 2.608 ms
+// implicit trigger; profiles/r2_pdl_trigger_ab.txt; -DPGH_PDL_EARLY_TRIGGER restores it).  Kernels
+// of other libraries (cuBLAS, ATen) in between serialise as usual.
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                        Args&&... args) {
@@ -68,7 +72,9 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_enter() {
+#ifdef PGH_PDL_EARLY_TRIGGER
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 #endif

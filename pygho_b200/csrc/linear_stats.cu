@@ -185,9 +185,11 @@ linear_stats_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   __shared__ double s_fin[2 * kLsBN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (ls_smem_u32(ls_smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B: 1024-B aligned
-  // programmatic dependent launch: barrier set-up and the TMEM allocation below overlap the
-  // predecessor's tail; global memory is first touched after griddepcontrol.wait
+  // programmatic dependent launch (common.cuh): global memory is first touched after the
+  // griddepcontrol.wait that follows the barrier set-up and the TMEM allocation
+#ifdef PGH_PDL_EARLY_TRIGGER
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
   const int m_tiles = (int)((M + kLsBM - 1) / kLsBM);
   const int kblocks = K / kLsBK;
 
