@@ -76,13 +76,14 @@ class SpModel(nn.Module):
 
     def tupleinit(self, X: SparseTensor, x: torch.Tensor) -> SparseTensor:
         # zinc.py:270-276 indexes with X.indices[0] / [1]; use the gather kernel
-        root = X.unpooling_fromdense1dim(0, self.lin_tupleinit0(x)).values
-        node = X.unpooling_fromdense1dim(1, self.lin_tupleinit1(x)).values
         if self.conv_name == "I2GNN":
+            root = X.unpooling_fromdense1dim(0, self.lin_tupleinit0(x)).values
+            node = X.unpooling_fromdense1dim(1, self.lin_tupleinit1(x)).values
             # zinc.py:271-273: the third factor is gathered with X.indices[1] too (kept as is)
             third = X.unpooling_fromdense1dim(1, self.lin_tupleinit2(x)).values
             return X.tuplewiseapply(lambda val: root * node * third * val)
-        return X.tuplewiseapply(lambda val: root * node * val)
+        # root[i] * node[j] * val in one gather-multiply launch + one product (ops.GatherProduct)
+        return X.gather_product(self.lin_tupleinit0(x), self.lin_tupleinit1(x))
 
     def forward(self, datadict: dict) -> torch.Tensor:
         x, A, X = self.encode(datadict)

@@ -180,6 +180,39 @@ class SparseTensor:
             cache[ck] = plan
         return plan
 
+    def _pair_plan(self):
+        """Index arrays of :class:`pygho_b200.ops.GatherProduct` for sparse dims (0, 1): the int32
+        coordinates, and for each of the two dims the CSR over its coordinate together with the
+        tuple ids and the OTHER coordinate in that order.  Cached on the indices."""
+        cache = P._cache(self._indices)
+        hit = cache.get("pairplan")
+        if hit is None:
+            p0, p1 = self._key_plan((0,)), self._key_plan((1,))
+            i32, j32 = p0.idx["a"], p1.idx["a"]
+            g0, g1 = p0.group("a"), p1.group("a")       # first = tuple ids in that order (or None)
+            j_i = j32 if g0.first is None else P.gather_i32(j32, g0.first)
+            i_j = i32 if g1.first is None else P.gather_i32(i32, g1.first)
+            hit = (i32, j32, g0.rowptr, g0.first, j_i, g1.rowptr, g1.first, i_j)
+            cache["pairplan"] = hit
+        return hit
+
+    def gather_product(self, X0: Tensor, X1: Tensor) -> "SparseTensor":
+        """values[t] = X0[indices[0, t]] * X1[indices[1, t]] * values[t] -- what the reference
+        models write as ``X.tuplewiseapply(lambda val: X0[X.indices[0]] * X1[X.indices[1]] * val)``
+        (example/zinc.py:270-276), without materialising the two gathered factors (extension:
+        not in the reference API; 2-D float32 dense features on CUDA, else the generic path)."""
+        v = self._values
+        if (self._sd >= 2 and v is not None and v.ndim == 2 and X0.ndim == 2 and X1.ndim == 2
+                and v.is_cuda and v.dtype == X0.dtype == X1.dtype == torch.float32
+                and X0.shape[1] == X1.shape[1] == v.shape[1] and v.shape[1] % 4 == 0
+                and X0.shape[0] == self._shape[0] and X1.shape[0] == self._shape[1] and self.nnz):
+            from ..ops import GatherProduct
+            return self._same_pattern(GatherProduct.apply(X0.contiguous(), X1.contiguous(),
+                                                          v.contiguous(), self._pair_plan()))
+        root = self.unpooling_fromdense1dim(0, X0).values
+        node = self.unpooling_fromdense1dim(1, X1).values
+        return self._same_pattern(root * node * v)
+
     def _sparse_pool_plan(self, keep: Tuple[int, ...]):
         cache = P._cache(self._indices)
         ck = ("spool", keep)

@@ -169,6 +169,8 @@ def _rebuild(dd: dict, t: torch.Tensor, key, template=None):
         return P.embedding_plan(t, key[1], key[2])
     if kind == "pool":
         return _owner_of(dd, t)._key_plan(key[1])
+    if kind == "pairplan":
+        return _owner_of(dd, t)._pair_plan()
     if kind == "spmm":
         from .backend.Spmm import _spmm_plan
         return _spmm_plan(_owner_of(dd, t), key[1])

@@ -760,6 +760,34 @@ def test_acd_regroup_one_call_equals_lazy_groupings(T_, with_fillers):
             assert x.dtype == y.dtype == torch.int32 and torch.equal(x, y), k
 
 
+def test_gather_product_matches_indexing(B):
+    """SparseTensor.gather_product (ops.GatherProduct: the reference models' tuple initialisation
+    X0[X.indices[0]] * X1[X.indices[1]] * val, example/zinc.py:270-276) against plain torch
+    indexing: values and the gradients of all three factors."""
+    from pygho_b200.hodata.device import sp_datadict
+    from pygho_b200.hodata.synthetic import make_batch
+    dd = sp_datadict(make_batch(24, seed=9), DEV, [])
+    X = dd["X"]
+    n, d = X.shape[0], 32
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    P0 = torch.randn(n, d, generator=gen, device=DEV)
+    Q0 = torch.randn(n, d, generator=gen, device=DEV)
+    V0 = torch.randn(X.nnz, d, generator=gen, device=DEV)
+    w = torch.randn(X.nnz, d, generator=gen, device=DEV)
+    res = []
+    for fused in (False, True):
+        Pm, Qm, Vm = (t.clone().requires_grad_(True) for t in (P0, Q0, V0))
+        Xv = B.SparseTensor(X.indices, Vm, X.shape[:2] + (d,), True)
+        if fused:
+            out = Xv.gather_product(Pm, Qm).values
+        else:
+            out = Pm[X.indices[0]] * Qm[X.indices[1]] * Vm
+        (out * w).sum().backward()
+        res.append((out.detach(), Pm.grad, Qm.grad, Vm.grad))
+    for got, want in zip(res[1], res[0]):
+        close(got, want, 2e-5)
+
+
 @pytest.mark.parametrize("residual", [False, True])
 def test_sswl_merged_gradient_plan_matches_two_launches(residual):
     """ops.SswlAggregate.backward with the merged plan (plans.sswl_bwd_group: both products'
