@@ -727,6 +727,14 @@ def run_b200(args):
         # two full cycles over the host batches: every allocation size of both streams was seen
         e2e_steps(max(args.warmup, 2 * len(hbs) + 1))
         losses.clear()
+        if os.environ.get("PYGHO_B200_PROFILE_LOADER") and static_ok:
+            # launch list of ONE batch load (H2D, plan regrouping, copy into the static slot) for
+            # `ncu --profile-from-start off`: profiles/r2_loader_launches_*.csv
+            torch.cuda.synchronize(device)
+            torch.cuda.profiler.start()
+            feeder._load(feeder.pos + 1)
+            torch.cuda.synchronize(device)
+            torch.cuda.profiler.stop()
         import gc
         gc.collect()
         gc.freeze()    # long-lived objects out of the collector's way: no multi-ms gen-2 pauses
