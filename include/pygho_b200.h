@@ -207,6 +207,15 @@ int pgh_acd_regroup(const int64_t* acd, int64_t T, int64_t n_out, int64_t n_a, i
                     int32_t* second_a, int32_t* rowptr_c, int32_t* first_c, int32_t* second_c,
                     int32_t* rowptr_d, int32_t* first_d, int32_t* second_d, void* ws,
                     size_t ws_bytes, void* stream);
+/* Row-wise concatenation of two CSR groupings over the same n_rows rows (rowptr (n_rows + 1),
+ * first / second (T)): row r of the result = the entries of grouping 1's row r followed by those of
+ * grouping 2's row r, first indices remapped to stride * first + off.  Entries behind
+ * rowptr[n_rows] (fillers of capacity-padded plans) become zeros behind the result's last row. */
+int pgh_merge_groups_i32(const int32_t* rowptr1, const int32_t* first1, const int32_t* second1,
+                         int64_t T1, const int32_t* rowptr2, const int32_t* first2,
+                         const int32_t* second2, int64_t T2, int64_t n_rows, int stride, int off1,
+                         int off2, int32_t* rowptr_out, int32_t* first_out, int32_t* second_out,
+                         void* stream);
 /* info[0] += number of descents key[i] > key[i+1] (0 <=> non-decreasing);
  * with strict != 0 equal neighbours count as well (sorted AND duplicate free) */
 int pgh_check_sorted_i64(const int64_t* key, int64_t n, int strict, int32_t* info,

@@ -334,6 +334,18 @@ def merge_groups(g1: Group, g2: Group, n_rows: int, stride: int, off1: int, off2
     entries behind ``rowptr[n_rows]`` of the result."""
     if g1.rowptr is None or g2.rowptr is None:
         raise ValueError("merge_groups needs CSR groupings")
+    if g1.rowptr.is_cuda and all(t.dtype == torch.int32 for t in (g1.rowptr, g1.first, g1.second,
+                                                                  g2.rowptr, g2.first, g2.second)):
+        # one rowptr kernel + one entry kernel (binary search of the row) instead of ~14 torch ops
+        T1, T2 = g1.first.numel(), g2.first.numel()
+        dev = g1.rowptr.device
+        rp = _empty(n_rows + 1, torch.int32, dev)
+        first, second = _empty(T1 + T2, torch.int32, dev), _empty(T1 + T2, torch.int32, dev)
+        _launch("pgh_merge_groups_i32", ptr(g1.rowptr.contiguous()), ptr(g1.first.contiguous()),
+                ptr(g1.second.contiguous()), T1, ptr(g2.rowptr.contiguous()), ptr(g2.first.contiguous()),
+                ptr(g2.second.contiguous()), T2, int(n_rows), int(stride), int(off1), int(off2),
+                ptr(rp), ptr(first), ptr(second), stream_ptr(dev))
+        return Group(rp, first, second)
     rp1, rp2 = g1.rowptr.to(torch.int64), g2.rowptr.to(torch.int64)
     T1, T2 = g1.first.numel(), g2.first.numel()
     dev = rp1.device

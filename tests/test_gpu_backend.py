@@ -788,6 +788,28 @@ def test_gather_product_matches_indexing(B):
         close(got, want, 2e-5)
 
 
+def test_merge_groups_kernel_equals_torch_version():
+    """pgh_merge_groups_i32 (CUDA groupings) against the fixed-shape torch version of
+    plans.merge_groups (CPU groupings, tests/test_merge_groups_cpu.py), with filler entries."""
+    from pygho_b200 import plans as P
+    try:
+        from test_merge_groups_cpu import _group
+    except ImportError:
+        from tests.test_merge_groups_cpu import _group
+    rng = np.random.default_rng(5)
+    for n_rows, T1, cap1, T2, cap2 in ((7, 20, 20, 13, 13), (50, 300, 340, 0, 5), (9, 0, 0, 4, 4),
+                                       (3000, 20000, 20480, 17000, 17000)):
+        g1, _ = _group(rng, n_rows, T1, cap1, 400, 110)
+        g2, _ = _group(rng, n_rows, T2, cap2, 400, 110)
+        want = P.merge_groups(g1, g2, n_rows, 3, 1, 2)
+        got = P.merge_groups(P.Group(*(t.to(DEV) for t in g1)), P.Group(*(t.to(DEV) for t in g2)),
+                             n_rows, 3, 1, 2)
+        assert torch.equal(got.rowptr.cpu(), want.rowptr)
+        real = int(want.rowptr[-1])
+        assert torch.equal(got.first.cpu()[:real], want.first[:real])
+        assert torch.equal(got.second.cpu()[:real], want.second[:real])
+
+
 @pytest.mark.parametrize("residual", [False, True])
 def test_sswl_merged_gradient_plan_matches_two_launches(residual):
     """ops.SswlAggregate.backward with the merged plan (plans.sswl_bwd_group: both products'
