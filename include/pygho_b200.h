@@ -207,6 +207,15 @@ int pgh_acd_regroup(const int64_t* acd, int64_t T, int64_t n_out, int64_t n_a, i
                     int32_t* second_a, int32_t* rowptr_c, int32_t* first_c, int32_t* second_c,
                     int32_t* rowptr_d, int32_t* first_d, int32_t* second_d, void* ws,
                     size_t ws_bytes, void* stream);
+/* Index structures of one embedding lookup (the encoders of the reference models,
+ * example/zinc.py:233-239) in one call: idx32 (n), perm (n) = stable sort of the positions by index
+ * value, levels = the row pointers of the deterministic reduction tree of the weight gradient,
+ * concatenated: while size > max(2 V, 4 chunk): an array of V + ceil(size / chunk) + 1 entries
+ * (size = its row count afterwards), then one of V + 1.  bounds_ws: 2 (V + 1) ints of scratch. */
+size_t pgh_embedding_plan_ws_bytes(int64_t n);
+int pgh_embedding_plan(const void* idx, int idx_is_i64, int64_t n, int64_t V, int64_t chunk,
+                       int32_t* idx32, int32_t* perm, int32_t* levels, int64_t levels_len,
+                       int32_t* bounds_ws, void* ws, size_t ws_bytes, void* stream);
 /* Row-wise concatenation of two CSR groupings over the same n_rows rows (rowptr (n_rows + 1),
  * first / second (T)): row r of the result = the entries of grouping 1's row r followed by those of
  * grouping 2's row r, first indices remapped to stride * first + off.  Entries behind

@@ -42,6 +42,8 @@ SIGNATURES = {
     "pgh_unpack_tight": (_i, [_p, _i64, _p, _i, _p, _i64, _p]),
     "pgh_multi_copy": (_i, [_p, _p, _p, _i, _p]),
     "pgh_merge_groups_i32": (_i, [_p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i, _i, _i, _p, _p, _p, _p]),
+    "pgh_embedding_plan_ws_bytes": (_sz, [_i64]),
+    "pgh_embedding_plan": (_i, [_p, _i, _i64, _i64, _i64, _p, _p, _p, _i64, _p, _p, _sz, _p]),
     "pgh_acd_regroup_ws_bytes": (_sz, [_i64]),
     "pgh_acd_regroup": (_i, [_p, _i64, _i64, _i64, _i64, _i, _p] + [_p] * 9 + [_p, _sz, _p]),
     "pgh_sort_ws_bytes": (_sz, [_i64]),

@@ -489,6 +489,99 @@ extern "C" int pgh_acd_regroup(const int64_t* acd, int64_t T, int64_t n_out, int
   return check_launch("acd_regroup");
 }
 
+// ------------------------------------------------------------------ embedding plan in one call
+// plans.EmbeddingPlan: idx32, the stable sort of the positions by index value, and the row
+// pointers of the reduction tree (all shapes static: V + ceil(size / chunk) rows per level).  One
+// 32-bit radix sort and one small kernel per level instead of ~35 torch operations per table.
+template <typename T>
+__global__ void emb_convert_kernel(const T* __restrict__ idx, long long n, int* __restrict__ idx32,
+                                   int* __restrict__ iota) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  idx32[i] = (int)idx[i];
+  iota[i] = (int)i;
+}
+
+// One level of the tree.  bounds (V + 1, non-decreasing, bounds[V] = size): where each index value's
+// range starts in the current level.  level (rows + 1) = sorted union of bounds[0..V) and the cuts
+// 0, chunk, 2 chunk, ... (< size), then size; next (V + 1) = position of each value's first row.
+__global__ void emb_level_kernel(const int* __restrict__ bounds, int V, int size, int chunk,
+                                 int* __restrict__ level, int* __restrict__ next) {
+  const int n_cuts = (size + chunk - 1) / chunk;
+  const int rows = V + n_cuts;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { level[rows] = bounds[V]; next[V] = rows; }
+  if (i < V) {
+    const int b = bounds[i];
+    const int below_cuts = min(n_cuts, (b + chunk - 1) / chunk);        // cuts < b
+    level[i + below_cuts] = b;                     // ties among equal values: any order, same content
+    int lo = 0, hi = i;                            // first u with bounds[u] == b
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (bounds[mid] < b) lo = mid + 1; else hi = mid;
+    }
+    next[i] = lo + below_cuts;
+  } else if (i < rows) {
+    const int j = i - V, cut = j * chunk;
+    int lo = 0, hi = V;                            // number of bounds[0..V) <= cut
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (bounds[mid] <= cut) lo = mid + 1; else hi = mid;
+    }
+    level[j + lo] = cut;
+  }
+}
+
+extern "C" size_t pgh_embedding_plan_ws_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const unsigned int*)nullptr, (unsigned int*)nullptr,
+                                  (const int*)nullptr, (int*)nullptr, (int)n, 0, 32);
+  return align_up(tmp) + 2 * align_up(sizeof(int) * (size_t)n) + align_up(sizeof(int) * 2);
+}
+
+// levels: concatenation of the level arrays (sizes as computed by the caller with the same rule:
+// while size > max(2 V, 4 chunk): rows = V + ceil(size / chunk), array of rows + 1; then V + 1);
+// bounds_ws: 2 * (V + 1) ints of scratch.
+extern "C" int pgh_embedding_plan(const void* idx, int idx_is_i64, int64_t n, int64_t V, int64_t chunk,
+                                  int32_t* idx32, int32_t* perm, int32_t* levels, int64_t levels_len,
+                                  int32_t* bounds_ws, void* ws, size_t ws_bytes, void* stream) {
+  if (!idx || !idx32 || !perm || !levels || !bounds_ws || !ws) return arg_error("embedding_plan: null pointer");
+  if (n <= 0 || n > 0x7fffffff || V <= 0 || V > (1 << 24) || chunk < 2 || chunk > (1 << 20))
+    return arg_error("embedding_plan: sizes");
+  if (ws_bytes < pgh_embedding_plan_ws_bytes(n)) return arg_error("embedding_plan: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  const size_t arr = align_up(sizeof(int) * (size_t)n);
+  char* p = static_cast<char*>(ws);
+  int* iota = reinterpret_cast<int*>(p);
+  int* ks = reinterpret_cast<int*>(p + arr);
+  void* tmp = p + 2 * arr;
+  size_t tb = ws_bytes - 2 * arr;
+  if (idx_is_i64)
+    emb_convert_kernel<long long><<<blocks_for(n, kT), kT, 0, s>>>((const long long*)idx, n, idx32, iota);
+  else
+    emb_convert_kernel<int><<<blocks_for(n, kT), kT, 0, s>>>((const int*)idx, n, idx32, iota);
+  PGH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, (const unsigned int*)idx32, (unsigned int*)ks,
+                                           (const int*)iota, perm, (int)n, 0, bit_length(V), s));
+  int* bounds = bounds_ws;
+  int* next = bounds_ws + (V + 1);
+  rowptr_kernel<<<blocks_for(n + 1, kT), kT, 0, s>>>(ks, n, V, bounds);
+  int64_t size = n, off = 0;
+  const int64_t stop = (2 * V > 4 * chunk) ? 2 * V : 4 * chunk;
+  while (size > stop) {
+    const int64_t rows = V + (size + chunk - 1) / chunk;
+    if (off + rows + 1 > levels_len) return arg_error("embedding_plan: levels buffer too small");
+    emb_level_kernel<<<blocks_for(rows, kT), kT, 0, s>>>(bounds, (int)V, (int)size, (int)chunk,
+                                                        levels + off, next);
+    off += rows + 1;
+    size = rows;
+    int* t = bounds; bounds = next; next = t;
+  }
+  if (off + V + 1 > levels_len) return arg_error("embedding_plan: levels buffer too small");
+  PGH_CUDA(cudaMemcpyAsync(levels + off, bounds, sizeof(int) * (size_t)(V + 1), cudaMemcpyDeviceToDevice, s));
+  return check_launch("embedding_plan");
+}
+
 // ------------------------------------------------------------------ row-wise merge of two CSRs
 // Row r of the result = the entries of g1's row r followed by those of g2's row r; first indices
 // are remapped to stride * first + off (plans.merge_groups: the one-launch SSWL gradient).  Filler

@@ -618,6 +618,29 @@ def embedding_plan(idx: Tensor, num_embeddings: int, chunk: int = 64) -> Embeddi
     dev = _lib.require_cuda(idx)
     flat = idx.reshape(-1)
     n, V = flat.numel(), int(num_embeddings)
+    if n and flat.dtype in (torch.int64, torch.int32) and V < (1 << 24):
+        # one library call: a 32-bit radix sort + one small kernel per level of the tree
+        flat = flat.contiguous()
+        sizes, size = [], n
+        while size > max(2 * V, 4 * chunk):
+            size = V + (size + chunk - 1) // chunk
+            sizes.append(size + 1)
+        sizes.append(V + 1)
+        idx32 = _empty(n, torch.int32, dev)
+        perm = _empty(n, torch.int32, dev)
+        lv = _empty(sum(sizes), torch.int32, dev)
+        bws = _empty(2 * (V + 1), torch.int32, dev)
+        ws = _ws(size_query("pgh_embedding_plan_ws_bytes", n), dev)
+        _launch("pgh_embedding_plan", ptr(flat), int(flat.dtype == torch.int64), n, V, int(chunk),
+                ptr(idx32), ptr(perm), ptr(lv), lv.numel(), ptr(bws), ptr(ws), ws.numel(),
+                stream_ptr(dev))
+        levels, off = [], 0
+        for sz in sizes:
+            levels.append(lv[off:off + sz])
+            off += sz
+        plan = EmbeddingPlan(idx32, perm, tuple(levels), V)
+        cache[ck] = plan
+        return plan
     idx32 = to_i32(flat)
     rowptr_id, perm = csr_of(idx32, V)                 # positions grouped by index value
     if perm is None:
