@@ -152,6 +152,9 @@ int pgh_unpack_tight(const int64_t* key, int64_t n, const int64_t* dims_host, in
 size_t pgh_sort_ws_bytes(int64_t n);
 int pgh_sort_keys_perm(const int64_t* key_in, int64_t n, int end_bit, int64_t* key_out,
                        int32_t* perm_out, void* ws, size_t ws_bytes, void* stream);
+/* the same for int32 keys (row ids: what the CSR builders sort); workspace pgh_sort_ws_bytes(n) */
+int pgh_sort_i32_perm(const int32_t* key_in, int64_t n, int end_bit, int32_t* key_out,
+                      int32_t* perm_out, void* ws, size_t ws_bytes, void* stream);
 
 /* run-length unique of sorted keys: ukey[0..count), seg[i] = index of key[i]'s run,
  * count written to *count_dev (torch.unique(sorted, return_inverse), Spspmm.py:135) */

@@ -48,6 +48,7 @@ SIGNATURES = {
     "pgh_acd_regroup": (_i, [_p, _i64, _i64, _i64, _i64, _i, _p] + [_p] * 9 + [_p, _sz, _p]),
     "pgh_sort_ws_bytes": (_sz, [_i64]),
     "pgh_sort_keys_perm": (_i, [_p, _i64, _i, _p, _p, _p, _sz, _p]),
+    "pgh_sort_i32_perm": (_i, [_p, _i64, _i, _p, _p, _p, _sz, _p]),
     "pgh_unique_ws_bytes": (_sz, [_i64]),
     "pgh_unique_sorted": (_i, [_p, _i64, _p, _p, _p, _p, _sz, _p]),
     "pgh_rowptr_from_sorted": (_i, [_p, _i64, _i64, _p, _p]),

@@ -642,6 +642,28 @@ extern "C" int pgh_merge_groups_i32(const int32_t* rowptr1, const int32_t* first
   return check_launch("merge_groups");
 }
 
+// 32-bit keys: what every CSR builder sorts (row ids) -- half the key traffic of the 64-bit entry
+// point and no conversion kernels around it.  Workspace: pgh_sort_ws_bytes(n).
+extern "C" int pgh_sort_i32_perm(const int32_t* key_in, int64_t n, int end_bit, int32_t* key_out,
+                                 int32_t* perm_out, void* ws, size_t ws_bytes, void* stream) {
+  if (n <= 0) return 0;
+  if (n > 0x7fffffff) return arg_error("sort: n too large");
+  if (!key_in || !key_out || !perm_out || !ws) return arg_error("sort: null pointer");
+  if (end_bit < 1) end_bit = 1;
+  if (end_bit > 32) end_bit = 32;
+  cudaStream_t s = as_stream(stream);
+  const size_t iota_bytes = align_up(sizeof(int) * (size_t)n);
+  if (ws_bytes < iota_bytes + 256) return arg_error("sort: workspace too small");
+  int* iota = reinterpret_cast<int*>(ws);
+  void* tmp = reinterpret_cast<char*>(ws) + iota_bytes;
+  size_t tmp_bytes = ws_bytes - iota_bytes;
+  iota_kernel<<<blocks_for(n, kT), kT, 0, s>>>(iota, n);
+  PGH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const unsigned int*)key_in,
+                                           (unsigned int*)key_out, (const int*)iota, (int*)perm_out,
+                                           (int)n, 0, end_bit, s));
+  return check_launch("sort_i32_perm");
+}
+
 extern "C" size_t pgh_unique_ws_bytes(int64_t n) {
   if (n <= 0) return 256;
   size_t tmp = 0;

@@ -126,8 +126,13 @@ def csr_of(key32: Tensor, n_rows: int, assume_sorted: bool = False
     are never visited (filler entries of capacity-padded plans, pygho_b200/static.py)."""
     if assume_sorted or key32.numel() == 0:
         return rowptr_from_sorted(key32, n_rows), None
-    ks, perm = sort_keys(to_i64(key32), max(1, int(n_rows).bit_length()))
-    return rowptr_from_sorted(to_i32(ks), n_rows), perm
+    n, dev = key32.numel(), key32.device
+    key32 = key32.contiguous()
+    ks, perm = _empty(n, torch.int32, dev), _empty(n, torch.int32, dev)
+    ws = _ws(size_query("pgh_sort_ws_bytes", n), dev)
+    _launch("pgh_sort_i32_perm", ptr(key32), n, max(1, int(n_rows).bit_length()), ptr(ks), ptr(perm),
+            ptr(ws), ws.numel(), stream_ptr(dev))
+    return rowptr_from_sorted(ks, n_rows), perm
 
 
 def _take(x: Optional[Tensor], perm: Optional[Tensor]) -> Optional[Tensor]:
